@@ -21,6 +21,7 @@ The arithmetic restated here follows gpytorch 0.3.x definitions:
   * MultivariateNormal.log_prob: dense Cholesky with psd-safe jitter escalation
 """
 import copy
+import importlib.machinery
 import math
 import sys
 import types
@@ -240,6 +241,9 @@ def _sq_dist(x1, x2, x1_eq_x2=False):
     x2 = x2 - adjustment
     x1_norm = x1.pow(2).sum(dim=-1, keepdim=True)
     x1_pad = torch.ones_like(x1_norm)
+    # gpytorch only takes the x1==x2 shortcut when no input gradient is required; without that guard the
+    # reference's GradientGP Hessians at x == x' (gp_algebra.py:352-393) would vanish.
+    x1_eq_x2 = x1_eq_x2 and not x1.requires_grad and not x2.requires_grad
     if x1_eq_x2:
         x2_norm, x2_pad = x1_norm, x1_pad
     else:
@@ -492,6 +496,22 @@ def cached(*a, **k):
 
 
 # ----------------------------------------------------------------------------- install
+class _MockModule(types.ModuleType):
+    """Importable stand-in for an absent package: every attribute is a MagicMock."""
+
+    def __init__(self, name):
+        super().__init__(name)
+        self.__path__ = []
+        self.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=True)
+
+    def __getattr__(self, item):
+        if item.startswith('__') and item.endswith('__'):
+            raise AttributeError(item)
+        val = mock.MagicMock(name=self.__name__ + '.' + item)
+        setattr(self, item, val)
+        return val
+
+
 def _mod(name, **attrs):
     m = types.ModuleType(name)
     for k, v in attrs.items():
@@ -528,21 +548,15 @@ def install(reference_root='/root/reference'):
     g = _mod('gpytorch', settings=settings, lazy=lazy, kernels=kernels, means=means, distributions=dists,
              likelihoods=likelihoods, models=models, mlls=mlls, priors=priors, utils=utils)
     g._bcbf_shim = True
-    # matplotlib / kwplus / misc absent packages -> MagicMock modules
+    # matplotlib / kwplus / other absent packages -> permissive mock modules
     for name in ['matplotlib', 'matplotlib.pyplot', 'matplotlib.transforms', 'matplotlib.patches',
                  'matplotlib.colors', 'matplotlib.cm', 'matplotlib.ticker', 'matplotlib.animation',
-                 'matplotlib.lines', 'mpl_toolkits', 'mpl_toolkits.mplot3d']:
+                 'matplotlib.lines', 'matplotlib.axes', 'matplotlib.collections', 'matplotlib.gridspec',
+                 'matplotlib.figure', 'mpl_toolkits', 'mpl_toolkits.mplot3d', 'kwplus', 'kwplus.functools',
+                 'kwplus.variations', 'cvxopt', 'cvxpy', 'bdlqr', 'bdlqr.full', 'mpc', 'mpc.mpc']:
         if name not in sys.modules:
-            m = mock.MagicMock(name=name)
-            m.__path__ = []
-            sys.modules[name] = m
-    sys.modules['matplotlib.pyplot'].subplots.return_value = (mock.MagicMock(), mock.MagicMock())
-    if 'kwplus' not in sys.modules:
-        kw = mock.MagicMock(name='kwplus')
-        kw.__path__ = []
-        for sub in ['kwplus.functools', 'kwplus.variations']:
-            sys.modules[sub] = kw
-        sys.modules['kwplus'] = kw
+            sys.modules[name] = _MockModule(name)
+    sys.modules['matplotlib.pyplot'].subplots = mock.MagicMock(return_value=(mock.MagicMock(), mock.MagicMock()))
     # removed torch APIs still used by the reference (gp_algebra.py:385,389)
     if not getattr(torch, '_bcbf_eig_compat', False):
         def _eig(A, eigenvectors=False):
