@@ -1,0 +1,434 @@
+// C-ABI glue: error reporting, CBC epilogue kernel and the host-pointer model handle (include/bcbf.h).
+#include "../../include/bcbf.h"
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+namespace bcbf {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_last_error("CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+  return BCBF_ERR_CUDA;
+}
+
+// ---- relative-degree-1 CBC terms, one thread per constraint --------------------------------------------
+__global__ void cbc1_terms_kernel(const double* __restrict__ Mk, const double* __restrict__ Bk,
+                                  const double* __restrict__ Amat, const double* __restrict__ grad_h,
+                                  const double* __restrict__ h, const double* __restrict__ Fbar, double gamma, int n,
+                                  int p, int Q, double* __restrict__ bfe, double* __restrict__ e,
+                                  double* __restrict__ Asq, double* __restrict__ A_socp, double* __restrict__ bfb,
+                                  int* __restrict__ status) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int m = p - 1;
+  double gh[BCBF_MAX_N_DIM];
+  for (int r = 0; r < n; ++r) gh[r] = grad_h[(long long)q * n + r];
+  // affine (mean) terms
+  for (int j = 0; j < p; ++j) {
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) {
+      double f = Mk[((long long)q * n + r) * p + j];
+      if (Fbar) f += Fbar[((long long)q * n + r) * p + j];
+      s = fma(gh[r], f, s);
+    }
+    if (j == 0) e[q] = s + gamma * h[q];
+    else bfe[(long long)q * m + (j - 1)] = s;
+  }
+  // quadratic (variance) terms: Asq = (gh^T A gh) * B_k
+  double sA = 0.0;
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c) sA = fma(gh[r] * Amat[r * n + c], gh[c], sA);
+  double M[BCBF_MAX_P_DIM][BCBF_MAX_P_DIM], Ls[BCBF_MAX_P_DIM][BCBF_MAX_P_DIM];
+  for (int i = 0; i < p; ++i)
+    for (int j = 0; j < p; ++j) {
+      M[i][j] = sA * Bk[((long long)q * p + i) * p + j];
+      Ls[i][j] = 0.0;
+      if (Asq) Asq[((long long)q * p + i) * p + j] = M[i][j];
+    }
+  int st = 0;
+  for (int j = 0; j < p; ++j) {
+    double d = M[j][j];
+    for (int k = 0; k < j; ++k) d -= Ls[j][k] * Ls[j][k];
+    if (!(d > 0.0)) {
+      if (st == 0) st = j + 1;
+      d = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    d = sqrt(d);
+    Ls[j][j] = d;
+    for (int i = j + 1; i < p; ++i) {
+      double s = M[i][j];
+      for (int k = 0; k < j; ++k) s -= Ls[i][k] * Ls[j][k];
+      Ls[i][j] = s / d;
+    }
+  }
+  if (status) status[q] = st;
+  // A_socp = Ls^T[:, 1:]  (p, m);  bfb = Ls^T[:, 0]  (p)
+  for (int i = 0; i < p; ++i) {
+    if (bfb) bfb[(long long)q * p + i] = Ls[0][i];
+    if (A_socp)
+      for (int c = 0; c < m; ++c) A_socp[((long long)q * p + i) * m + c] = Ls[c + 1][i];
+  }
+}
+
+// ---- model-handle helper kernels -----------------------------------------------------------------------
+__global__ void prep_train_kernel(const double* __restrict__ U, const double* __restrict__ Xdot, int N, int Npad, int n,
+                                  int p, const double* __restrict__ Bm, const double* __restrict__ C,
+                                  double* __restrict__ UH, double* __restrict__ G, double* __restrict__ Y, int ldy) {
+  // UH = [1 | U] (N,p); G = UH B (Npad,p; pad rows 0); Y = Xdot - UH C (Npad, ldy; pad 0)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  const int m = p - 1;
+  double uh[BCBF_MAX_P_DIM];
+  if (i < N) {
+    uh[0] = 1.0;
+    for (int j = 0; j < m; ++j) uh[j + 1] = U[(long long)i * m + j];
+    for (int j = 0; j < p; ++j) UH[(long long)i * p + j] = uh[j];
+  }
+  for (int j = 0; j < p; ++j) {
+    double g = 0.0;
+    if (i < N)
+      for (int t = 0; t < p; ++t) g = fma(uh[t], Bm[t * p + j], g);
+    G[(long long)i * p + j] = g;
+  }
+  for (int r = 0; r < ldy; ++r) {
+    double y = 0.0;
+    if (i < N && r < n) {
+      y = Xdot[(long long)i * n + r];
+      for (int t = 0; t < p; ++t) y -= uh[t] * C[t * n + r];
+    }
+    Y[(long long)i * ldy + r] = y;
+  }
+}
+
+__global__ void build_w_kernel(const double* __restrict__ alpha, int lda, const double* __restrict__ G, int Npad,
+                               int n, int p, double* __restrict__ W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  for (int r = 0; r < n; ++r)
+    for (int j = 0; j < p; ++j) W[((long long)i * n + r) * p + j] = alpha[(long long)i * lda + r] * G[(long long)i * p + j];
+}
+
+__global__ void build_uh_kernel(const double* __restrict__ U, int Q, int p, double* __restrict__ UH) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q) return;
+  UH[(long long)i * p] = 1.0;
+  for (int j = 1; j < p; ++j) UH[(long long)i * p + j] = U ? U[(long long)i * (p - 1) + (j - 1)] : 0.0;
+}
+
+}  // namespace bcbf
+
+using namespace bcbf;
+
+extern "C" const char* bcbf_last_error(void) { return g_err; }
+extern "C" int bcbf_version(void) { return 100; }
+extern "C" int bcbf_padded(int N) { return ((N + kBlk - 1) / kBlk) * kBlk; }
+
+extern "C" int bcbf_cbc1_terms(const double* Mk, const double* Bk, const double* Amat, const double* grad_h,
+                               const double* h, const double* Fbar, double gamma, int n, int p, int Q, double* bfe,
+                               double* e, double* Asq, double* A_socp, double* bfb, int* status, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(Mk && Bk && Amat && grad_h && h && bfe && e, "bcbf_cbc1_terms: null pointer");
+  BCBF_REQUIRE(n >= 1 && n <= BCBF_MAX_N_DIM && p >= 2 && p <= BCBF_MAX_P_DIM && Q >= 1, "bcbf_cbc1_terms: n=%d p=%d Q=%d",
+               n, p, Q);
+  cbc1_terms_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(Mk, Bk, Amat, grad_h, h, Fbar, gamma, n, p, Q, bfe, e, Asq,
+                                                          A_socp, bfb, status);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+// ======================================================================================================
+// Model handle
+// ======================================================================================================
+struct bcbf_model {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bcbf_hyper hyp{};
+  int N = 0, Npad = 0;
+  bool fitted = false;
+  // fitted state (device)
+  double *X = nullptr, *UH = nullptr, *L = nullptr, *Linv = nullptr, *dinv = nullptr, *alpha = nullptr, *G = nullptr,
+         *W = nullptr, *Y = nullptr, *hyp_dev = nullptr;
+  int* info = nullptr;
+  size_t cap_N = 0;  // capacity (Npad) of the factor-sized buffers
+  // query scratch (device), grown on demand
+  double *Xq = nullptr, *Uq = nullptr, *UHq = nullptr, *Kstar = nullptr, *Mk = nullptr, *Bk = nullptr, *mean = nullptr,
+         *svar = nullptr;
+  size_t cap_Q = 0, cap_K = 0;
+  double fit_ms[5] = {0, 0, 0, 0, 0};
+};
+
+namespace {
+constexpr int kLdY = 4;  // alpha / Y leading dimension (>= n, even) when n <= 4; generalised below
+
+int ld_y(int n) { return (n + 1) / 2 * 2; }
+
+template <class T>
+int dev_alloc(T** p, size_t count) {
+  if (*p) { BCBF_CUDA(cudaFree(*p)); *p = nullptr; }
+  if (count == 0) return BCBF_OK;
+  BCBF_CUDA(cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * count));
+  return BCBF_OK;
+}
+
+int query_batch(int p) {
+  // queries per device batch: 4 waves of one CTA per SM (148 SMs) with the posterior kernel's TQ
+  const int tq = (p == 1) ? 96 : (p == 2 ? 48 : 32);
+  return 148 * tq * 4;
+}
+}  // namespace
+
+extern "C" int bcbf_model_create(bcbf_model** out, int device) {
+  BCBF_REQUIRE(out, "bcbf_model_create: null out");
+  BCBF_CUDA(cudaSetDevice(device));
+  bcbf_model* m = new (std::nothrow) bcbf_model();
+  BCBF_REQUIRE(m, "bcbf_model_create: out of host memory");
+  m->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+  *out = m;
+  return BCBF_OK;
+}
+
+extern "C" void bcbf_model_destroy(bcbf_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  double** bufs[] = {&m->X, &m->UH, &m->L, &m->Linv, &m->dinv, &m->alpha, &m->G, &m->W, &m->Y, &m->hyp_dev,
+                     &m->Xq, &m->Uq, &m->UHq, &m->Kstar, &m->Mk, &m->Bk, &m->mean, &m->svar};
+  for (double** b : bufs)
+    if (*b) cudaFree(*b);
+  if (m->info) cudaFree(m->info);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+extern "C" int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int N) {
+  BCBF_REQUIRE(m && hyp, "bcbf_model_alloc_state: null pointer");
+  BCBF_REQUIRE(N >= 1 && hyp->n >= 1 && hyp->n <= BCBF_MAX_N_DIM && hyp->p >= 1 && hyp->p <= BCBF_MAX_P_DIM,
+               "bcbf_model_alloc_state: N=%d n=%d p=%d", N, hyp->n, hyp->p);
+  BCBF_CUDA(cudaSetDevice(m->device));
+  m->hyp = *hyp;
+  const int Npad = bcbf_padded(N), n = hyp->n, p = hyp->p;
+  if ((size_t)Npad > m->cap_N) {
+    int rc;
+    if ((rc = dev_alloc(&m->L, (size_t)Npad * Npad))) return rc;
+    if ((rc = dev_alloc(&m->Linv, (size_t)Npad * Npad))) return rc;
+    if ((rc = dev_alloc(&m->dinv, (size_t)bcbf_dinv_elems(Npad)))) return rc;
+    if ((rc = dev_alloc(&m->X, (size_t)Npad * BCBF_MAX_N_DIM))) return rc;
+    if ((rc = dev_alloc(&m->UH, (size_t)Npad * BCBF_MAX_P_DIM))) return rc;
+    if ((rc = dev_alloc(&m->G, (size_t)Npad * BCBF_MAX_P_DIM))) return rc;
+    if ((rc = dev_alloc(&m->alpha, (size_t)Npad * BCBF_MAX_N_DIM))) return rc;
+    if ((rc = dev_alloc(&m->Y, (size_t)Npad * BCBF_MAX_N_DIM * 2))) return rc;
+    if ((rc = dev_alloc(&m->W, (size_t)Npad * BCBF_MAX_N_DIM * BCBF_MAX_P_DIM))) return rc;
+    if ((rc = dev_alloc(&m->hyp_dev, (size_t)256))) return rc;
+    if (!m->info) BCBF_CUDA(cudaMalloc(&m->info, sizeof(int)));
+    m->cap_N = Npad;
+  }
+  m->N = N;
+  m->Npad = Npad;
+  // hyper-parameter block on the device: [lengthscale(8) | B(16) | C(32) | Ct(32) | A(64)]
+  double hbuf[256];
+  memset(hbuf, 0, sizeof(hbuf));
+  for (int d = 0; d < n; ++d) hbuf[d] = hyp->lengthscale[d];
+  for (int i = 0; i < p * p; ++i) hbuf[8 + i] = hyp->B[i];
+  for (int i = 0; i < p * n; ++i) hbuf[24 + i] = hyp->C[i];
+  for (int r = 0; r < n; ++r)
+    for (int j = 0; j < p; ++j) hbuf[56 + r * p + j] = hyp->C[j * n + r];
+  for (int i = 0; i < n * n; ++i) hbuf[88 + i] = hyp->A[i];
+  BCBF_CUDA(cudaMemcpyAsync(m->hyp_dev, hbuf, sizeof(hbuf), cudaMemcpyHostToDevice, m->stream));
+  BCBF_CUDA(cudaStreamSynchronize(m->stream));
+  return BCBF_OK;
+}
+
+static int finish_fit_from_factor(bcbf_model* m) {
+  // alpha = Linv^T (Linv Y);  W = alpha (.) G
+  const int n = m->hyp.n, p = m->hyp.p, Npad = m->Npad, ldy = ld_y(n);
+  double* tmp = m->Y + (size_t)Npad * ldy;  // second half of the Y buffer
+  int rc = bcbf_trmm_lower(m->Linv, Npad, Npad, 0, m->Y, ldy, ldy, 1.0, 0.0, tmp, ldy, m->stream);
+  if (rc) return rc;
+  rc = bcbf_trmm_lower(m->Linv, Npad, Npad, 1, tmp, ldy, ldy, 1.0, 0.0, m->alpha, ldy, m->stream);
+  if (rc) return rc;
+  build_w_kernel<<<ceil_div(Npad, 128), 128, 0, m->stream>>>(m->alpha, ldy, m->G, Npad, n, p, m->W);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double* X, const double* U, const double* Xdot,
+                              int N, const double* jitter, double jitter_scale) {
+  BCBF_REQUIRE(m && hyp && X && U && Xdot, "bcbf_model_fit: null pointer");
+  m->fitted = false;
+  int rc = bcbf_model_alloc_state(m, hyp, N);
+  if (rc) return rc;
+  const int n = hyp->n, p = hyp->p, mm = p - 1, Npad = m->Npad, ldy = ld_y(n);
+  cudaStream_t s = m->stream;
+  cudaEvent_t ev[6];
+  for (auto& e : ev) BCBF_CUDA(cudaEventCreate(&e));
+  // stage inputs: U and Xdot go through the (not yet used) Linv buffer, jitter through dinv
+  double* dU = m->Linv;
+  double* dXdot = m->Linv + (size_t)N * BCBF_MAX_P_DIM;
+  double* djit = nullptr;
+  BCBF_CUDA(cudaMemcpyAsync(m->X, X, sizeof(double) * (size_t)N * n, cudaMemcpyHostToDevice, s));
+  if (mm > 0) BCBF_CUDA(cudaMemcpyAsync(dU, U, sizeof(double) * (size_t)N * mm, cudaMemcpyHostToDevice, s));
+  BCBF_CUDA(cudaMemcpyAsync(dXdot, Xdot, sizeof(double) * (size_t)N * n, cudaMemcpyHostToDevice, s));
+  if (jitter) {
+    djit = m->W;  // W is rebuilt at the end of fit; N doubles of it carry the jitter until potrf has consumed it
+    BCBF_CUDA(cudaMemcpyAsync(djit, jitter, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+  }
+  BCBF_CUDA(cudaEventRecord(ev[0], s));
+  prep_train_kernel<<<ceil_div(Npad, 128), 128, 0, s>>>(dU, dXdot, N, Npad, n, p, m->hyp_dev + 8, m->hyp_dev + 24,
+                                                        m->UH, m->G, m->Y, ldy);
+  BCBF_LAUNCH_CHECK();
+  rc = bcbf_gram_train(m->X, m->UH, hyp->B, hyp->lengthscale, hyp->outputscale, N, n, p, m->L, Npad, Npad, s);
+  if (rc) return rc;
+  BCBF_CUDA(cudaEventRecord(ev[1], s));
+  rc = bcbf_potrf(m->L, Npad, Npad, N, djit, jitter_scale, m->dinv, m->info, s);
+  if (rc) return rc;
+  BCBF_CUDA(cudaEventRecord(ev[2], s));
+  rc = bcbf_check_info(m->info, s);
+  if (rc) return rc;
+  // scratch for trtri: a fresh Npad^2 buffer is avoided by borrowing the query Kstar buffer when big enough
+  if (m->cap_K < (size_t)Npad * Npad) {
+    if ((rc = dev_alloc(&m->Kstar, (size_t)Npad * Npad))) return rc;
+    m->cap_K = (size_t)Npad * Npad;
+  }
+  rc = bcbf_trtri(m->L, m->dinv, m->Linv, m->Kstar, Npad, Npad, s);
+  if (rc) return rc;
+  BCBF_CUDA(cudaEventRecord(ev[3], s));
+  rc = finish_fit_from_factor(m);
+  if (rc) return rc;
+  BCBF_CUDA(cudaEventRecord(ev[4], s));
+  BCBF_CUDA(cudaStreamSynchronize(s));
+  float ms;
+  for (int i = 0; i < 4; ++i) {
+    BCBF_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    m->fit_ms[i] = ms;
+  }
+  BCBF_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[4]));
+  m->fit_ms[4] = ms;
+  for (auto& e : ev) cudaEventDestroy(e);
+  m->fitted = true;
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_model_fit_timing(bcbf_model* m, double out_ms[5]) {
+  BCBF_REQUIRE(m && out_ms, "bcbf_model_fit_timing: null pointer");
+  for (int i = 0; i < 5; ++i) out_ms[i] = m->fit_ms[i];
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_model_state(bcbf_model* m, int* N, int* Npad, double** L, double** Linv, double** alpha,
+                                double** G, double** W, double** Xtrain) {
+  BCBF_REQUIRE(m, "bcbf_model_state: null model");
+  if (N) *N = m->N;
+  if (Npad) *Npad = m->Npad;
+  if (L) *L = m->L;
+  if (Linv) *Linv = m->Linv;
+  if (alpha) *alpha = m->alpha;
+  if (G) *G = m->G;
+  if (W) *W = m->W;
+  if (Xtrain) *Xtrain = m->X;
+  // a rank that received the state by broadcast marks itself fitted by asking for it
+  m->fitted = true;
+  return BCBF_OK;
+}
+
+static int ensure_query_capacity(bcbf_model* m, int Qb) {
+  const int Npad = m->Npad;
+  const int ldks = ((Qb + 95) / 96) * 96;
+  int rc;
+  if ((size_t)Qb > m->cap_Q) {
+    if ((rc = dev_alloc(&m->Xq, (size_t)Qb * BCBF_MAX_N_DIM))) return rc;
+    if ((rc = dev_alloc(&m->Uq, (size_t)Qb * BCBF_MAX_P_DIM))) return rc;
+    if ((rc = dev_alloc(&m->UHq, (size_t)Qb * BCBF_MAX_P_DIM))) return rc;
+    if ((rc = dev_alloc(&m->Mk, (size_t)Qb * BCBF_MAX_N_DIM * BCBF_MAX_P_DIM))) return rc;
+    if ((rc = dev_alloc(&m->Bk, (size_t)Qb * BCBF_MAX_P_DIM * BCBF_MAX_P_DIM))) return rc;
+    if ((rc = dev_alloc(&m->mean, (size_t)Qb * BCBF_MAX_N_DIM))) return rc;
+    if ((rc = dev_alloc(&m->svar, (size_t)Qb))) return rc;
+    m->cap_Q = Qb;
+  }
+  if ((size_t)Npad * ldks > m->cap_K) {
+    if ((rc = dev_alloc(&m->Kstar, (size_t)Npad * ldks))) return rc;
+    m->cap_K = (size_t)Npad * ldks;
+  }
+  return BCBF_OK;
+}
+
+// One device batch: Xq/Uq device pointers (Qb queries) -> device outputs (any may be null)
+static int query_batch_device(bcbf_model* m, const double* dXq, const double* dUq, int Qb, double* dmean, double* dsvar,
+                              double* dMk, double* dBk, cudaStream_t s) {
+  const int n = m->hyp.n, p = m->hyp.p, Npad = m->Npad, N = m->N;
+  const int ldks = ((Qb + 95) / 96) * 96;
+  int rc = bcbf_cross_gram(m->X, dXq, m->hyp.lengthscale, m->hyp.outputscale, N, Qb, n, m->Kstar, ldks, Npad, s);
+  if (rc) return rc;
+  double* Mk = dMk ? dMk : m->Mk;
+  double* Bk = dBk ? dBk : m->Bk;
+  const bool need_var = dBk || dsvar;
+  const bool need_mean = dMk || dmean;
+  rc = bcbf_posterior_blocks(m->Linv, Npad, Npad, m->Kstar, ldks, m->G, m->W, m->hyp_dev + 8, m->hyp_dev + 56,
+                             m->hyp.outputscale, n, p, Qb, need_mean ? Mk : nullptr, need_var ? Bk : nullptr, s);
+  if (rc) return rc;
+  if (dmean || dsvar) {
+    build_uh_kernel<<<ceil_div(Qb, 128), 128, 0, s>>>(dUq, Qb, p, m->UHq);
+    BCBF_LAUNCH_CHECK();
+    rc = bcbf_contract_u(Mk, Bk, m->UHq, n, p, Qb, dmean, dsvar, s);
+    if (rc) return rc;
+  }
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_model_query_device(bcbf_model* m, const double* Xq, const double* Uq, int Q, double* mean,
+                                       double* svar, double* Mk, double* Bk, void* stream_) {
+  BCBF_REQUIRE(m && Xq, "bcbf_model_query_device: null pointer");
+  if (!m->fitted) { set_last_error("bcbf_model_query_device: model is not fitted"); return BCBF_ERR_NOT_FITTED; }
+  BCBF_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = stream_ ? static_cast<cudaStream_t>(stream_) : m->stream;
+  const int n = m->hyp.n, p = m->hyp.p, mm = p - 1;
+  const int QB = query_batch(p);
+  int rc = ensure_query_capacity(m, Q < QB ? Q : QB);
+  if (rc) return rc;
+  for (int q0 = 0; q0 < Q; q0 += QB) {
+    const int Qb = (Q - q0) < QB ? (Q - q0) : QB;
+    rc = query_batch_device(m, Xq + (size_t)q0 * n, Uq ? Uq + (size_t)q0 * mm : nullptr, Qb,
+                            mean ? mean + (size_t)q0 * n : nullptr, svar ? svar + q0 : nullptr,
+                            Mk ? Mk + (size_t)q0 * n * p : nullptr, Bk ? Bk + (size_t)q0 * p * p : nullptr, s);
+    if (rc) return rc;
+  }
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_model_query(bcbf_model* m, const double* Xq, const double* Uq, int Q, double* mean, double* svar,
+                                double* Mk, double* Bk) {
+  BCBF_REQUIRE(m && Xq && Q >= 1, "bcbf_model_query: null pointer / empty query");
+  if (!m->fitted) { set_last_error("bcbf_model_query: model is not fitted"); return BCBF_ERR_NOT_FITTED; }
+  BCBF_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  const int n = m->hyp.n, p = m->hyp.p, mm = p - 1;
+  const int QB = query_batch(p);
+  int rc = ensure_query_capacity(m, Q < QB ? Q : QB);
+  if (rc) return rc;
+  for (int q0 = 0; q0 < Q; q0 += QB) {
+    const int Qb = (Q - q0) < QB ? (Q - q0) : QB;
+    BCBF_CUDA(cudaMemcpyAsync(m->Xq, Xq + (size_t)q0 * n, sizeof(double) * (size_t)Qb * n, cudaMemcpyHostToDevice, s));
+    if (Uq && mm > 0)
+      BCBF_CUDA(cudaMemcpyAsync(m->Uq, Uq + (size_t)q0 * mm, sizeof(double) * (size_t)Qb * mm, cudaMemcpyHostToDevice, s));
+    rc = query_batch_device(m, m->Xq, Uq ? m->Uq : nullptr, Qb, mean ? m->mean : nullptr, svar ? m->svar : nullptr,
+                            Mk ? m->Mk : nullptr, Bk ? m->Bk : nullptr, s);
+    if (rc) return rc;
+    if (mean) BCBF_CUDA(cudaMemcpyAsync(mean + (size_t)q0 * n, m->mean, sizeof(double) * (size_t)Qb * n, cudaMemcpyDeviceToHost, s));
+    if (svar) BCBF_CUDA(cudaMemcpyAsync(svar + q0, m->svar, sizeof(double) * (size_t)Qb, cudaMemcpyDeviceToHost, s));
+    if (Mk) BCBF_CUDA(cudaMemcpyAsync(Mk + (size_t)q0 * n * p, m->Mk, sizeof(double) * (size_t)Qb * n * p, cudaMemcpyDeviceToHost, s));
+    if (Bk) BCBF_CUDA(cudaMemcpyAsync(Bk + (size_t)q0 * p * p, m->Bk, sizeof(double) * (size_t)Qb * p * p, cudaMemcpyDeviceToHost, s));
+  }
+  BCBF_CUDA(cudaStreamSynchronize(s));
+  return BCBF_OK;
+}

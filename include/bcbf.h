@@ -1,0 +1,172 @@
+/*
+ * bcbf.h — C ABI of the B200-native MVGP hot path (libbcbf.so).
+ *
+ * Drop-in boundary for the matrix-variate GP path of wecacuee/Bayesian_CBF.  The reference has no
+ * FFI: the path sits behind Python classes (bayes_cbf/control_affine_model.py).  Each entry point below
+ * names the reference statement(s) it replaces (file:line in the reference repo).  The Python host side
+ * (bayesian_cbf_b200/) keeps the reference's class API and binds these symbols with ctypes; see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - all matrices are row-major float64; "device" pointers are CUDA device pointers on the current device;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous w.r.t. the
+ *     host unless stated otherwise;
+ *   - N  = number of training points, Npad = N rounded up to a multiple of 128 (bcbf_padded()); factor-sized
+ *     buffers are Npad x Npad with leading dimension ld >= Npad, the pad region holds the identity;
+ *   - n  = state dim, m = control dim, p = 1 + m (homogeneous control [1;u]);
+ *   - return value: BCBF_OK (0) or a negative error code; bcbf_last_error() describes the last failure
+ *     of the calling thread.  There is NO CPU fallback anywhere: without a CUDA device every compute
+ *     entry point returns BCBF_ERR_CUDA.
+ */
+#ifndef BCBF_H_
+#define BCBF_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCBF_OK 0
+#define BCBF_ERR_INVALID (-1)
+#define BCBF_ERR_CUDA (-2)
+#define BCBF_ERR_NOT_PD (-3) /* Cholesky met a non-positive pivot: the caller retries with more jitter */
+#define BCBF_ERR_NOT_FITTED (-4)
+
+#define BCBF_BLOCK 128
+#define BCBF_MAX_N_DIM 8 /* state dim n  */
+#define BCBF_MAX_P_DIM 4 /* p = 1 + m    */
+
+const char* bcbf_last_error(void);
+int bcbf_version(void);
+/* N rounded up to the block size the kernels tile by. */
+int bcbf_padded(int N);
+/* Bytes of scratch bcbf_potrf/bcbf_trtri need for a factor of padded size Npad. */
+long long bcbf_dinv_elems(int Npad);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Control-affine Gram matrix.
+ * Replaces control_affine_model.py:370-372:  KXX = k(X,X); uBu = UH @ B @ UH.T; Kb = KXX * uBu
+ * with k = ScaleKernel(RBFKernel(ard))  (control_affine_model.py:164-171).
+ *   X (N,n)  UH (N,p)  Bmat (p,p)  lengthscale (n)  -> Kb (Npad,Npad; ld)
+ * Writes the FULL symmetric matrix on [0,N)^2 (so the result equals the reference's dense Kb), the identity on
+ * the pad diagonal and zeros elsewhere in the pad.
+ */
+int bcbf_gram_train(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                    double outputscale, int N, int n, int p, double* Kb, int ld, int Npad, void* stream);
+
+/* Cross Gram  Kstar[i, j] = k(X_i, Xq_j)   (control_affine_model.py:536 / :1051, the k_xs / k_sx factor).
+ *   X (N,n), Xq (Q,n) -> Kstar (Npad, ldks) row-major with ldks >= Q; rows >= N are written as zero.     */
+int bcbf_cross_gram(const double* X, const double* Xq, const double* lengthscale, double outputscale, int N,
+                    int Q, int n, double* Kstar, int ldks, int Npad, void* stream);
+
+/* General k(X1, X2) (a x c) dense, plus optional closed-form derivative blocks
+ *   dK[i,j,:]   = d k(x1_i, x2_j) / d x1_i                      (a,c,n)     [may be NULL]
+ *   d2K[i,j,:,:] = d^2 k(x1_i, x2_j) / d x1_i d x2_j^T           (a,c,n,n)   [may be NULL]
+ * Replaces the autograd-through-gpytorch derivative kernels grad_ksx / grad_kxs / Hessian_kxx
+ * (control_affine_model.py:465-477, misc.py:236-245).                                                   */
+int bcbf_rbf_blocks(const double* X1, const double* X2, const double* lengthscale, double outputscale, int a,
+                    int c, int n, double* K, double* dK, double* d2K, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Blocked FP64 Cholesky  A + scale*diag(jitter) = L L^T, in place, lower (upper triangle is zeroed).
+ * Replaces make_psd's  torch.linalg.cholesky(Kb + factor * eye * rand)  (control_affine_model.py:907-911).
+ *   A (Npad,Npad; ld) in/out;  jitter (N) may be NULL;  dinv: bcbf_dinv_elems(Npad) doubles of scratch that
+ *   receives the inverses of the 128x128 diagonal blocks of L;  info: device int, 0 on success else
+ *   1 + index of the first non-positive pivot (LAPACK convention).  Asynchronous: read *info after a sync,
+ *   or call bcbf_check_info() which synchronises the stream and maps info != 0 to BCBF_ERR_NOT_PD.
+ */
+int bcbf_potrf(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale, double* dinv,
+               int* info, void* stream);
+int bcbf_check_info(const int* info, void* stream);
+
+/* Linv = L^{-1} (lower; strictly-upper blocks are zero) from L and the diagonal-block inverses of bcbf_potrf.
+ * scratch: Npad*Npad doubles.  Everything downstream (alpha, v = L \ kb*, posterior covariance) multiplies by
+ * Linv instead of running triangular solves (torch.cholesky_solve / torch.linalg.solve at
+ * control_affine_model.py:545,565,575,1053).                                                              */
+int bcbf_trtri(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad,
+               void* stream);
+
+/* C (M,Ncols; ldc) = alpha * op(A) * B + beta * C  with A = a lower-triangular factor-sized matrix
+ * (Npad,Npad; lda): op = identity (trans=0) or transpose (trans=1).  B (Npad,Ncols; ldb).
+ * Used for  v = Linv @ kb*,  alpha = Linv^T (Linv Y).                                                  */
+int bcbf_trmm_lower(const double* A, int lda, int Npad, int trans, const double* B, int ldb, int ncols,
+                    double alpha, double beta, double* C, int ldc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Batched posterior of F(x) over many query states (matrix form).
+ * Replaces ControlAffineRegressorExact._custom_predict_matrix, per-query diagonal blocks
+ * (control_affine_model.py:1051-1091):
+ *     M_k(x) = C^T + Y^T Kb^{-1} frakB(x)                       (Q,n,p)
+ *     B_k(x) = B k(x,x) - frakB(x)^T Kb^{-1} frakB(x)           (Q,p,p)
+ * with frakB(x) = k(X,x)[:,None] * G,  G = UH @ B (Npad,p; pad rows zero),  W[i, r*p+q] = alpha[i,r]*G[i,q]
+ * (Npad, n*p).  Kstar from bcbf_cross_gram.  Ct is C^T (n,p).  kss = k(x,x) = outputscale.
+ * The random output jitter the reference adds at :1089 is NOT applied here (host adds it when asked).
+ */
+int bcbf_posterior_blocks(const double* Linv, int ld, int Npad, const double* Kstar, int ldks, const double* G,
+                          const double* W, const double* Bmat, const double* Ct, double kss, int n, int p, int Q,
+                          double* Mk, double* Bk, void* stream);
+
+/* u-contraction epilogue (control_affine_model.py:952-958):  mean = M_k [1;u]  (Q,n),
+ * svar = [1;u]^T B_k [1;u] (Q).  UHq (Q,p).                                                             */
+int bcbf_contract_u(const double* Mk, const double* Bk, const double* UHq, int n, int p, int Q, double* mean,
+                    double* svar, void* stream);
+
+/* Fold-in form of the base class (control_affine_model.py:536-586): one column per query,
+ *     mean = UHq C + kb*^T alpha (Q,n),   svar = kb** - |Linv kb*|^2 (Q)
+ * with kb*[i] = k(X_i,x) * (G_i . uh).  Uses Kstar from bcbf_cross_gram.  alpha (Npad,n; pad rows zero).  */
+int bcbf_posterior_fu(const double* Linv, int ld, int Npad, const double* Kstar, int ldks, const double* G,
+                      const double* alpha, const double* Bmat, const double* C, const double* UHq, double kss,
+                      int n, int p, int Q, double* mean, double* svar, void* stream);
+
+/* Relative-degree-1 control-barrier-condition terms in closed form, replacing the autograd
+ * extraction of cbc2_quadratic_terms (cbc2.py:7-23) + convert_cbc_terms_to_socp_terms
+ * (unicycle_move_to_pose.py:837-878), batched over Q constraints:
+ *   row = grad_h^T (Fbar + M_k);  e = row[0] + gamma*h;  bfe = row[1:]
+ *   Asq = (grad_h^T A grad_h) * B_k = Ls Ls^T;  A_socp = Ls^T[:,1:] (p,m);  bfb = Ls^T[:,0] (p)
+ * Fbar (Q,n,p) may be NULL.  Outputs: bfe (Q,m), e (Q), Asq (Q,p,p), A_socp (Q,p,m), bfb (Q,p),
+ * status (Q) = 0 or 1+index of a non-positive pivot of Asq.                                             */
+int bcbf_cbc1_terms(const double* Mk, const double* Bk, const double* Amat, const double* grad_h, const double* h,
+                    const double* Fbar, double gamma, int n, int p, int Q, double* bfe, double* e, double* Asq,
+                    double* A_socp, double* bfb, int* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model handle: owns device memory for one fitted MVGP; HOST-pointer interface (pinned or pageable).
+ * This is what a non-torch caller (and bench.py's e2e leg) binds.
+ */
+typedef struct bcbf_model bcbf_model;
+
+typedef struct bcbf_hyper {
+  int n;                                              /* state dim */
+  int p;                                              /* 1 + control dim */
+  double outputscale;                                 /* ScaleKernel.outputscale */
+  double lengthscale[BCBF_MAX_N_DIM];                 /* RBFKernel.lengthscale (ARD) */
+  double A[BCBF_MAX_N_DIM * BCBF_MAX_N_DIM];          /* task_covar.U.covar_matrix (n,n) row-major */
+  double B[BCBF_MAX_P_DIM * BCBF_MAX_P_DIM];          /* task_covar.V.covar_matrix (p,p) row-major */
+  double C[BCBF_MAX_P_DIM * BCBF_MAX_N_DIM];          /* mean constants (p,n) row-major */
+} bcbf_hyper;
+
+int bcbf_model_create(bcbf_model** out, int device);
+void bcbf_model_destroy(bcbf_model* m);
+/* Gram + jittered Cholesky + Linv + alpha at fixed hyper-parameters ("fit time" of BASELINE.json; what
+ * _perturbed_cholesky + the alpha solve of custom_predict do on first use, control_affine_model.py:366-385,545).
+ * X (N,n) U (N,m) Xdot (N,n) jitter (N) are HOST pointers.  Synchronous.  BCBF_ERR_NOT_PD -> retry with 10x scale. */
+int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double* X, const double* U, const double* Xdot,
+                   int N, const double* jitter, double jitter_scale);
+/* Posterior of F(x)[1;u] for Q queries, HOST pointers in and out (any output may be NULL):
+ *   mean (Q,n), svar (Q) [cov = svar * A], Mk (Q,n,p), Bk (Q,p,p).  Synchronous; copies are inside the call. */
+int bcbf_model_query(bcbf_model* m, const double* Xq, const double* Uq, int Q, double* mean, double* svar,
+                     double* Mk, double* Bk);
+/* Same with DEVICE pointers on `stream`, asynchronous (used by the sharded bench and the Python host). */
+int bcbf_model_query_device(bcbf_model* m, const double* Xq, const double* Uq, int Q, double* mean, double* svar,
+                            double* Mk, double* Bk, void* stream);
+/* Device pointers of the fitted state, for NCCL broadcast of the factor (multi-GPU: fit on one rank,
+ * bcbf_model_adopt on the others).  Layout documented in DESIGN.md.                                       */
+int bcbf_model_state(bcbf_model* m, int* N, int* Npad, double** L, double** Linv, double** alpha, double** G,
+                     double** W, double** Xtrain);
+int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int N);
+/* Milliseconds spent in the stages of the last bcbf_model_fit (gram, potrf, trtri, alpha, total). */
+int bcbf_model_fit_timing(bcbf_model* m, double out_ms[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCBF_H_ */

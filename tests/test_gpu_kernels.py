@@ -1,0 +1,235 @@
+"""GPU parity tests: every CUDA kernel (called through the C ABI) against the CPU oracle on the same
+seeded inputs.  float64; tolerances are norm-wise relative, written next to each check."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvgp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(seed, N, n, m, Q, box=2.0):
+    g = torch.Generator().manual_seed(seed)
+    p = m + 1
+    X = box * (2 * torch.rand(N, n, generator=g, dtype=torch.float64) - 1)
+    U = 2 * torch.rand(N, m, generator=g, dtype=torch.float64) - 1
+    Xdot = torch.sin(X @ torch.randn(n, n, generator=g, dtype=torch.float64)) \
+        + 0.01 * torch.randn(N, n, generator=g, dtype=torch.float64)
+    Ra = torch.randn(n, n, generator=g, dtype=torch.float64)
+    Rb = torch.randn(p, p, generator=g, dtype=torch.float64)
+    hyp = O.Hyper(lengthscale=0.6 + 0.5 * torch.rand(n, generator=g, dtype=torch.float64),
+                  outputscale=torch.tensor(1.3, dtype=torch.float64),
+                  A=Ra @ Ra.T + torch.eye(n, dtype=torch.float64),
+                  B=Rb @ Rb.T + torch.eye(p, dtype=torch.float64),
+                  C=0.3 * torch.randn(p, n, generator=g, dtype=torch.float64))
+    jit = torch.rand(N, generator=g, dtype=torch.float64)
+    Xq = box * (2 * torch.rand(Q, n, generator=g, dtype=torch.float64) - 1)
+    Uq = 2 * torch.rand(Q, m, generator=g, dtype=torch.float64) - 1
+    return X, U, Xdot, hyp, jit, Xq, Uq
+
+
+def _d(t):
+    return t.contiguous().cuda()
+
+
+def _relerr(got, want):
+    want = want if isinstance(want, torch.Tensor) else torch.as_tensor(want)
+    return ((got.cpu() - want).abs().max() / want.abs().max().clamp_min(1e-300)).item()
+
+
+@pytest.mark.parametrize('N,n,m', [(300, 3, 2), (129, 2, 1), (64, 1, 3)])
+def test_gram_train(N, n, m):
+    from bayesian_cbf_b200 import ops
+    X, U, _, hyp, _, _, _ = _mk(1, N, n, m, 4)
+    UH = O.homogeneous(U)
+    Kb = ops.gram_train(_d(X), _d(UH), _d(hyp.B), _d(hyp.lengthscale), float(hyp.outputscale))
+    Npad = ops.padded(N)
+    assert Kb.shape == (Npad, Npad)
+    ref = O.gram_train(hyp, X, UH, direct=True)
+    assert _relerr(Kb[:N, :N], ref) < 1e-14          # same formula, FMA-level differences only
+    ref_g = O.gram_train(hyp, X, UH, direct=False)    # gpytorch's expanded-distance form
+    assert _relerr(Kb[:N, :N], ref_g) < 1e-13
+    pad = Kb.cpu()[N:, N:]
+    assert torch.equal(pad, torch.eye(Npad - N, dtype=torch.float64))
+    assert Kb.cpu()[N:, :N].abs().max() == 0 and Kb.cpu()[:N, N:].abs().max() == 0
+
+
+def test_cross_gram_and_rbf_blocks():
+    from bayesian_cbf_b200 import ops
+    X, _, _, hyp, _, Xq, _ = _mk(2, 200, 3, 2, 70)
+    Ks = ops.cross_gram(_d(X), _d(Xq), _d(hyp.lengthscale), float(hyp.outputscale))
+    assert Ks.shape == (256, 96)
+    ref = O.rbf_ard(X, Xq, hyp.lengthscale, hyp.outputscale, direct=True)
+    assert _relerr(Ks[:200, :70], ref) < 1e-14
+    assert Ks.cpu()[200:].abs().max() == 0 and Ks.cpu()[:, 70:].abs().max() == 0
+    K, dK, d2K = ops.rbf_blocks(_d(Xq[:5]), _d(X[:7]), _d(hyp.lengthscale), float(hyp.outputscale), True, True)
+    for i in range(5):
+        for j in range(7):
+            k, g, H = O.rbf_grad_hess(Xq[i], X[j], hyp.lengthscale, hyp.outputscale)
+            assert abs(K[i, j].item() - k.item()) < 1e-14
+            assert (dK[i, j].cpu() - g).abs().max() < 1e-13
+            assert (d2K[i, j].cpu() - H).abs().max() < 1e-13
+
+
+@pytest.mark.parametrize('N', [100, 128, 300, 640, 1100])
+def test_potrf_trtri(N):
+    from bayesian_cbf_b200 import ops
+    X, U, _, hyp, jit, _, _ = _mk(3, N, 3, 2, 4, box=3.0)
+    UH = O.homogeneous(U)
+    Kb = ops.gram_train(_d(X), _d(UH), _d(hyp.B), _d(hyp.lengthscale), float(hyp.outputscale))
+    Kb_host = Kb.cpu().clone()
+    Npad = Kb.shape[0]
+    L, dinv = ops.potrf_(Kb, N, _d(jit), 1e-5)
+    Lh = L.cpu()
+    jpad = torch.zeros(Npad, dtype=torch.float64)
+    jpad[:N] = 1e-5 * jit
+    Kbp = Kb_host + torch.diag(jpad)
+    assert torch.equal(Lh, torch.tril(Lh))                               # upper triangle zeroed
+    resid = (Lh @ Lh.T - Kbp).abs().max() / Kbp.abs().max()
+    assert resid < 1e-14, resid                                          # backward error of the factorisation
+    Lref = torch.linalg.cholesky(Kbp)
+    # forward agreement with LAPACK is conditioning-limited: eps * cond(Kb) — bound it loosely
+    assert _relerr(L, Lref) < 1e-7
+    Linv = ops.trtri(L, dinv).cpu()
+    assert torch.equal(Linv, torch.tril(Linv))
+    I = torch.eye(Npad, dtype=torch.float64)
+    condL = torch.linalg.cond(Lref).item()
+    assert (Linv @ Lh - I).abs().max() < 1e-15 * condL * 50 + 1e-12
+
+
+def test_potrf_not_pd_raises_runtimeerror():
+    from bayesian_cbf_b200 import ops
+    A = torch.eye(256, dtype=torch.float64)
+    A[200, 200] = -1.0
+    with pytest.raises(RuntimeError, match="not positive-definite"):
+        ops.potrf_(_d(A), 256, None, 0.0)
+
+
+def test_trmm_lower():
+    from bayesian_cbf_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    Npad = 384
+    A = torch.tril(torch.randn(Npad, Npad, generator=g, dtype=torch.float64))
+    Bm = torch.randn(Npad, 7, generator=g, dtype=torch.float64)
+    C = ops.trmm_lower(_d(A), _d(Bm))
+    assert _relerr(C, A @ Bm) < 1e-13
+    Ct = ops.trmm_lower(_d(A), _d(Bm), trans=True, alpha=-2.0)
+    assert _relerr(Ct, -2.0 * A.T @ Bm) < 1e-13
+
+
+def _fit_on_gpu(X, U, Xdot, hyp, jit):
+    from bayesian_cbf_b200 import ops
+    N = X.shape[0]
+    UH = O.homogeneous(U)
+    Kb = ops.gram_train(_d(X), _d(UH), _d(hyp.B), _d(hyp.lengthscale), float(hyp.outputscale))
+    L, dinv = ops.potrf_(Kb, N, _d(jit), 1e-5)
+    Linv = ops.trtri(L, dinv)
+    Npad = L.shape[0]
+    G = torch.zeros(Npad, hyp.p, dtype=torch.float64)
+    G[:N] = UH @ hyp.B
+    Y = torch.zeros(Npad, hyp.n, dtype=torch.float64)
+    Y[:N] = O.residual_targets(hyp, UH, Xdot)
+    z = ops.trmm_lower(Linv, _d(Y))
+    alpha = ops.trmm_lower(Linv, z.contiguous(), trans=True).contiguous()
+    W = (alpha.unsqueeze(-1) * _d(G).unsqueeze(1)).reshape(Npad, -1).contiguous()
+    return L, Linv, _d(G), alpha, W
+
+
+@pytest.mark.parametrize('N,n,m,Q', [(500, 3, 2, 200), (1000, 2, 1, 333), (260, 3, 3, 50), (150, 2, 0, 40)])
+def test_posterior_blocks(N, n, m, Q):
+    from bayesian_cbf_b200 import ops
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(7, N, n, m, Q, box=3.0)
+    p = m + 1
+    L, Linv, G, alpha, W = _fit_on_gpu(X, U, Xdot, hyp, jit)
+    Ks = ops.cross_gram(_d(X), _d(Xq), _d(hyp.lengthscale), float(hyp.outputscale))
+    Mk, Bk = ops.posterior_blocks(Linv, Ks, G, W, _d(hyp.B), _d(hyp.C.t()), float(hyp.outputscale), n, p, Q)
+    # oracle on the SAME jitter (CPU LAPACK factor)
+    Lref = O.perturbed_cholesky(hyp, X, O.homogeneous(U), [jit], direct=True)
+    Mk_o, Bk_o, mean_o, svar_o = O.posterior_blocks(hyp, X, U, Xdot, Lref, Xq, Uq, direct=True)
+    prior = (hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)).item()
+    # covariance: norm-wise relative to the prior scale s*|B| (difference of nearly equal numbers)
+    assert (Bk.cpu() - Bk_o).abs().max() / prior < 1e-9
+    # mean: relative to max|M_k|; conditioning-limited (alpha = Kb^-1 Y), measured against the oracle's own
+    # sensitivity to the formulation (cholesky_solve vs explicit triangular solves)
+    al1 = torch.cholesky_solve(O.residual_targets(hyp, O.homogeneous(U), Xdot), Lref)
+    Linv_o = torch.linalg.solve_triangular(Lref, torch.eye(N, dtype=torch.float64), upper=False)
+    al2 = Linv_o.T @ (Linv_o @ O.residual_targets(hyp, O.homogeneous(U), Xdot))
+    Ks_o = O.rbf_ard(X, Xq, hyp.lengthscale, hyp.outputscale, direct=True)
+    floor = (Ks_o.T @ (al1 - al2)).abs().max().item()
+    tol = max(1e-9 * Mk_o.abs().max().item(), 20 * floor)
+    assert (Mk.cpu() - Mk_o).abs().max() < tol, ((Mk.cpu() - Mk_o).abs().max(), tol)
+    # u-contraction
+    UHq = O.homogeneous(Uq)
+    mean, svar = ops.contract_u(Mk, Bk, _d(UHq))
+    assert (mean.cpu() - mean_o).abs().max() < tol * p * 2
+    assert (svar.cpu() - svar_o).abs().max() / prior < 1e-8
+    # fold-in form
+    sv2 = ops.posterior_fu_var(Linv, Ks, G, _d(hyp.B), _d(UHq), float(hyp.outputscale), n, p)
+    assert (sv2.cpu() - svar_o).abs().max() / prior < 1e-8
+    assert (svar_o > -1e-9 * prior).all()
+
+
+def test_cbc1_terms():
+    from bayesian_cbf_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    Q, n, p = 37, 3, 3
+    Mk = torch.randn(Q, n, p, generator=g, dtype=torch.float64)
+    R = torch.randn(Q, p, p, generator=g, dtype=torch.float64)
+    Bk = R @ R.transpose(1, 2) + 0.1 * torch.eye(p, dtype=torch.float64)
+    Ra = torch.randn(n, n, generator=g, dtype=torch.float64)
+    A = Ra @ Ra.T + torch.eye(n, dtype=torch.float64)
+    gh = torch.randn(Q, n, generator=g, dtype=torch.float64)
+    h = torch.randn(Q, generator=g, dtype=torch.float64)
+    Fbar = torch.randn(Q, n, p, generator=g, dtype=torch.float64)
+    bfe, e, Asq, A_socp, bfb, status = ops.cbc1_terms(_d(Mk), _d(Bk), _d(A), _d(gh), _d(h), 0.7, _d(Fbar))
+    assert (status.cpu() == 0).all()
+    for q in range(Q):
+        bfe_o, e_o, V, bfv, v = O.cbc1_terms_closed_form(Mk[q], Bk[q], A, gh[q], h[q], 0.7, Fbar[q])
+        A_o, bfb_o, bfc_o, d_o = O.convert_cbc_terms_to_socp_terms(bfe_o, e_o, V, bfv, v, 0)
+        assert (bfe[q].cpu() - bfe_o).abs().max() < 1e-12
+        assert abs(e[q].item() - e_o.item()) < 1e-12
+        assert (A_socp[q].cpu() - A_o).abs().max() < 1e-11
+        assert (bfb[q].cpu() - bfb_o).abs().max() < 1e-11
+
+
+def test_model_handle_host_pointers():
+    """bcbf_model_* entry points with HOST buffers (what bench.py's e2e leg and a non-torch caller bind)."""
+    from bayesian_cbf_b200 import _lib
+    lib = _lib.load()
+    N, n, m, Q = 700, 3, 2, 1000
+    p = m + 1
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(11, N, n, m, Q, box=3.0)
+    h = _lib.Hyper()
+    h.n, h.p, h.outputscale = n, p, float(hyp.outputscale)
+    for i, v in enumerate(hyp.lengthscale.tolist()):
+        h.lengthscale[i] = v
+    for i, v in enumerate(hyp.A.reshape(-1).tolist()):
+        h.A[i] = v
+    for i, v in enumerate(hyp.B.reshape(-1).tolist()):
+        h.B[i] = v
+    for i, v in enumerate(hyp.C.reshape(-1).tolist()):
+        h.C[i] = v
+    model = ctypes.c_void_p()
+    _lib.check(lib.bcbf_model_create(ctypes.byref(model), 0))
+    try:
+        arrs = [a.contiguous().numpy() for a in (X, U, Xdot, jit, Xq, Uq)]
+        ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(lib.bcbf_model_fit(model, ctypes.byref(h), ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), N,
+                                      ptr(arrs[3]), 1e-5))
+        mean = np.empty((Q, n)); svar = np.empty(Q); Mk = np.empty((Q, n, p)); Bk = np.empty((Q, p, p))
+        _lib.check(lib.bcbf_model_query(model, ptr(arrs[4]), ptr(arrs[5]), Q, ptr(mean), ptr(svar), ptr(Mk), ptr(Bk)))
+        ms = (ctypes.c_double * 5)()
+        _lib.check(lib.bcbf_model_fit_timing(model, ctypes.byref(ms)))
+        assert ms[4] > 0
+    finally:
+        lib.bcbf_model_destroy(model)
+    Lref = O.perturbed_cholesky(hyp, X, O.homogeneous(U), [jit], direct=True)
+    Mk_o, Bk_o, mean_o, svar_o = O.posterior_blocks(hyp, X, U, Xdot, Lref, Xq, Uq, direct=True)
+    prior = (hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)).item()
+    assert np.abs(Bk - Bk_o.numpy()).max() / prior < 1e-9
+    assert np.abs(svar - svar_o.numpy()).max() / prior < 1e-8
+    assert np.abs(Mk - Mk_o.numpy()).max() < 1e-6 * np.abs(Mk_o.numpy()).max()
+    assert np.abs(mean - mean_o.numpy()).max() < 1e-6 * np.abs(mean_o.numpy()).max()
