@@ -41,6 +41,9 @@ _SIGNATURES = {
     'bcbf_last_error': (c_char_p, []),
     'bcbf_version': (c_int, []),
     'bcbf_padded': (c_int, [c_int]),
+    'bcbf_launch_count': (ctypes.c_ulonglong, []),
+    'bcbf_profile_enable': (c_int, [c_int]),
+    'bcbf_profile_read': (c_int, [POINTER(c_double), POINTER(c_int)]),
     'bcbf_dinv_elems': (c_longlong, [c_int]),
     'bcbf_gram_train': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     'bcbf_cross_gram': (c_int, [_P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),

@@ -9,6 +9,7 @@
 namespace bcbf {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -132,6 +133,7 @@ using namespace bcbf;
 
 extern "C" const char* bcbf_last_error(void) { return g_err; }
 extern "C" int bcbf_version(void) { return 100; }
+extern "C" unsigned long long bcbf_launch_count(void) { return g_launch_count; }
 extern "C" int bcbf_padded(int N) { return ((N + kBlk - 1) / kBlk) * kBlk; }
 
 extern "C" int bcbf_cbc1_terms(const double* Mk, const double* Bk, const double* Amat, const double* grad_h,

@@ -21,7 +21,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (_e != cudaSuccess) return ::bcbf::cuda_fail(_e, #call, __FILE__, __LINE__); \
   } while (0)
 
-#define BCBF_LAUNCH_CHECK() BCBF_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through one of these (bench.py reports the count as gpu_launches)
+extern unsigned long long g_launch_count;
+#define BCBF_LAUNCH_CHECK()        \
+  do {                             \
+    ++::bcbf::g_launch_count;      \
+    BCBF_CUDA(cudaGetLastError()); \
+  } while (0)
 
 #define BCBF_REQUIRE(cond, ...)                 \
   do {                                          \

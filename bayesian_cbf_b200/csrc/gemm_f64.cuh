@@ -178,6 +178,7 @@ inline cudaError_t launch_gemm(GemmArgs a, int batch, cudaStream_t stream) {
                                              : (long long)a.mtiles * a.ntiles;
   dim3 grid((unsigned)tiles, 1, (unsigned)batch);
   gemm_f64_kernel<A_KC, B_KC><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(a);
+  ++g_launch_count;
   return cudaGetLastError();
 }
 

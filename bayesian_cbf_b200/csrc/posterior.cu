@@ -16,6 +16,9 @@
 #include "../../include/bcbf.h"
 #include "common.cuh"
 
+#include <utility>
+#include <vector>
+
 namespace bcbf {
 
 constexpr int kPA_Stride = 20;                  // A tile row stride (16 + 4 pad doubles)
@@ -342,12 +345,29 @@ static int get_workspace(size_t bytes, double** out) {
   return BCBF_OK;
 }
 
+// ---- optional event profiling of the dominant kernel (bench.py's roofline leg) ------------------------
+struct KernelProfile {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+};
+static KernelProfile g_prof;
+
 template <class Cfg>
 static int launch_post_var(PostArgs a, cudaStream_t stream) {
   BCBF_CUDA(cudaFuncSetAttribute(post_var_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SmemBytes));
   dim3 grid(a.Qpad / Cfg::TQ, a.nsplit);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    BCBF_CUDA(cudaEventCreate(&e0));
+    BCBF_CUDA(cudaEventCreate(&e1));
+    BCBF_CUDA(cudaEventRecord(e0, stream));
+  }
   post_var_kernel<Cfg><<<grid, kPThreads, Cfg::SmemBytes, stream>>>(a);
   BCBF_LAUNCH_CHECK();
+  if (g_prof.on) {
+    BCBF_CUDA(cudaEventRecord(e1, stream));
+    g_prof.spans.emplace_back(e0, e1);
+  }
   return BCBF_OK;
 }
 
@@ -475,5 +495,29 @@ extern "C" int bcbf_contract_u(const double* Mk, const double* Bk, const double*
   BCBF_REQUIRE(UHq && Q >= 1 && n >= 1 && p >= 1 && p <= BCBF_MAX_P_DIM, "bcbf_contract_u: bad arguments");
   contract_u_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(Mk, Bk, UHq, n, p, Q, mean, svar);
   BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+// Event profiling of post_var_kernel launches: enable (clears history), then read after the timed region.
+extern "C" int bcbf_profile_enable(int on) {
+  for (auto& sp : g_prof.spans) {
+    cudaEventDestroy(sp.first);
+    cudaEventDestroy(sp.second);
+  }
+  g_prof.spans.clear();
+  g_prof.on = on != 0;
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_profile_read(double* total_ms, int* launches) {
+  double tot = 0.0;
+  for (auto& sp : g_prof.spans) {
+    BCBF_CUDA(cudaEventSynchronize(sp.second));
+    float ms = 0.f;
+    BCBF_CUDA(cudaEventElapsedTime(&ms, sp.first, sp.second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int)g_prof.spans.size();
   return BCBF_OK;
 }

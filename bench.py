@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — posterior queries/sec (mean + cov of F(x)u) and fit time at N training points.
+
+Workload (BASELINE.json configs[3]): synthetic unicycle MVGP, n=3, m=2, N=16384 training
+points, queries in steps of `--queries-per-step` states (default 18944 = 148 SMs x 32 queries x 4 waves;
+53 steps = 1.004M queries).  One "step" = one pass of the hot path over one batch of queries: cross-Gram,
+posterior mean M_k (3x3), posterior covariance B_k (3x3) [N^2 p flops per query on the FP64 tensor pipe],
+u-contraction to mean (3) and scalar variance.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DIM, M_DIM = 3, 2
+P_DIM = M_DIM + 1
+
+
+# --------------------------------------------------------------------------------------------- workload
+def make_workload(N, seed=0):
+    """SURVEY §8d config 4.  Everything is drawn from one CPU generator so CPU and GPU arms see identical bits."""
+    g = torch.Generator().manual_seed(seed)
+    f64 = dict(dtype=torch.float64, generator=g)
+    X = 4 * torch.rand(N, N_DIM, **f64) - 2
+    U = 2 * torch.rand(N, M_DIM, **f64) - 1
+
+    def ackermann_F(X, L):  # reference unicycle_move_to_pose.py:235-260  F = [f | g], f = 0
+        th = X[:, 2]
+        F = torch.zeros(X.shape[0], 3, 3, dtype=torch.float64)
+        F[:, 0, 1] = th.cos()
+        F[:, 1, 1] = th.sin()
+        F[:, 2, 2] = 1.0 / L
+        return F
+    Ftrue = ackermann_F(X, 1.0) - ackermann_F(X, 12.0)
+    UH = torch.cat([torch.ones(N, 1, dtype=torch.float64), U], dim=1)
+    Xdot = torch.einsum('inp,ip->in', Ftrue, UH) + 0.01 * torch.randn(N, N_DIM, **f64)
+    Ra = torch.randn(N_DIM, N_DIM, **f64)
+    Rb = torch.randn(P_DIM, P_DIM, **f64)
+    hyp = dict(lengthscale=torch.tensor([0.7, 0.9, 1.1], dtype=torch.float64),
+               outputscale=torch.tensor(1.3, dtype=torch.float64),
+               A=Ra @ Ra.T + torch.eye(N_DIM, dtype=torch.float64),
+               B=Rb @ Rb.T + torch.eye(P_DIM, dtype=torch.float64),
+               C=torch.zeros(P_DIM, N_DIM, dtype=torch.float64))
+    jitter = torch.rand(N, **f64)
+    return X, U, Xdot, hyp, jitter
+
+
+def make_queries(Q, seed):
+    g = torch.Generator().manual_seed(1000 + seed)
+    Xq = 4 * torch.rand(Q, N_DIM, dtype=torch.float64, generator=g) - 2
+    Uq = 2 * torch.rand(Q, M_DIM, dtype=torch.float64, generator=g) - 1
+    return Xq, Uq
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(',')]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
+                                     parts[3:7]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- CPU legs
+def oracle_hyper(hyp):
+    from oracle import mvgp_oracle as O
+    return O.Hyper(hyp['lengthscale'], hyp['outputscale'], hyp['A'], hyp['B'], hyp['C'])
+
+
+def cpu_fit(hyp, X, U, Xdot, jitter):
+    """Gram + jittered Cholesky (control_affine_model.py:366-377, 899-921) on the host cores; returns (L, seconds)."""
+    from oracle import mvgp_oracle as O
+    h = oracle_hyper(hyp)
+    t0 = time.perf_counter()
+    L = O.perturbed_cholesky(h, X, O.homogeneous(U), [jitter])
+    return L, time.perf_counter() - t0
+
+
+def cpu_queries(hyp, X, U, Xdot, L, Xq, Uq, chunk=1024):
+    from oracle import mvgp_oracle as O
+    h = oracle_hyper(hyp)
+    t0 = time.perf_counter()
+    out = O.posterior_blocks(h, X, U, Xdot, L, Xq, Uq, chunk=chunk)
+    return out, time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    """The reference's algorithm (restated op for op in oracle/; the reference itself is pure Python over a
+    gpytorch fork that cannot be installed here) on the host cores, all threads, same workload config."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    N = args.n_train
+    X, U, Xdot, hyp, jitter = make_workload(N)
+    L, fit_s = cpu_fit(hyp, X, U, Xdot, jitter)
+    qs = args.ref_queries_per_step
+    times = []
+    for s in range(args.warmup + args.steps):
+        Xq, Uq = make_queries(qs, s)
+        _, dt = cpu_queries(hyp, X, U, Xdot, L, Xq, Uq, chunk=qs)
+        if s >= args.warmup:
+            times.append(dt)
+    total = float(sum(times))
+    value = qs * len(times) / total
+    sample = ("N=%d factor built once on the host (%.2f s: Gram + jittered Cholesky), then %d steps of %d queries "
+              "(multi-RHS triangular solve + per-query 3x3 blocks, float64)" % (N, fit_s, len(times), qs))
+    line = dict(impl='reference', metric='posterior queries/sec (mean+cov of F(x)u) at N train pts', value=value,
+                unit='queries/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f64', data='synthetic',
+                config=dict(workload='synthetic unicycle MVGP fit N=%d + batched posterior query (BASELINE configs[3])' % N,
+                            n_train=N, n=N_DIM, m=M_DIM, queries_per_step=qs,
+                            note='bounded CPU sample of the same workload; inputs larger than L2/LLC'),
+                fit_s=fit_s,
+                cpu_baseline=dict(value=value, unit='queries/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=value, unit='queries/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def measure_dgemm_peak(device):
+    """cuBLAS DGEMM 8192^3 on this GPU: the FP64 tensor-pipe roofline denominator (MEASURED_PEAKS.json has no
+    FP64 entry).  Library call, used ONLY as the denominator."""
+    n = 8192
+    a = torch.randn(n, n, device=device, dtype=torch.float64)
+    b = torch.randn(n, n, device=device, dtype=torch.float64)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2 * n ** 3 / best * 1e-9
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from bayesian_cbf_b200 import _lib
+    from bayesian_cbf_b200.model import MVGPModel, make_hyper
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    N, QS, K, W = args.n_train, args.queries_per_step, args.steps, args.warmup
+    X, U, Xdot, hyp, jitter = make_workload(N)
+    hyper = make_hyper(N_DIM, P_DIM, hyp['lengthscale'].numpy(), float(hyp['outputscale']), hyp['A'].numpy(),
+                       hyp['B'].numpy(), hyp['C'].numpy())
+    model = MVGPModel(local_rank)
+
+    # ---- fit (Gram + jittered Cholesky + L^-1 + alpha): rank 0 factorises, NCCL broadcasts the state ----------
+    fit = dict()
+    t0 = time.perf_counter()
+    if rank == 0:
+        model.fit(hyper, X.numpy(), U.numpy(), Xdot.numpy(), jitter.numpy(), 1e-5)
+        fit = model.fit_timing_ms()
+    else:
+        model.alloc_state(hyper, N)
+    bcast_ms = 0.0
+    if world > 1:
+        st = model.state_tensors()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for key in ('Linv', 'alpha', 'G', 'W', 'X'):
+            dist.broadcast(st[key], src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+    fit_wall_s = time.perf_counter() - t0
+
+    # ---- queries: weak scaling, every rank runs K steps of QS queries on its own shard -------------------------
+    steps_total = W + K
+    Xq_all, Uq_all = make_queries(QS * steps_total, 7919 * rank)
+    Xq_d, Uq_d = Xq_all.to(dev), Uq_all.to(dev)   # resident in HBM before the timed region
+    outs = None
+
+    def step(i):
+        s = slice(i * QS, (i + 1) * QS)
+        return model.query_device(Xq_d[s], Uq_d[s])
+
+    for i in range(W):
+        outs = step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.bcbf_profile_enable(1)
+    launches0 = lib.bcbf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(W, W + K):
+        outs = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.bcbf_launch_count() - launches0
+    import ctypes
+    kms, kn = ctypes.c_double(), ctypes.c_int()
+    lib.bcbf_profile_read(ctypes.byref(kms), ctypes.byref(kn))
+    lib.bcbf_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else {}
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    checksum = float(outs['svar'].sum().item())
+
+    # ---- e2e: same metric through the C ABI with HOST buffers (pinned), copies inside the timed region ----------
+    pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory()
+    hXq, hUq = pin(QS, N_DIM), pin(QS, M_DIM)
+    hmean, hsvar, hMk, hBk = pin(QS, N_DIM), pin(QS), pin(QS, N_DIM, P_DIM), pin(QS, P_DIM, P_DIM)
+    Ke = max(2, min(K, args.e2e_steps))
+    e2e_times = []
+    for i in range(W + Ke):
+        s = slice((i % steps_total) * QS, (i % steps_total + 1) * QS)
+        hXq.copy_(Xq_all[s])
+        hUq.copy_(Uq_all[s])
+        if world > 1:
+            dist.barrier()
+        t1 = time.perf_counter()
+        model.query_into(hXq.numpy(), hUq.numpy(), hmean.numpy(), hsvar.numpy(), hMk.numpy(), hBk.numpy())
+        dt = time.perf_counter() - t1      # bcbf_model_query is synchronous (stream sync inside)
+        if i >= W:
+            e2e_times.append(dt)
+    te = torch.tensor([sum(e2e_times)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * QS * len(e2e_times) / float(te.item())
+    h2d = QS * (N_DIM + M_DIM) * 8
+    d2h = QS * (N_DIM + 1 + N_DIM * P_DIM + P_DIM * P_DIM) * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (post_var_kernel: N^2 p flops per query) ---------------------
+    flops_per_launch = float(N) * N * P_DIM * QS
+    kernel_ms = kms.value / max(kn.value, 1)
+    achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
+    peak_live = measure_dgemm_peak(dev)
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'post_var_ncu_summary.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+    roofline = dict(bound='tensor', achieved=achieved, peak=peak_live, unit='TFLOP/s', frac=achieved / peak_live,
+                    traffic=traffic, kernel='post_var_kernel', kernel_ms=kernel_ms,
+                    kernel_share_of_step=kms.value / ms,
+                    algorithmic_flops_per_launch=flops_per_launch,
+                    peak_source='cuBLAS DGEMM 8192^3 measured live on this GPU (FP64 tensor pipe; MEASURED_PEAKS.json '
+                                'has no FP64 entry; DMMA instruction peak measured 37.1 TFLOP/s, profiles/r01_fp64_peaks.txt)')
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 only, N=1 only --------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        Lc, cfit_s = cpu_fit(hyp, X, U, Xdot, jitter)
+        qs = args.cpu_sample_queries
+        (cMk, cBk, cmean, csvar), cq_s = cpu_queries(hyp, X, U, Xdot, Lc, Xq_all[:qs], Uq_all[:qs], chunk=qs)
+        # parity spot-check of the benchmarked path against the oracle on the sample
+        got = model.query(Xq_all[:qs].numpy(), Uq_all[:qs].numpy())
+        prior = float(hyp['outputscale'] * torch.linalg.matrix_norm(hyp['B'], 2))
+        parity = dict(Bk_rel=float(np.abs(got['Bk'] - cBk.numpy()).max() / prior),
+                      svar_rel=float(np.abs(got['svar'] - csvar.numpy()).max() / prior),
+                      mean_rel=float(np.abs(got['mean'] - cmean.numpy()).max() / max(1e-300, np.abs(cmean.numpy()).max())))
+        cpu = dict(value=qs / cq_s, unit='queries/s', cores=cores, kind='port',
+                   sample='N=%d: host Gram + Cholesky once (%.2f s), then %d queries in %.2f s (multi-RHS triangular '
+                          'solve + per-query blocks, torch float64, %d threads)' % (N, cfit_s, qs, cq_s, cores),
+                   fit_s=cfit_s, parity_vs_gpu=parity)
+
+    line = dict(metric='posterior queries/sec (mean+cov of F(x)u) at N train pts', value=world * QS * K / (ms_max * 1e-3),
+                unit='queries/s', n_gpus=world, steps=K, warmup=W, ms_per_step=ms_max / K, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+                config=dict(workload='synthetic unicycle MVGP fit N=%d + batched posterior query, %d queries/step/GPU '
+                                     '(BASELINE configs[3]; 53 steps = 1.004M queries)' % (N, QS),
+                            n_train=N, n=N_DIM, m=M_DIM, queries_per_step=QS, outputs='M_k(3x3), B_k(3x3), mean(3), svar',
+                            parallelism='queries sharded, factor broadcast once (NCCL)' if world > 1 else 'single GPU',
+                            l2='inputs larger than L2: L^-1 is %.2f GB (lower triangle), streamed every step' % (4.0 * N * (N + 1) / 1e9)),
+                fit_ms=fit.get('total'), fit_breakdown_ms=fit, fit_wall_s=fit_wall_s, factor_broadcast_ms=bcast_ms,
+                clocks=dict(sm_mhz=clocks.get('sm_mhz'), sm_max_mhz=clocks.get('sm_max_mhz'), reasons=clocks.get('reasons', []),
+                            samples=clocks.get('samples', 0)),
+                e2e=dict(value=e2e_value, unit='queries/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=len(e2e_times)),
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, checksum_svar=checksum)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=53)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n-train', type=int, default=16384)
+    ap.add_argument('--queries-per-step', type=int, default=18944)
+    ap.add_argument('--e2e-steps', type=int, default=8)
+    ap.add_argument('--cpu-sample-queries', type=int, default=2048)
+    ap.add_argument('--ref-queries-per-step', type=int, default=1024)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

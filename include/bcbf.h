@@ -37,6 +37,12 @@ extern "C" {
 
 const char* bcbf_last_error(void);
 int bcbf_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches claim). */
+unsigned long long bcbf_launch_count(void);
+/* CUDA-event timing of the dominant kernel (post_var_kernel, the N^2 p contraction): enable clears the history;
+ * read synchronises and returns the summed device time and the number of launches since enable.            */
+int bcbf_profile_enable(int on);
+int bcbf_profile_read(double* total_ms, int* launches);
 /* N rounded up to the block size the kernels tile by. */
 int bcbf_padded(int N);
 /* Bytes of scratch bcbf_potrf/bcbf_trtri need for a factor of padded size Npad. */
