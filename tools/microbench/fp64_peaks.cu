@@ -34,6 +34,29 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
   for(int j=0;j<NACC;j++) s+=c[j];
   out[blockIdx.x*blockDim.x+threadIdx.x]=s;
 }
+// DMMA and DFMA interleaved in one instruction stream: if the two share the FP64 datapath the time is the SUM of
+// the separate times, if they are separate pipes it is the MAX (decides whether CUDA-core FMAs are "free" next to DMMA).
+__global__ void __launch_bounds__(256) mixed_kernel(double* out, int iters, double a, double b){
+  double ma=threadIdx.x*1e-3, mb=threadIdx.x*2e-3;
+  double c[8][2], f[16];
+  #pragma unroll
+  for(int j=0;j<8;j++){c[j][0]=0;c[j][1]=0;}
+  #pragma unroll
+  for(int j=0;j<16;j++) f[j]=threadIdx.x+j;
+  for(int i=0;i<iters;i++){
+    #pragma unroll
+    for(int j=0;j<8;j++){
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[j][0]),"+d"(c[j][1]) : "d"(ma),"d"(mb));
+      f[2*j]=fma(f[2*j],a,b); f[2*j+1]=fma(f[2*j+1],a,b);
+    }
+  }
+  double s=0;
+  #pragma unroll
+  for(int j=0;j<8;j++) s+=c[j][0]+c[j][1];
+  #pragma unroll
+  for(int j=0;j<16;j++) s+=f[j];
+  out[blockIdx.x*blockDim.x+threadIdx.x]=s;
+}
 __global__ void __launch_bounds__(256) exp_kernel(double* out, int iters, double a){
   double x0=-(threadIdx.x%97)*0.01, s=0;
   for(int i=0;i<iters;i++){ s+=exp(x0); x0-=a; }
@@ -65,6 +88,12 @@ int main(){
     }
     fl=(double)grid*256*iters*16*2.0;
     printf("DFMA NACC=16 ctas/sm=%d: %.3f ms  %.2f TFLOP/s\n",ctas_per_sm,ms,fl/ms*1e-9);
+    for(int rep=0;rep<3;rep++){
+      cudaEventRecord(e0); mixed_kernel<<<grid,256>>>(out,iters,1.0000001,1e-9); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+      cudaEventElapsedTime(&ms,e0,e1);
+    }
+    printf("MIXED 8 DMMA + 16 DFMA per iter ctas/sm=%d: %.3f ms  DMMA part %.2f TFLOP/s + DFMA part %.2f TFLOP/s\n",ctas_per_sm,ms,
+           (double)grid*8*iters*8*512.0/ms*1e-9,(double)grid*256*iters*16*2.0/ms*1e-9);
     for(int rep=0;rep<3;rep++){
       cudaEventRecord(e0); exp_kernel<<<grid,256>>>(out,2000,1e-4); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
       cudaEventElapsedTime(&ms,e0,e1);
