@@ -185,7 +185,7 @@ int dev_alloc(T** p, size_t count) {
 
 int query_batch(int p) {
   // queries per device batch: 4 waves of one CTA per SM (148 SMs) with the posterior kernel's TQ
-  const int tq = (p == 1) ? 96 : (p == 2 ? 48 : 32);
+  const int tq = (p == 1) ? 96 : (p == 2 ? 64 : 32);
   return 148 * tq * 4;
 }
 }  // namespace
@@ -346,7 +346,7 @@ extern "C" int bcbf_model_state(bcbf_model* m, int* N, int* Npad, double** L, do
 
 static int ensure_query_capacity(bcbf_model* m, int Qb) {
   const int Npad = m->Npad;
-  const int ldks = ((Qb + 95) / 96) * 96;
+  const int ldks = ((Qb + 191) / 192) * 192;
   int rc;
   if ((size_t)Qb > m->cap_Q) {
     if ((rc = dev_alloc(&m->Xq, (size_t)Qb * BCBF_MAX_N_DIM))) return rc;
@@ -369,7 +369,7 @@ static int ensure_query_capacity(bcbf_model* m, int Qb) {
 static int query_batch_device(bcbf_model* m, const double* dXq, const double* dUq, int Qb, double* dmean, double* dsvar,
                               double* dMk, double* dBk, cudaStream_t s) {
   const int n = m->hyp.n, p = m->hyp.p, Npad = m->Npad, N = m->N;
-  const int ldks = ((Qb + 95) / 96) * 96;
+  const int ldks = ((Qb + 191) / 192) * 192;
   int rc = bcbf_cross_gram(m->X, dXq, m->hyp.lengthscale, m->hyp.outputscale, N, Qb, n, m->Kstar, ldks, Npad, s);
   if (rc) return rc;
   double* Mk = dMk ? dMk : m->Mk;

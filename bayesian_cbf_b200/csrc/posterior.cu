@@ -21,172 +21,185 @@
 
 namespace bcbf {
 
-constexpr int kPA_Stride = 20;                  // A tile row stride (16 + 4 pad doubles)
-constexpr int kPA_Elems = 128 * kPA_Stride;     // 2560
-constexpr int kPStages = 3;
-constexpr int kPThreads = 256;
+constexpr int kPBK = 32;                        // k extent of one pipeline stage
+constexpr int kPA_Stride = kPBK + 4;            // A tile row stride in doubles (== 4 mod 16: conflict-free fragments)
+constexpr int kPA_Elems = 128 * kPA_Stride;     // 4608
+constexpr int kPMmaWarps = 8;                   // consumer warps: 2 (rows) x 4 (query groups), 64 x (P*H*8) each
+constexpr int kPProdWarps = 1;                  // producer warp: streams L^-1, K* and G tiles with cp.async
+constexpr int kPThreads = 32 * (kPMmaWarps + kPProdWarps);
 
-template <int P_, int QW_, bool FOLD_>
+// P = columns per query; H = 8-query fragments per warp; GMUL: B operand = K*[k,t] * G[k,q] formed in registers
+// (false: the K* operand is used as is — fold-in form, where kb* already carries the (G . uh) factor).
+template <int P_, int H_, bool GMUL_>
 struct PostCfg {
-  static constexpr int P = P_;                       // columns per query (p, or 1 when u is folded in)
-  static constexpr int QW = QW_;                     // queries per warp column (multiple of 8)
-  static constexpr bool FOLD = FOLD_;
-  static constexpr int TQ = 2 * QW;                  // queries per CTA
-  static constexpr int BN = P * TQ;                  // tile columns
-  static constexpr int H = QW / 8;                   // n-fragments per (warp, q)
+  static constexpr int P = P_;
+  static constexpr int H = H_;
+  static constexpr bool GMUL = GMUL_;
+  static constexpr int QW = 8 * H;                   // queries per warp column
+  static constexpr int TQ = 4 * QW;                  // queries per CTA
   static constexpr int NF = P * H;                   // n-fragments per warp
-  static constexpr int BStride = BN + 4;             // == 4 (mod 16): conflict-free fragment reads
-  static constexpr int BElems = 16 * BStride;
+  static constexpr int KStride = TQ + 4;             // == 4 (mod 16): conflict-free fragment reads
+  static constexpr int KElems = kPBK * KStride;
+  static constexpr int GElems = kPBK * 4;            // packed G rows of the stage (32 * p doubles, p <= 4)
   static constexpr int NPair = P * (P + 1) / 2;
-  static constexpr int StageElems = kPA_Elems + BElems;
-  static constexpr int NChunk = (8 * TQ + kPThreads - 1) / kPThreads;  // double2 Kstar chunks per thread/stage
-  static constexpr int SmemBytes = (kPStages * StageElems + 4 * TQ * NPair) * (int)sizeof(double);
-  static_assert(BN % 16 == 0, "tile width must keep the padded stride at 4 mod 16");
-  static_assert(QW % 8 == 0, "");
+  static constexpr int StageElems = kPA_Elems + KElems + GElems;
+  static constexpr int Stages = (TQ <= 32) ? 4 : 3;
+  static constexpr int SmemBytes = (Stages * StageElems + 2 * TQ * NPair) * (int)sizeof(double) + 64;
+  static_assert(TQ % 16 == 0, "tile width must keep the padded stride at 4 mod 16");
+  static_assert(SmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
 struct PostArgs {
   const double* Linv; int ld; int Npad;
-  const double* Kstar; int ldks;
-  const double* G;       // (Npad, pg) row-major, pad rows zero
-  int pg;                // true p (row length of G / UHq)
-  const double* UHq;     // (Q, pg) fold-in mode only
+  const double* Kstar; int ldks;   // (Npad, ldks): K* (GMUL) or kb* (fold-in)
+  const double* G;       // (Npad, P) row-major, pad rows zero (GMUL only)
   int Q;
   double* Spart;         // [nsplit][Qpad][NPair] partial Gram sums
   int Qpad; int nsplit;
 };
 
+// ---- mbarrier helpers (CTA-scope producer/consumer pipeline; no __syncthreads in the steady state) ------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrival that fires when all cp.async issued so far by this thread have landed (counted in the init count: .noinc)
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra WAIT_DONE;\n"
+      " bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+// Warp-specialised persistent kernel.  Warps 0..7 issue DMMA only (plus NF DMULs per 8*NF DMMAs to form the frakB
+// fragments); warp 8 streams every operand with cp.async.  Stage s of the ring is handed over with full[s]
+// (32 cp.async-completion arrivals) and returned with empty[s] (one arrival per MMA warp).
 template <class Cfg>
 __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
-  constexpr int P = Cfg::P, QW = Cfg::QW, TQ = Cfg::TQ, H = Cfg::H, NF = Cfg::NF, BS = Cfg::BStride;
-  constexpr int NPair = Cfg::NPair, NCH = Cfg::NChunk;
+  constexpr int P = Cfg::P, QW = Cfg::QW, TQ = Cfg::TQ, H = Cfg::H, NF = Cfg::NF, KS = Cfg::KStride;
+  constexpr int NPair = Cfg::NPair, S = Cfg::Stages;
   extern __shared__ __align__(16) double smem[];
-  double* Ssm = smem + kPStages * Cfg::StageElems;  // [4][TQ][NPair]
+  double* Ssm = smem + S * Cfg::StageElems;  // [2][TQ][NPair]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(Ssm + 2 * TQ * NPair);
+  unsigned long long* empty = full + S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;
-  const int lr = lane >> 2, lk = lane & 3;
   const int q0 = blockIdx.x * TQ;
   const int nb = a.Npad / kBlk;
   const int split = blockIdx.y, nsplit = a.nsplit;
+  constexpr int kStagesPerBlk = kBlk / kPBK;  // 4
 
-  for (int i = tid; i < 4 * TQ * NPair; i += kPThreads) Ssm[i] = 0.0;
+  for (int i = tid; i < 2 * TQ * NPair; i += kPThreads) Ssm[i] = 0.0;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 32);
+      mbar_init(empty + s, kPMmaWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
-  // ---- iteration space: row blocks I = split, split+nsplit, ... ; stages kt in [0, (I+1)*8) ----------
-  auto block_stages = [](int I) { return (I + 1) * (kBlk / 16); };
-  long long total = 0;
-  for (int I = split; I < nb; I += nsplit) total += block_stages(I);
-
-  struct Cursor { int I, kt; };
-  auto advance = [&](Cursor& c) {
-    if (++c.kt == block_stages(c.I)) { c.kt = 0; c.I += nsplit; }
-  };
+  // iteration space: row blocks I = split, split+nsplit, ... ; stages kt in [0, (I+1)*4)
   auto stA = [&](int s) { return smem + s * Cfg::StageElems; };
-  auto stB = [&](int s) { return smem + s * Cfg::StageElems + kPA_Elems; };
+  auto stK = [&](int s) { return smem + s * Cfg::StageElems + kPA_Elems; };
+  auto stG = [&](int s) { return smem + s * Cfg::StageElems + kPA_Elems + Cfg::KElems; };
 
-  auto loadA = [&](const Cursor& c, int slot) {
-    const double* g = a.Linv + (long long)c.I * kBlk * a.ld + c.kt * 16;
-    double* s = stA(slot);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int ch = tid + i * kPThreads;
-      int row = ch >> 3, kc = (ch & 7) * 2;
-      cp_async16(s + row * kPA_Stride + kc, g + (long long)row * a.ld + kc, true);
-    }
-  };
-
-  // B-operand producer: registers <- Kstar / G (global), then registers -> shared tile
-  double2 kv[NCH];
-  double gq[NCH][Cfg::FOLD ? 1 : P];
-  auto ldgB = [&](const Cursor& c) {
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      int ch = tid + i * kPThreads;
-      if (ch < 8 * TQ) {
-        int k = ch / (TQ / 2), t2 = (ch % (TQ / 2)) * 2;
-        int row = c.kt * 16 + k;
-        kv[i] = *reinterpret_cast<const double2*>(a.Kstar + (long long)row * a.ldks + q0 + t2);
-        if (Cfg::FOLD) {
-          // (G[row] . uh[t]) for the two queries of this chunk is folded into kv directly
-          double g0 = 0.0, g1 = 0.0;
-          for (int j = 0; j < a.pg; ++j) {
-            double g = a.G[(long long)row * a.pg + j];
-            int qa = min(q0 + t2, a.Q - 1), qb = min(q0 + t2 + 1, a.Q - 1);
-            g0 = fma(g, a.UHq[(long long)qa * a.pg + j], g0);
-            g1 = fma(g, a.UHq[(long long)qb * a.pg + j], g1);
+  if (warp == kPMmaWarps) {
+    // ================= producer: L^-1[I rows, k..k+32) -> As[128][36]; K*[k..k+32, q0..q0+TQ) -> Ks[32][TQ+4];
+    //                   G[k..k+32, :] -> Gs (packed) ===============================================================
+    int slot = 0;
+    unsigned phase = 0;
+    const double* gK0 = a.Kstar + q0;
+    for (int I = split; I < nb; I += nsplit) {
+      const double* gI = a.Linv + (long long)I * kBlk * a.ld;
+      const int nst = (I + 1) * kStagesPerBlk;
+      for (int kt = 0; kt < nst; ++kt) {
+        mbar_wait(empty + slot, phase ^ 1u);
+        {
+          double* s = stA(slot);
+          const double* g = gI + kt * kPBK + (long long)(lane >> 4) * a.ld + (lane & 15) * 2;
+          double* sd = s + (lane >> 4) * kPA_Stride + (lane & 15) * 2;
+          // 128 rows x 16 chunks of 16 B: lane -> (row = it*2 + lane/16, chunk = lane%16)
+#pragma unroll 8
+          for (int it = 0; it < 64; ++it)
+            cp_async16(sd + it * 2 * kPA_Stride, g + (long long)it * 2 * a.ld, true);
+        }
+        {
+          double* s = stK(slot);
+          const double* g = gK0 + (long long)kt * kPBK * a.ldks;
+          constexpr int CPR = TQ / 2;  // 16-byte chunks per k row
+#pragma unroll 4
+          for (int it = 0; it < kPBK * CPR / 32; ++it) {
+            const int ch = it * 32 + lane, k = ch / CPR, c2 = (ch % CPR) * 2;
+            cp_async16(s + k * KS + c2, g + (long long)k * a.ldks + c2, true);
           }
-          kv[i].x *= g0;
-          kv[i].y *= g1;
-          gq[i][0] = 1.0;
-        } else {
-#pragma unroll
-          for (int q = 0; q < P; ++q) gq[i][q] = a.G[(long long)row * P + q];
         }
+        if (Cfg::GMUL) {
+          double* s = stG(slot);
+          const double* g = a.G + (long long)kt * kPBK * P;
+          for (int ch = lane; ch < kPBK * P / 2; ch += 32) cp_async16(s + ch * 2, g + ch * 2, true);
+        }
+        mbar_arrive_cp_async(full + slot);
+        if (++slot == S) { slot = 0; phase ^= 1u; }
       }
     }
-  };
-  auto stsB = [&](int slot) {
-    double* s = stB(slot);
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      int ch = tid + i * kPThreads;
-      if (ch < 8 * TQ) {
-        int k = ch / (TQ / 2), t2 = (ch % (TQ / 2)) * 2;
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-          double g = Cfg::FOLD ? 1.0 : gq[i][q];
-          *reinterpret_cast<double2*>(s + k * BS + q * TQ + t2) = make_double2(kv[i].x * g, kv[i].y * g);
-        }
-      }
-    }
-  };
-
-  double acc[4][NF][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int f = 0; f < NF; ++f) acc[i][f][0] = acc[i][f][1] = 0.0;
-
-  Cursor cl{split, 0};  // loader cursor (A, runs 2 stages ahead)
-  Cursor cb{split, 0};  // B producer cursor
-  Cursor cc{split, 0};  // consumer cursor
-  // prologue
-  if (total > 0) { loadA(cl, 0); advance(cl); }
-  cp_async_commit();
-  if (total > 1) { loadA(cl, 1); advance(cl); }
-  cp_async_commit();
-  if (total > 0) { ldgB(cb); advance(cb); stsB(0); }
-  if (total > 1) { ldgB(cb); advance(cb); }
-
-  for (long long s = 0; s < total; ++s) {
-    cp_async_wait<1>();
-    __syncthreads();
-    const int slot = (int)(s % kPStages);
-    if (s + 2 < total) { loadA(cl, (int)((s + 2) % kPStages)); advance(cl); }
     cp_async_commit();
-    if (s + 1 < total) stsB((int)((s + 1) % kPStages));
-    if (s + 2 < total) { ldgB(cb); advance(cb); }
-
-    const double* As = stA(slot);
-    const double* Bs = stB(slot);
+    cp_async_wait<0>();
+  } else {
+    // ================= consumers: DMMA on the staged tiles ====================================================
+    const int wm = warp >> 2, wn = warp & 3;
+    const int lr = lane >> 2, lk = lane & 3;
+    double acc[8][NF][2];
 #pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-      const int kk = k4 * 4 + lk;
-      double af[4], bf[NF];
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = As[(wm * 32 + i * 8 + lr) * kPA_Stride + kk];
+      for (int f = 0; f < NF; ++f) acc[i][f][0] = acc[i][f][1] = 0.0;
+    int slot = 0;
+    unsigned phase = 0;
+    for (int I = split; I < nb; I += nsplit) {
+      const int nst = (I + 1) * kStagesPerBlk;
+      for (int kt = 0; kt < nst; ++kt) {
+        mbar_wait(full + slot, phase);
+        const double* As = stA(slot) + (wm * 64 + lr) * kPA_Stride + lk;
+        const double* Ks = stK(slot) + lk * KS + wn * QW + lr;
+        const double* Gs = stG(slot) + lk * P;
 #pragma unroll
-      for (int q = 0; q < P; ++q)
+        for (int k4 = 0; k4 < kPBK / 4; ++k4) {
+          double af[8], kq[H], bf[NF];
 #pragma unroll
-        for (int h = 0; h < H; ++h) bf[q * H + h] = Bs[kk * BS + q * TQ + wn * QW + h * 8 + lr];
+          for (int i = 0; i < 8; ++i) af[i] = As[i * 8 * kPA_Stride + k4 * 4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+          for (int h = 0; h < H; ++h) kq[h] = Ks[k4 * 4 * KS + h * 8];
+          if (Cfg::GMUL) {
 #pragma unroll
-        for (int f = 0; f < NF; ++f) dmma884(acc[i][f][0], acc[i][f][1], af[i], bf[f]);
-    }
-
-    const bool last_of_block = (cc.kt + 1 == block_stages(cc.I));
-    if (last_of_block) {
-      // per-query Gram of this row block: sum over the warp's 32 rows of V[:,q] V[:,r]
+            for (int q = 0; q < P; ++q) {
+              const double g = Gs[k4 * 4 * P + q];
+#pragma unroll
+              for (int h = 0; h < H; ++h) bf[q * H + h] = kq[h] * g;
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < H; ++h) bf[h] = kq[h];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) dmma884(acc[i][f][0], acc[i][f][1], af[i], bf[f]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+        if (++slot == S) { slot = 0; phase ^= 1u; }
+      }
+      // per-query Gram of this row block: sum over the warp's 64 rows of V[:,q] V[:,r]
 #pragma unroll
       for (int h = 0; h < H; ++h)
 #pragma unroll
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
 #pragma unroll
           for (int e = 0; e < NPair; ++e) sp[e] = 0.0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 8; ++i) {
             int e = 0;
 #pragma unroll
             for (int q = 0; q < P; ++q)
@@ -218,19 +231,32 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
           }
         }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int f = 0; f < NF; ++f) acc[i][f][0] = acc[i][f][1] = 0.0;
     }
-    advance(cc);
   }
-  cp_async_wait<0>();
   __syncthreads();
   for (int i = tid; i < TQ * NPair; i += kPThreads) {
     int t = i / NPair, e = i % NPair;
-    double v = Ssm[(0 * TQ + t) * NPair + e] + Ssm[(1 * TQ + t) * NPair + e] + Ssm[(2 * TQ + t) * NPair + e] +
-               Ssm[(3 * TQ + t) * NPair + e];
+    double v = Ssm[(0 * TQ + t) * NPair + e] + Ssm[(1 * TQ + t) * NPair + e];
     a.Spart[((long long)split * a.Qpad + q0 + t) * NPair + e] = v;
+  }
+}
+
+// kb*[i, q] = K*[i, q] * (G[i,:] . UHq[q,:])   (fold-in form, control_affine_model.py:536)
+__global__ void fold_kbstar_kernel(const double* __restrict__ Kstar, int ldks, const double* __restrict__ G,
+                                   const double* __restrict__ UHq, int p, int Npad, int Q, int Qpad,
+                                   double* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.y * 64;
+  if (q >= Qpad) return;
+  double uh[BCBF_MAX_P_DIM];
+  for (int j = 0; j < p; ++j) uh[j] = (q < Q) ? UHq[(long long)q * p + j] : 0.0;
+  for (int i = i0; i < min(Npad, i0 + 64); ++i) {
+    double w = 0.0;
+    for (int j = 0; j < p; ++j) w = fma(G[(long long)i * p + j], uh[j], w);
+    out[(long long)i * Qpad + q] = (q < Q) ? Kstar[(long long)i * ldks + q] * w : 0.0;
   }
 }
 
@@ -328,12 +354,12 @@ struct Workspace {
   double* ptr = nullptr;
   size_t bytes = 0;
 };
-static Workspace g_ws[64];
+static Workspace g_ws[3][64];  // slot 0: Gram partials, 1: mean partials, 2: fold-in kb*
 
-static int get_workspace(size_t bytes, double** out) {
+static int get_workspace(int slot, size_t bytes, double** out) {
   int dev = 0;
   BCBF_CUDA(cudaGetDevice(&dev));
-  Workspace& w = g_ws[dev & 63];
+  Workspace& w = g_ws[slot][dev & 63];
   if (w.bytes < bytes) {
     if (w.ptr) BCBF_CUDA(cudaFree(w.ptr));
     w.ptr = nullptr;
@@ -382,25 +408,36 @@ static int pick_split(int tiles, int nb) {
   return s < 1 ? 1 : s;
 }
 
-static int var_dispatch(bool fold, int p, PostArgs& a, cudaStream_t stream) {
-  // (P, QW) -> TQ: p=1:96  p=2:48  p=3:32  p=4:32 ; fold-in: 96.  Fills a.Qpad / a.nsplit / a.Spart.
-  const int TQ = (fold || p == 1) ? 96 : (p == 2 ? 48 : 32);
+static int var_dispatch(bool fold, int p, PostArgs& a, const double* UHq, cudaStream_t stream) {
+  // queries per CTA: p=1 / fold-in: 96, p=2: 64, p=3,4: 32.  Fills a.Qpad / a.nsplit / a.Spart.
+  const int TQ = (fold || p == 1) ? 96 : (p == 2 ? 64 : 32);
   a.Qpad = ((a.Q + TQ - 1) / TQ) * TQ;
   BCBF_REQUIRE(a.ldks >= a.Qpad,
-               "posterior: Kstar leading dimension %d < padded query count %d (pad to a multiple of 96)", a.ldks,
+               "posterior: Kstar leading dimension %d < padded query count %d (pad to a multiple of 192)", a.ldks,
                a.Qpad);
   a.nsplit = pick_split(a.Qpad / TQ, a.Npad / kBlk);
   const int npair = fold ? 1 : p * (p + 1) / 2;
   double* ws = nullptr;
-  int rc = get_workspace(sizeof(double) * (size_t)a.nsplit * a.Qpad * npair, &ws);
+  int rc = get_workspace(0, sizeof(double) * (size_t)a.nsplit * a.Qpad * npair, &ws);
   if (rc != BCBF_OK) return rc;
   a.Spart = ws;
-  if (fold) return launch_post_var<PostCfg<1, 48, true>>(a, stream);
+  if (fold) {
+    // kb* = K* (.) (G UHq^T) once, then the p = 1 contraction on it
+    double* kb = nullptr;
+    rc = get_workspace(2, sizeof(double) * (size_t)a.Npad * a.Qpad, &kb);
+    if (rc != BCBF_OK) return rc;
+    fold_kbstar_kernel<<<dim3(ceil_div(a.Qpad, 128), ceil_div(a.Npad, 64)), 128, 0, stream>>>(
+        a.Kstar, a.ldks, a.G, UHq, p, a.Npad, a.Q, a.Qpad, kb);
+    BCBF_LAUNCH_CHECK();
+    a.Kstar = kb;
+    a.ldks = a.Qpad;
+    return launch_post_var<PostCfg<1, 3, false>>(a, stream);
+  }
   switch (p) {
-    case 1: return launch_post_var<PostCfg<1, 48, false>>(a, stream);
-    case 2: return launch_post_var<PostCfg<2, 24, false>>(a, stream);
-    case 3: return launch_post_var<PostCfg<3, 16, false>>(a, stream);
-    case 4: return launch_post_var<PostCfg<4, 16, false>>(a, stream);
+    case 1: return launch_post_var<PostCfg<1, 3, true>>(a, stream);
+    case 2: return launch_post_var<PostCfg<2, 2, true>>(a, stream);
+    case 3: return launch_post_var<PostCfg<3, 1, true>>(a, stream);
+    case 4: return launch_post_var<PostCfg<4, 1, true>>(a, stream);
     default: break;
   }
   set_last_error("posterior: p=%d unsupported", p);
@@ -423,20 +460,10 @@ static int run_mean(const double* Kstar, int ldks, const double* W, const double
   nsplit = ceil_div(N, rows_per_split);
   const int Qpad = qblocks * kMeanThreads;
   double* ws = nullptr;
-  // the variance path owns the front of the workspace; the mean partials live in their own allocation
-  static double* mean_ws[64] = {nullptr};
-  static size_t mean_ws_bytes[64] = {0};
-  int dev = 0;
-  BCBF_CUDA(cudaGetDevice(&dev));
-  size_t need = sizeof(double) * (size_t)nsplit * Qpad * nc;
-  if (mean_ws_bytes[dev & 63] < need) {
-    if (mean_ws[dev & 63]) BCBF_CUDA(cudaFree(mean_ws[dev & 63]));
-    mean_ws[dev & 63] = nullptr;
-    mean_ws_bytes[dev & 63] = 0;
-    BCBF_CUDA(cudaMalloc(&mean_ws[dev & 63], need));
-    mean_ws_bytes[dev & 63] = need;
+  {
+    int rc = get_workspace(1, sizeof(double) * (size_t)nsplit * Qpad * nc, &ws);
+    if (rc != BCBF_OK) return rc;
   }
-  ws = mean_ws[dev & 63];
   post_mean_partial_kernel<<<dim3(qblocks, nsplit), kMeanThreads, 0, stream>>>(Kstar, ldks, W, nc, N, Q,
                                                                                rows_per_split, ws, Qpad);
   BCBF_LAUNCH_CHECK();
@@ -460,8 +487,8 @@ extern "C" int bcbf_posterior_blocks(const double* Linv, int ld, int Npad, const
   }
   if (Bk) {
     PostArgs a{};
-    a.Linv = Linv; a.ld = ld; a.Npad = Npad; a.Kstar = Kstar; a.ldks = ldks; a.G = G; a.pg = p; a.UHq = nullptr; a.Q = Q;
-    int rc = var_dispatch(false, p, a, stream);
+    a.Linv = Linv; a.ld = ld; a.Npad = Npad; a.Kstar = Kstar; a.ldks = ldks; a.G = G; a.Q = Q;
+    int rc = var_dispatch(false, p, a, nullptr, stream);
     if (rc != BCBF_OK) return rc;
     post_var_finalize_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(a.Spart, a.Qpad, a.nsplit, Q, p, Bmat, kss, Bk,
                                                                    nullptr, nullptr);
@@ -480,8 +507,8 @@ extern "C" int bcbf_posterior_fu(const double* Linv, int ld, int Npad, const dou
   BCBF_REQUIRE(Npad > 0 && Npad % kBlk == 0 && ld >= Npad && ld % 2 == 0 && Q >= 1 && ldks % 2 == 0,
                "bcbf_posterior_fu: Npad=%d ld=%d Q=%d ldks=%d", Npad, ld, Q, ldks);
   PostArgs a{};
-  a.Linv = Linv; a.ld = ld; a.Npad = Npad; a.Kstar = Kstar; a.ldks = ldks; a.G = G; a.pg = p; a.UHq = UHq; a.Q = Q;
-  int rc = var_dispatch(true, p, a, stream);
+  a.Linv = Linv; a.ld = ld; a.Npad = Npad; a.Kstar = Kstar; a.ldks = ldks; a.G = G; a.Q = Q;
+  int rc = var_dispatch(true, p, a, UHq, stream);
   if (rc != BCBF_OK) return rc;
   post_var_finalize_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(a.Spart, a.Qpad, a.nsplit, Q, p, Bmat, kss, nullptr,
                                                                  UHq, svar);

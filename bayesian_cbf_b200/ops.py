@@ -31,7 +31,7 @@ def padded(N):
 
 
 def query_pad(Q):
-    return (Q + 95) // 96 * 96
+    return (Q + 191) // 192 * 192
 
 
 def gram_train(X, UH, B, lengthscale, outputscale, Npad=None):

@@ -61,7 +61,7 @@ def test_cross_gram_and_rbf_blocks():
     from bayesian_cbf_b200 import ops
     X, _, _, hyp, _, Xq, _ = _mk(2, 200, 3, 2, 70)
     Ks = ops.cross_gram(_d(X), _d(Xq), _d(hyp.lengthscale), float(hyp.outputscale))
-    assert Ks.shape == (256, 96)
+    assert Ks.shape == (256, 192)
     ref = O.rbf_ard(X, Xq, hyp.lengthscale, hyp.outputscale, direct=True)
     assert _relerr(Ks[:200, :70], ref) < 1e-14
     assert Ks.cpu()[200:].abs().max() == 0 and Ks.cpu()[:, 70:].abs().max() == 0
