@@ -47,6 +47,11 @@ _SIGNATURES = {
     'bcbf_dinv_elems': (c_longlong, [c_int]),
     'bcbf_gram_train': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     'bcbf_cross_gram': (c_int, [_P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    'bcbf_gram_ca': (c_int, [_P, _P, c_int, _P, _P, c_int, _P, _P, c_double, c_int, c_int, _P, c_int, _P]),
+    'bcbf_gemm': (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, c_double, _P, c_int, _P]),
+    'bcbf_gram_train_backward': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, c_int,
+                                         _P, c_longlong, _P, _P]),
+    'bcbf_gram_backward_layout': (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'bcbf_rbf_blocks': (c_int, [_P, _P, _P, c_double, c_int, c_int, c_int, _P, _P, _P, _P]),
     'bcbf_potrf': (c_int, [_P, c_int, c_int, c_int, _P, c_double, _P, _P, _P]),
     'bcbf_check_info': (c_int, [_P, _P]),
@@ -58,6 +63,7 @@ _SIGNATURES = {
     'bcbf_posterior_fu': (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, c_double, c_int, c_int, c_int,
                                   _P, _P, _P]),
     'bcbf_cbc1_terms': (c_int, [_P, _P, _P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    'bcbf_socp_factor': (c_int, [_P, c_int, c_int, c_double, _P, _P, _P, _P]),
     'bcbf_model_create': (c_int, [POINTER(c_void_p), c_int]),
     'bcbf_model_destroy': (None, [c_void_p]),
     'bcbf_model_fit': (c_int, [c_void_p, POINTER(Hyper), _P, _P, _P, c_int, _P, c_double]),

@@ -1,0 +1,744 @@
+"""Drop-in host API of the MVGP regressor — same class / method names, argument meaning, shapes and error behaviour as
+the reference's bayes_cbf/control_affine_model.py, with every N-sized computation running in the hand-written CUDA
+kernels of libbcbf.so (no CPU path: a regressor placed on a non-CUDA device raises at the first computation).
+
+    reference                                              here
+    ---------------------------------------------------    ---------------------------------------------------------
+    ControlAffineExactGP (:139-218)                        same name; parameters via gp_modules (gpytorch names)
+    ControlAffineRegressor.fit (:268-335)                  Adam + MultiStepLR on the fused GPU log marginal (mll.py)
+    _perturbed_cholesky[_compute], make_psd (:366-385,     fused Gram -> blocked DMMA Cholesky with the 10x jitter retry;
+        :899-921)                                          L and L^-1 cached under the reference's cache key
+    custom_predict (:390-613)                              control-affine cross Gram + L^-1 products (DMMA)
+    ControlAffineRegressorExact (:930-1096)                frakB Gram + L^-1 products; per-query block fast path
+    closures f_func_* / fu_func_* / covar_fu_f (:685-848)  same names (consumed by gp_algebra / cbc1 / cbc2)
+
+The random Cholesky jitter is drawn with `torch.rand` on the CPU generator (the reference draws it on the tensor's
+device, :907-910), so that a seeded CPU run of the reference and a seeded run of this class consume the same
+numbers; the jitter vectors can also be supplied explicitly (`set_jitter_source`) for parity tests.
+
+Extension (not in the reference, needed for the 1M-query workload where a (b,b,p,p) result is impossible):
+`custom_predict_blocks(X, U=None)` -> per-query M_k (b,n,p), B_k (b,p,p) [, mean (b,n), svar (b,)].
+"""
+import logging
+import warnings
+from functools import partial
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import autograd_ops, ops
+from ._lib import NotPositiveDefiniteError
+from .gp_algebra import GaussianProcess
+from .gp_modules import (ConstantMean, GammaPrior, IndexKernel, MultivariateNormalResult, RBFKernel, ScaleKernel)
+from .matrix_variate_multitask_kernel import HetergeneousMatrixVariateKernel, MatrixVariateIndexKernel
+from .matrix_variate_multitask_model import HetergeneousMatrixVariateMean
+from .misc import DynamicsModel, torch_kron
+from .mll import mvgp_log_marginal
+
+LOG = logging.getLogger(__name__)
+LOG.setLevel(logging.INFO)
+
+
+class CatEncoder:
+    """Encodes / decodes arrays by concatenation along the last axis (reference :74-100)."""
+
+    def __init__(self, *sizes):
+        self.sizes = list(sizes)
+
+    @classmethod
+    def from_data(cls, *arrays):
+        self = cls(*[A.shape[-1] for A in arrays])
+        return self, self.encode(*arrays)
+
+    def encode(self, *arrays):
+        if isinstance(arrays[0], torch.Tensor):
+            return torch.cat(arrays, dim=-1)
+        return np.concatenate(arrays, axis=-1)
+
+    def decode(self, X):
+        idxs = np.cumsum([0] + self.sizes)
+        return [X[..., s:e] for s, e in zip(idxs[:-1], idxs[1:])]
+
+    def state_dict(self):
+        return dict(sizes=self.sizes)
+
+    def load_state_dict(self, state_dict):
+        self.sizes = state_dict['sizes']
+
+
+class IdentityLikelihood(nn.Module):
+    """y = f(x) exactly (reference :103-136): `marginal` is the identity and `noise` reads 0."""
+
+    def __init__(self):
+        super().__init__()
+        self.min_possible_noise = 1e-6
+
+    @property
+    def noise(self):
+        return 0
+
+    @noise.setter
+    def noise(self, _):
+        LOG.warning("Ignore setting of noise")
+
+    def marginal(self, function_dist, *params, **kwargs):
+        return function_dist
+
+    def forward(self, function_dist, *params, **kwargs):
+        return function_dist
+
+
+class ControlAffineExactGP(nn.Module):
+    """Heterogeneous MVGP model (reference :139-218): MXU = [M, X, UH]; M = 1 rows observe F(x)[1;u], M = 0 rows F(x)."""
+
+    def __init__(self, x_dim, u_dim, likelihood, rank=None, gamma_length_scale_prior=None):
+        super().__init__()
+        self.likelihood = likelihood
+        self.matshape = (1 + u_dim, x_dim)
+        self.decoder = CatEncoder(1, x_dim, 1 + u_dim)
+        self.mean_module = HetergeneousMatrixVariateMean(ConstantMean(), self.decoder, self.matshape)
+        self.task_covar = MatrixVariateIndexKernel(
+            IndexKernel(num_tasks=self.matshape[1], rank=(self.matshape[1] if rank is None else rank)),
+            IndexKernel(num_tasks=self.matshape[0], rank=(self.matshape[0] if rank is None else rank)))
+        prior = None if gamma_length_scale_prior is None else GammaPrior(*gamma_length_scale_prior)
+        self.input_covar = ScaleKernel(RBFKernel(ard_num_dims=x_dim, lengthscale_prior=prior))
+        self.covar_module = HetergeneousMatrixVariateKernel(self.task_covar, self.input_covar, self.decoder)
+        self.train_inputs = None
+        self.train_targets = None
+
+    def set_train_data(self, Xtrain, Utrain, XdotTrain):
+        assert self.matshape == (1 + Utrain.shape[-1], Xtrain.shape[-1])
+        assert Xtrain.shape[-1] == XdotTrain.shape[-1]
+        _, MXUtrain = self.encode_from_XU(Xtrain, Utrain, 1)
+        self.train_inputs = (MXUtrain,)
+        self.train_targets = XdotTrain.reshape(-1)
+
+    def encode_from_XU(self, Xtrain, Utrain=None, M=0):
+        Mtrain = Xtrain.new_full([Xtrain.size(0), 1], M)
+        if M:
+            assert Utrain is not None
+            UHtrain = torch.cat([Mtrain, Utrain], dim=1)
+        else:
+            UHtrain = Xtrain.new_zeros((Xtrain.size(0), self.matshape[0]))
+        return CatEncoder.from_data(Mtrain, Xtrain, UHtrain)
+
+    def forward(self, mxu):
+        return MultivariateNormalResult(self.mean_module(mxu), self.covar_module(mxu))
+
+    def state_dict(self, *a, **k):
+        return dict(matshape=self.matshape,
+                    decoder=self.decoder.state_dict(),
+                    mean_module=self.mean_module.state_dict(),
+                    task_covar=nn.Module.state_dict(self.task_covar),
+                    input_covar=nn.Module.state_dict(self.input_covar),
+                    train_inputs=self.train_inputs,
+                    train_targets=self.train_targets)
+
+    def load_state_dict(self, state_dict, *a, **k):
+        sd = dict(state_dict)
+        self.matshape = sd.pop('matshape')
+        self.train_inputs = sd.pop('train_inputs')
+        self.train_targets = sd.pop('train_targets')
+        self.decoder.load_state_dict(sd['decoder'])
+        self.mean_module.load_state_dict(sd['mean_module'])
+        self.task_covar.load_state_dict(sd['task_covar'])
+        self.input_covar.load_state_dict(sd['input_covar'])
+        return self
+
+
+def default_device():
+    return 'cuda' if torch.cuda.is_available() else 'cpu'
+
+
+def _need_cuda(device):
+    if torch.device(device).type != 'cuda':
+        raise RuntimeError("bayesian_cbf_b200: the MVGP path runs on a CUDA device only (no CPU fallback); this "
+                           "regressor lives on %r" % (device,))
+
+
+def _draw_jitter(n, dtype):
+    """One U(0,1)^n draw from the CPU generator (reference make_psd :907-910 draws `torch.rand` per attempt)."""
+    return torch.rand(n, dtype=dtype)
+
+
+def make_psd(Kb, cholesky_tries=10, cholesky_perturb_init=1e-5, cholesky_perturb_scale=10, jitters=None):
+    """Kb + factor * diag(U(0,1)) with the reference's retry schedule (:899-921); returns (Kbp, lower factor).
+    Kb is a CUDA tensor (n, n); the factorisation is the blocked DMMA Cholesky.  `jitters`: optional iterator of
+    explicit U(0,1)^n vectors (parity tests)."""
+    _need_cuda(Kb.device)
+    n = Kb.shape[0]
+    npad = ops.padded(n)
+    factor = cholesky_perturb_init
+    K64 = Kb.double()
+    for ntry in range(cholesky_tries):
+        eps = next(jitters) if jitters is not None else _draw_jitter(n, Kb.dtype)
+        eps = eps.to(device=Kb.device, dtype=torch.float64).contiguous()
+        buf = torch.eye(npad, dtype=torch.float64, device=Kb.device)
+        buf[:n, :n] = K64
+        try:
+            L, _ = ops.potrf_(buf, n, eps, factor)
+            Kbp = K64 + factor * torch.diag(eps)
+            return Kbp.to(Kb.dtype), L[:n, :n].to(Kb.dtype)
+        except RuntimeError as e:
+            if ntry == cholesky_tries - 1:
+                raise
+            LOG.warning("Cholesky failed with perturb={} on error {}".format(factor, str(e)))
+            factor = factor * cholesky_perturb_scale
+    raise AssertionError("unreachable")
+
+
+def is_psd(X):
+    try:
+        buf = torch.eye(ops.padded(X.shape[0]), dtype=torch.float64, device=X.device)
+        buf[:X.shape[0], :X.shape[0]] = X.double()
+        ops.potrf_(buf, X.shape[0], None, 0.0)
+    except RuntimeError as e:
+        print(e)
+        return False
+    return True
+
+
+class ControlAffineRegressor(DynamicsModel):
+    """Scikit-like wrapper: F(X), COV(F(X)) = ControlAffineRegressor().fit(X, U, Xdot).predict(Xtest)."""
+    ground_truth = False
+
+    def __init__(self, x_dim, u_dim, device=None, default_device=default_device, gamma_length_scale_prior=None,
+                 model_class=ControlAffineExactGP):
+        super().__init__()
+        self.device = device or default_device()
+        self.x_dim = x_dim
+        self.u_dim = u_dim
+        self.likelihood = IdentityLikelihood()
+        self.model_class = model_class
+        self.model = model_class(x_dim, u_dim, self.likelihood,
+                                 gamma_length_scale_prior=gamma_length_scale_prior).to(device=self.device)
+        self._cache = dict()
+        self._jitter_source = None
+        self._f_func_gp = GaussianProcess(self.f_func_mean, self.f_func_knl, (self.x_dim,), name="f")
+
+    # ------------------------------------------------------------------------------------------ bookkeeping
+    @property
+    def ctrl_size(self):
+        return self.u_dim
+
+    @property
+    def state_size(self):
+        return self.x_dim
+
+    @property
+    def dtype(self):
+        return next(self.model.parameters()).dtype
+
+    def to(self, dtype=torch.float64):
+        if dtype is torch.float64:
+            self.double_()
+        else:
+            self.float_()
+
+    def _cast(self, dt):
+        self.model.to(dtype=dt)
+        if self.model.train_inputs is not None:
+            self.model.train_inputs = tuple(inp.to(dt) for inp in self.model.train_inputs)
+            self.model.train_targets = self.model.train_targets.to(dt)
+        # the factor cache is kept in float64 (the kernels compute in float64 whatever the model dtype)
+
+    def double_(self):
+        self._cast(torch.float64)
+        assert self.dtype is torch.float64
+
+    def float_(self):
+        self._cast(torch.float32)
+        assert self.dtype is torch.float32
+
+    def set_jitter_source(self, vectors):
+        """Explicit U(0,1) jitter vectors (consumed in order by every make_psd attempt) instead of torch.rand."""
+        self._jitter_source = None if vectors is None else iter(vectors)
+
+    def _ensure_device_dtype(self, X):
+        if isinstance(X, np.ndarray):
+            X = torch.from_numpy(X)
+        return X.to(device=self.device, dtype=self.dtype)
+
+    def zero_grad(self):
+        for p in self.model.parameters():
+            if p.grad is not None:
+                p.grad.detach_()
+                p.grad.zero_()
+
+    def clear_cache(self):
+        self._cache = dict()
+
+    # ------------------------------------------------------------------------------------------ hyper-parameters
+    def _A_mat(self):
+        return self.model.covar_module.task_covar_module.U.covar_matrix.evaluate()
+
+    def _B_mat(self):
+        return self.model.covar_module.task_covar_module.V.covar_matrix.evaluate()
+
+    def _hyper64(self):
+        """(lengthscale (n,), outputscale float, A, B, C (p,n)) detached, float64, on the device."""
+        m = self.model
+        ls = m.input_covar.base_kernel.lengthscale.detach().reshape(-1).double().expand(self.x_dim).contiguous()
+        s = float(m.input_covar.outputscale.detach())
+        A = self._A_mat().detach().double().contiguous()
+        B = self._B_mat().detach().double().contiguous()
+        C = m.mean_module.constants().detach().double().contiguous()
+        return ls, s, A, B, C
+
+    def set_hyperparameters(self, lengthscale=None, outputscale=None, A=None, B=None, C=None):
+        """Set the constrained hyper-parameters directly (lengthscale (n,), outputscale, A (n,n), B (p,p), C (p,n)).
+        A / B are stored as a full-rank factor plus a small diagonal: chol(A - d I) chol(.)^T + d I with
+        d = lambda_min(A) / 2.  Clears the factor cache."""
+        from .gp_modules import inv_softplus
+        m = self.model
+        dev, dt = self.device, self.dtype
+        t = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float64) if not isinstance(v, torch.Tensor) else v,
+                                      dtype=torch.float64)
+        with torch.no_grad():
+            if lengthscale is not None:
+                m.input_covar.base_kernel.raw_lengthscale.copy_(inv_softplus(t(lengthscale)).reshape(1, -1).to(dev, dt))
+            if outputscale is not None:
+                m.input_covar.raw_outputscale.copy_(inv_softplus(t(outputscale)).reshape(()).to(dev, dt))
+            for mat, ik in ((A, m.task_covar.U), (B, m.task_covar.V)):
+                if mat is None:
+                    continue
+                M = t(mat)
+                d = 0.5 * float(torch.linalg.eigvalsh(M).min())
+                if not d > 0:
+                    raise ValueError("set_hyperparameters: covariance matrix must be positive definite")
+                Fm = torch.linalg.cholesky(M - d * torch.eye(M.shape[0], dtype=torch.float64))
+                ik.covar_factor = nn.Parameter(Fm.to(dev, dt))
+                ik.raw_var = nn.Parameter(inv_softplus(torch.full((M.shape[0],), d, dtype=torch.float64)).to(dev, dt))
+            if C is not None:
+                for bm, c in zip(m.mean_module.base_means, t(C).reshape(-1)):
+                    bm.constant.fill_(float(c))
+        self.clear_cache()
+        return self
+
+    def get_kernel_param(self, name):
+        if name == 'A':
+            return self._A_mat()
+        elif name == 'B':
+            return self._B_mat()
+        elif name == 'scalefactor':
+            return self.model.input_covar.outputscale
+        elif name == 'lengthscale':
+            return self.model.input_covar.base_kernel.lengthscale
+        raise ValueError('Unknown param %s' % name)
+
+    # ------------------------------------------------------------------------------------------ fit
+    def fit(self, *args, max_cg_iterations=2000, **kwargs):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return self._fit_with_warnings(*args, **kwargs)
+
+    def _fit_with_warnings(self, Xtrain_in, Utrain_in, XdotTrain_in, training_iter=50, lr=0.1):
+        if Xtrain_in.shape[0] == 0:
+            return self
+        _need_cuda(self.device)
+        model = self.model
+        Xtrain, Utrain, XdotTrain = [self._ensure_device_dtype(X) for X in (Xtrain_in, Utrain_in, XdotTrain_in)]
+        self.clear_cache()
+        model.set_train_data(Xtrain, Utrain, XdotTrain)
+        model.train()
+        optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+        scheduler = torch.optim.lr_scheduler.MultiStepLR(
+            optimizer, milestones=(torch.tensor([0.3, 0.6, 0.8, 0.90]) * training_iter).tolist())
+        N, n = Xtrain.shape
+        X64 = Xtrain.double().contiguous()
+        UH64 = torch.cat([Xtrain.new_ones(N, 1), Utrain], dim=1).double().contiguous()
+        prior = model.input_covar.base_kernel.lengthscale_prior
+        for i in range(training_iter):
+            optimizer.zero_grad()
+            for p in model.parameters(recurse=True):
+                assert not torch.isnan(p).any()
+            # fresh multiplicative target noise every iteration (reference :318-321), drawn on the CPU generator
+            noise = torch.rand(XdotTrain.shape, dtype=XdotTrain.dtype).to(self.device)
+            Y = (XdotTrain * (1 + 1e-6 * noise)).double()
+            ls = model.input_covar.base_kernel.lengthscale
+            logp = mvgp_log_marginal(ls.double().reshape(-1).expand(n), model.input_covar.outputscale.double(),
+                                     self._A_mat().double(), self._B_mat().double(),
+                                     model.mean_module.constants().double(), X64, UH64, Y)
+            if prior is not None:
+                logp = logp + prior.log_prob(ls.double())
+            loss = -logp / (N * n)
+            assert not torch.isnan(loss).any()
+            assert not torch.isinf(loss).any()
+            loss.backward()
+            for p in model.parameters(recurse=True):
+                if p.grad is not None:
+                    assert not torch.isnan(p.grad).any()
+            LOG.debug('Iter %d/%d - Loss: %.3f' % (i + 1, training_iter, loss.item()))
+            optimizer.step()
+            scheduler.step()
+        return self
+
+    # ------------------------------------------------------------------------------------------ factor
+    def _train_data(self):
+        MXUHtrain = self.model.train_inputs[0]
+        _, Xtrain, UHtrain = self.model.decoder.decode(MXUHtrain)
+        N = Xtrain.size(0)
+        return Xtrain, UHtrain, self.model.train_targets.reshape(N, -1)
+
+    def _perturbed_cholesky_compute(self, k, B, Xtrain, UHtrain, cholesky_tries=10, cholesky_perturb_init=1e-5,
+                                    cholesky_perturb_scale=10):
+        """Kb = k(X,X) o (UH B UH^T); L = chol(Kb + 1e-5 * 10^t * diag(U(0,1)))  (reference :366-377, :899-921).
+        `k` is accepted for signature compatibility; the data kernel's hyper-parameters are read from the model."""
+        _need_cuda(Xtrain.device)
+        ls, s, _, _, _ = self._hyper64()
+        X64, UH64 = Xtrain.double().contiguous(), UHtrain.double().contiguous()
+        B64 = B.detach().double().contiguous()
+        N = X64.shape[0]
+        factor = cholesky_perturb_init
+        for ntry in range(cholesky_tries):
+            eps = next(self._jitter_source) if self._jitter_source is not None else _draw_jitter(N, self.dtype)
+            eps = eps.to(device=X64.device, dtype=torch.float64).contiguous()
+            Kb = ops.gram_train(X64, UH64, B64, ls, s)
+            try:
+                L, dinv = ops.potrf_(Kb, N, eps, factor)
+                break
+            except RuntimeError as e:
+                if ntry == cholesky_tries - 1:
+                    raise
+                LOG.warning("Cholesky failed with perturb={} on error {}".format(factor, str(e)))
+                factor = factor * cholesky_perturb_scale
+        self._cache['_Lpad'] = L
+        self._cache['_Linv'] = ops.trtri(L, dinv)
+        return L[:N, :N]
+
+    def _perturbed_cholesky(self, k, B, Xtrain, UHtrain, cache_key="perturbed_cholesky"):
+        if cache_key not in self._cache:
+            self._cache[cache_key] = self._perturbed_cholesky_compute(k, B, Xtrain, UHtrain)
+        return self._cache[cache_key]
+
+    def _factor_state(self):
+        """Cached (Linv (Npad,Npad), alpha (Npad,n), G (Npad,p), Y (N,n)) for the current train data."""
+        Xtrain, UHtrain, targets = self._train_data()
+        ls, s, A, B, C = self._hyper64()
+        self._perturbed_cholesky(None, B, Xtrain, UHtrain)
+        if '_alpha' not in self._cache:
+            Linv = self._cache['_Linv']
+            Npad, N = Linv.shape[0], Xtrain.shape[0]
+            UH64 = UHtrain.double()
+            Y = targets.double() - UH64 @ C                           # Y = Xdot - UH C  (:525-532)
+            Ypad = torch.zeros(Npad, Y.shape[1], dtype=torch.float64, device=Y.device)
+            Ypad[:N] = Y
+            z = ops.trmm_lower(Linv, Ypad)
+            self._cache['_alpha'] = ops.trmm_lower(Linv, z.contiguous(), trans=True).contiguous()   # Kb^-1 Y (:545)
+            G = torch.zeros(Npad, B.shape[0], dtype=torch.float64, device=Y.device)
+            G[:N] = UH64 @ B
+            self._cache['_G'] = G
+        return self._cache['_Linv'], self._cache['_alpha'], self._cache['_G']
+
+    # ------------------------------------------------------------------------------------------ prediction
+    def _uh(self, X, U_in, fill):
+        if U_in is None:
+            UH = X.new_zeros(X.shape[0], self.model.matshape[0])
+            UH[:, 0] = 1
+            return UH
+        U = self._ensure_device_dtype(U_in)
+        return torch.cat((U.new_full((U.shape[0], 1), fill), U), dim=-1)
+
+    def _kb(self, X64, UH64, Xq, UHq, ls, s, B, Npad, diff):
+        """k(Xtrain, Xq) o (UHtrain B UHq^T), zero-padded to Npad rows."""
+        if diff:
+            K = autograd_ops.rbf_kernel(X64, Xq, ls, torch.as_tensor(s, dtype=torch.float64, device=Xq.device))
+            kb = K * ((UH64 @ B) @ UHq.transpose(0, 1))
+            return torch.nn.functional.pad(kb, (0, 0, 0, Npad - kb.shape[0]))
+        return ops.gram_ca(X64, Xq.contiguous(), ls, s, UH64, UHq.contiguous(), B, rows_pad=Npad)
+
+    def _kss(self, Xq, UHq, Xp, UHp, ls, s, B, diff):
+        if diff:
+            K = autograd_ops.rbf_kernel(Xq, Xp, ls, torch.as_tensor(s, dtype=torch.float64, device=Xq.device))
+            return K * (UHq @ B @ UHp.transpose(0, 1))
+        return ops.gram_ca(Xq.contiguous(), Xp.contiguous(), ls, s, UHq.contiguous(), UHp.contiguous(), B)
+
+    def custom_predict(self, Xtest_in, Utest_in=None, UHfill=1, Xtestp_in=None, Utestp_in=None, UHfillp=1,
+                       compute_cov=True, grad_gp=False, grad_check=False, scalar_var_only=False):
+        """Posterior of F(x)[UHfill;u] with u folded in before the solve (reference :390-613, R&W Alg. 2.1):
+        returns (mean (b,n), cov (1, b*n, b'*n) = scalar_var (x) A)  [or scalar_var (b,b') if scalar_var_only]."""
+        if grad_gp:
+            raise NotImplementedError(
+                "grad_gp=True (reference :447-477, not exercised by its callers) is not provided; differentiate "
+                "custom_predict through autograd (GradientGP) or use ops.rbf_blocks for the closed-form blocks")
+        _need_cuda(self.device)
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        Xtestp = self._ensure_device_dtype(Xtestp_in) if Xtestp_in is not None else Xtest
+        UHtest = self._uh(Xtest, Utest_in, UHfill)
+        UHtestp = UHtest if Utestp_in is None else self._uh(Xtestp, Utestp_in, UHfillp)
+        out_dt = self.dtype
+        ls, s, A, B, C = self._hyper64()
+        Xq, Xp, UHq, UHp = Xtest.double(), Xtestp.double(), UHtest.double(), UHtestp.double()
+        diff = any(t.requires_grad for t in (Xq, Xp, UHq, UHp))
+        fu_mean_test = UHq @ C                                              # (b, n): M(x)^T [1;u]
+        if self.model.train_inputs is None:
+            scalar_var = self._kss(Xq, UHq, Xp, UHp, ls, s, B, diff)
+            return fu_mean_test.to(out_dt), torch_kron(scalar_var.unsqueeze(0), A.unsqueeze(0)).to(out_dt)
+        Xtrain, UHtrain, _ = self._train_data()
+        X64, UH64 = Xtrain.double().contiguous(), UHtrain.double().contiguous()
+        Linv, alpha, _ = self._factor_state()
+        Npad = Linv.shape[0]
+        kb_star = self._kb(X64, UH64, Xq, UHq, ls, s, B, Npad, diff)       # (Npad, b)  (:536)
+        if diff:
+            mean = fu_mean_test + autograd_ops.mm_tn(kb_star, alpha)       # (:547)
+        else:
+            mean = fu_mean_test + ops.gemm(kb_star, alpha, transa=True)
+        if not compute_cov:
+            return mean.to(out_dt), (0 * A).to(out_dt)                      # (:612)
+        kb_star_p = self._kb(X64, UH64, Xp, UHp, ls, s, B, Npad, diff) if Xtestp_in is not None else kb_star
+        kb_ss = self._kss(Xq, UHq, Xp, UHp, ls, s, B, diff)                # (b, b')
+        if diff:
+            v = autograd_ops.linv_mm(Linv, kb_star)                        # L \ kb*  (:565)
+            vp = autograd_ops.linv_mm(Linv, kb_star_p) if Xtestp_in is not None else v
+            scalar_var = kb_ss - autograd_ops.mm_tn(v, vp)                 # (:586)
+        else:
+            v = ops.trmm_lower(Linv, kb_star.contiguous())
+            vp = ops.trmm_lower(Linv, kb_star_p.contiguous()) if Xtestp_in is not None else v
+            scalar_var = ops.gemm(v, vp, transa=True, alpha=-1.0, beta=1.0, C=kb_ss)
+        if scalar_var_only:
+            return mean.to(out_dt), scalar_var.to(out_dt)
+        return mean.to(out_dt), torch_kron(scalar_var.unsqueeze(0), A.unsqueeze(0)).to(out_dt)   # (:602)
+
+    # ---- matrix form (class Exact in the reference; kept on the base class so that predict() can use it) ----------
+    def _custom_predict_matrix(self, Xtest_in, Xtestp_in=None, compute_cov=True, _out_jitter=True):
+        """M_k (b,n,p), A (n,n), B_k (b,b',p,p)  (reference :983-1096)."""
+        _need_cuda(self.device)
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        Xtestp = self._ensure_device_dtype(Xtestp_in) if Xtestp_in is not None else Xtest
+        out_dt = self.dtype
+        ls, s, A, B, C = self._hyper64()
+        p, n = self.model.matshape
+        Xq, Xp = Xtest.double(), Xtestp.double()
+        b, bp_ = Xq.shape[0], Xp.shape[0]
+        diff = Xq.requires_grad or Xp.requires_grad
+        s_t = torch.as_tensor(s, dtype=torch.float64, device=Xq.device)
+        kfun = (lambda a, c: autograd_ops.rbf_kernel(a, c, ls, s_t)) if diff else \
+            (lambda a, c: ops.gram_ca(a.contiguous(), c.contiguous(), ls, s))
+        M0 = C.t().unsqueeze(0).expand(b, n, p)                             # (:1022-1023)
+        if self.model.train_inputs is None:
+            return M0.to(out_dt), A.to(out_dt), (B * kfun(Xq, Xp).unsqueeze(-1).unsqueeze(-1)).to(out_dt)
+        Xtrain, UHtrain, _ = self._train_data()
+        X64, UH64 = Xtrain.double().contiguous(), UHtrain.double().contiguous()
+        N = X64.shape[0]
+        Linv, alpha, G = self._factor_state()
+        Npad = Linv.shape[0]
+        # frakB[i, (t, q)] = k(X_i, x_t) G[i, q]   (Npad, b*p)   (:1051)
+        if diff:
+            K = kfun(X64, Xq)                                               # (N, b)
+            frakB = (K.unsqueeze(-1) * G[:N].unsqueeze(1)).reshape(N, b * p)
+            frakB = torch.nn.functional.pad(frakB, (0, 0, 0, Npad - N))
+            mean_k = M0 + autograd_ops.mm_tn(alpha, frakB).reshape(n, b, p).permute(1, 0, 2)
+        else:
+            Xr, E = HetergeneousMatrixVariateKernel._onehot_cols(Xq, p)
+            frakB = ops.gram_ca(X64, Xr, ls, s, UH64, E, B, rows_pad=Npad)
+            mean_k = M0 + ops.gemm(alpha, frakB.contiguous(), transa=True).reshape(n, b, p).permute(1, 0, 2)  # (:1055)
+        if not compute_cov:
+            return mean_k.to(out_dt), A.to(out_dt), Xtest.new_zeros(b, bp_, p, p)
+        KB = torch_kron(kfun(Xq, Xp), B, batch_dims=0)                      # (:1062-1063)
+        # the reference subtracts the Xtest term on both sides even when Xtestp is given (:1079-1088; needs b == b')
+        if diff:
+            V = autograd_ops.linv_mm(Linv, frakB)
+            BkXX = KB - autograd_ops.mm_tn(V, V)
+        else:
+            V = ops.trmm_lower(Linv, frakB.contiguous())
+            BkXX = ops.gemm(V, V, transa=True, alpha=-1.0, beta=1.0, C=KB)
+        if _out_jitter:
+            BkXX, _ = self._make_psd_output(BkXX)                           # (:1089)
+        BkXX = BkXX.reshape(b, p, bp_, p).transpose(1, 2)                   # (:1091)
+        return mean_k.to(out_dt), A.to(out_dt), BkXX.to(out_dt)
+
+    def _make_psd_output(self, M):
+        """The reference's second make_psd (:1089): random jitter ADDED to the returned covariance, retried x10 until
+        the blocked Cholesky accepts it."""
+        n = M.shape[0]
+        factor = 1e-5
+        for ntry in range(10):
+            eps = next(self._jitter_source) if self._jitter_source is not None else _draw_jitter(n, self.dtype)
+            eps = eps.to(device=M.device, dtype=torch.float64)
+            Mp = M + factor * torch.diag(eps)
+            buf = torch.eye(ops.padded(n), dtype=torch.float64, device=M.device)
+            buf[:n, :n] = Mp.detach()
+            try:
+                L, _ = ops.potrf_(buf, n, None, 0.0)
+                return Mp, L[:n, :n]
+            except RuntimeError as e:
+                if ntry == 9:
+                    raise
+                LOG.warning("Cholesky failed with perturb={} on error {}".format(factor, str(e)))
+                factor *= 10
+        raise AssertionError("unreachable")
+
+    def custom_predict_blocks(self, Xtest_in, Utest_in=None):
+        """Per-query posterior blocks for large batches (extension; the reference's (b,b,p,p) form is O(b^2)):
+        M_k (b,n,p), B_k (b,p,p) [no output jitter] and, when Utest is given, mean (b,n), svar (b,) = u^T B_k u.
+        Fused path: cross Gram -> persistent DMMA posterior kernel (bcbf_posterior_blocks)."""
+        _need_cuda(self.device)
+        Xq = self._ensure_device_dtype(Xtest_in).double().contiguous()
+        ls, s, A, B, C = self._hyper64()
+        p, n = self.model.matshape
+        Xtrain, _, _ = self._train_data()
+        Linv, alpha, G = self._factor_state()
+        if '_W' not in self._cache:
+            self._cache['_W'] = (alpha.unsqueeze(-1) * G.unsqueeze(1)).reshape(G.shape[0], n * p).contiguous()
+        Q = Xq.shape[0]
+        Ks = ops.cross_gram(Xtrain.double().contiguous(), Xq, ls, s, Npad=Linv.shape[0])
+        Mk, Bk = ops.posterior_blocks(Linv, Ks, G, self._cache['_W'], B, C.t().contiguous(), s, n, p, Q)
+        if Utest_in is None:
+            return Mk, Bk
+        UHq = self._uh(Xq, Utest_in, 1).double().contiguous()
+        mean, svar = ops.contract_u(Mk, Bk, UHq)
+        return Mk, Bk, mean, svar
+
+    def custom_predict_fullmat(self, Xtest_in, Xtestp_in=None):
+        """vec F(x) in (b,p,n) order and its (bpn, bpn) covariance (reference :963-980)."""
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        meanFX, A, BkXX = self._custom_predict_matrix(Xtest_in, Xtestp_in, compute_cov=True)
+        assert not torch.isnan(meanFX).any()
+        b, p = Xtest.shape[0], 1 + self.u_dim
+        assert meanFX.shape == (b, self.x_dim, p)
+        meanFX = meanFX.transpose(-2, -1)
+        var_FX = torch_kron(BkXX.transpose(2, 1).reshape(b * p, b * p), A, batch_dims=0)
+        return meanFX.reshape(-1), var_FX
+
+    def predict(self, Xtest_in, return_cov=True):
+        """mean F(x)^T (b,p,n) and covariance (bpn,bpn) on the INPUT's device / dtype (reference :343-364; there the
+        numbers come from gpytorch's eval-mode ExactGP — parity unpinned; here the closed form)."""
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        if isinstance(Xtest_in, np.ndarray):
+            Xtest_in = torch.from_numpy(Xtest_in)
+        meanFX, A, BkXX = self._custom_predict_matrix(Xtest, None, compute_cov=return_cov, _out_jitter=False)
+        b, p = Xtest.shape[0], 1 + self.u_dim
+        mean = meanFX.transpose(-2, -1).to(device=Xtest_in.device, dtype=Xtest_in.dtype)
+        if not return_cov:
+            return mean
+        cov = torch_kron(BkXX.transpose(2, 1).reshape(b * p, b * p), A, batch_dims=0)
+        return mean, cov.to(device=Xtest_in.device, dtype=Xtest_in.dtype)
+
+    # ------------------------------------------------------------------------------------------ closures
+    @staticmethod
+    def _b(t):
+        return t.unsqueeze(0) if t.ndim == 1 else t
+
+    def f_func(self, Xtest_in, return_cov=False):
+        Xtest = self._b(Xtest_in)
+        Utest = Xtest.new_zeros((Xtest.shape[0], self.u_dim))
+        mean_fx, cov_fx = self.custom_predict(Xtest, Utest)
+        if return_cov:
+            if Xtest_in.ndim == 1:
+                cov_fx = cov_fx.squeeze(0)
+            cov_fx = cov_fx.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
+        if Xtest_in.ndim == 1:
+            mean_fx = mean_fx.squeeze(0)
+        mean_fx = mean_fx.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
+        return (mean_fx, cov_fx) if return_cov else mean_fx
+
+    def f_func_mean(self, Xtest_in):
+        mean_f, _ = self.custom_predict(self._b(Xtest_in), compute_cov=False)
+        if Xtest_in.ndim == 1:
+            mean_f = mean_f.squeeze(0)
+        return mean_f.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
+
+    def f_func_knl(self, Xtest_in, Xtestp_in, grad_check=False):
+        _, var_f = self.custom_predict(self._b(Xtest_in), Xtestp_in=self._b(Xtestp_in), compute_cov=True)
+        if Xtest_in.ndim == 1:
+            var_f = var_f.squeeze(0)
+        return var_f.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
+
+    def f_func_gp(self):
+        return self._f_func_gp
+
+    def fu_func_mean(self, Utest_in, Xtest_in):
+        mean_f, _ = self.custom_predict(self._b(Xtest_in), self._b(Utest_in), compute_cov=False)
+        if Xtest_in.ndim == 1:
+            mean_f = mean_f.squeeze(0)
+        return mean_f.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
+
+    def fu_func_knl(self, Utest_in, Xtest_in, Xtestp_in):
+        _, var_f = self.custom_predict(self._b(Xtest_in), self._b(Utest_in), Xtestp_in=self._b(Xtestp_in),
+                                       compute_cov=True)
+        if Xtest_in.ndim == 1:
+            var_f = var_f.squeeze(0)
+        return var_f.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
+
+    def fu_func_gp(self, Utest_in):
+        gp = GaussianProcess(mean=partial(self.fu_func_mean, Utest_in), knl=partial(self.fu_func_knl, Utest_in),
+                             shape=(self.x_dim,), name="F(.)u")
+        gp.register_covar(self._f_func_gp, partial(self.covar_fu_f, Utest_in))
+        return gp
+
+    def covar_fu_f(self, Utest_in, Xtest_in, Xtestp_in):
+        Utest = self._b(Utest_in)
+        _, var_f = self.custom_predict(self._b(Xtest_in), Utest, Xtestp_in=self._b(Xtestp_in),
+                                       Utestp_in=torch.zeros_like(Utest), compute_cov=True)
+        if Xtest_in.ndim == 1:
+            var_f = var_f.squeeze(0)
+        return var_f.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
+
+    def g_func(self, Xtest_in, return_cov=False):
+        assert not return_cov, "Don't know what matrix covariance looks like"
+        mean_Fx = self.predict(self._b(Xtest_in), return_cov=False)
+        mean_gx = mean_Fx[:, 1:, :]
+        if Xtest_in.ndim == 1:
+            mean_gx = mean_gx.squeeze(0)
+        return mean_gx.to(dtype=Xtest_in.dtype, device=Xtest_in.device).transpose(-2, -1)
+
+    def _gu_func(self, Xtest_in, Utest_in=None, return_cov=False, Xtestp_in=None):
+        Xtest = self._b(Xtest_in)
+        Utest = self._b(Utest_in) if Utest_in is not None else Xtest_in.new_ones(Xtest.shape[0], self.u_dim)
+        mean_gu, var_gu = self.custom_predict(Xtest, Utest, UHfill=0, Xtestp_in=Xtestp_in, compute_cov=True)
+        if Xtest_in.ndim == 1 and (Utest_in is None or Utest_in.ndim == 1):
+            mean_gu = mean_gu.squeeze(0)
+            var_gu = var_gu.squeeze(0)
+        return (mean_gu, var_gu) if return_cov else mean_gu
+
+    def g_func_mean(self, Xtest_in):
+        return self._gu_func(Xtest_in, return_cov=False)
+
+    # ------------------------------------------------------------------------------------------ persistence
+    def state_dict(self):
+        return dict(model=self.model.state_dict(), likelihood=dict())
+
+    def load_state_dict(self, state_dict):
+        self.model.load_state_dict(state_dict['model'])
+
+    def save(self, path='/tmp/saved.pickle'):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path='/tmp/saved.pickle'):
+        self.load_state_dict(torch.load(path, weights_only=False))
+
+
+ControlAffineRegressorRankOne = partial(
+    ControlAffineRegressor,
+    model_class=partial(ControlAffineExactGP, rank=1, gamma_length_scale_prior=(1e-3, 1e-3)))
+
+
+class ControlAffineRegressorExact(ControlAffineRegressor):
+    """Matrix-variate form: posterior of F(x) first, then the [1;u] contraction (reference :930-1096)."""
+
+    def custom_predict(self, Xtest_in, Utest_in=None, UHfill=1, Xtestp_in=None, Utestp_in=None, UHfillp=1,
+                       compute_cov=True):
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        Xtestp = self._ensure_device_dtype(Xtestp_in) if Xtestp_in is not None else Xtest
+        meanFX, A, BkXX = self._custom_predict_matrix(Xtest_in, Xtestp_in, compute_cov=compute_cov)
+        UHtest = self._uh(Xtest, Utest_in, UHfill)
+        UHtestp = UHtest if Utestp_in is None else self._uh(Xtestp, Utestp_in, UHfillp)
+        meanFXU = meanFX.bmm(UHtest.unsqueeze(-1)).squeeze(-1)
+        if compute_cov:
+            l = UHtest.unsqueeze(-1).unsqueeze(1)       # (b, 1, p, 1)
+            r = UHtestp.unsqueeze(-1).unsqueeze(0)      # (1, b', p, 1)
+            varFXU = torch.matmul(torch.matmul(l.transpose(-2, -1), BkXX), r) * A
+        else:
+            varFXU = Xtest.new_zeros(Xtest.shape[0], Xtestp.shape[0], *A.shape)
+        return meanFXU, varFXU
+
+
+ControlAffineRegressorExactRankOne = partial(
+    ControlAffineRegressorExact,
+    model_class=partial(ControlAffineExactGP, rank=1))
+
+# rank-0 ("diagonal") variant of the task covariances (reference :1334-1336)
+ControlAffineRegMatrixDiag = partial(
+    ControlAffineRegressorExact,
+    model_class=partial(ControlAffineExactGP, rank=0))

@@ -82,6 +82,45 @@ __global__ void cbc1_terms_kernel(const double* __restrict__ Mk, const double* _
   }
 }
 
+// ---- batched factorisation of the SOCP matrix Asq = [[v, bfv^T/2],[bfv/2, V]] = Ls Ls^T (p x p, p <= 4) -------------
+__global__ void socp_factor_kernel(const double* __restrict__ Asq, int p, int Q, double reg, double* __restrict__ A_socp,
+                                   double* __restrict__ bfb, int* __restrict__ status) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int m = p - 1;
+  double M[BCBF_MAX_P_DIM][BCBF_MAX_P_DIM], Ls[BCBF_MAX_P_DIM][BCBF_MAX_P_DIM];
+  int st = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j < p; ++j) {
+        M[i][j] = Asq[((long long)q * p + i) * p + j] + ((attempt == 1 && i == j) ? reg : 0.0);
+        Ls[i][j] = 0.0;
+      }
+    st = 0;
+    for (int j = 0; j < p; ++j) {
+      double d = M[j][j];
+      for (int k = 0; k < j; ++k) d -= Ls[j][k] * Ls[j][k];
+      if (!(d > 0.0)) {
+        if (st == 0) st = j + 1;
+        d = __longlong_as_double(0x7ff8000000000000LL);
+      }
+      d = sqrt(d);
+      Ls[j][j] = d;
+      for (int i = j + 1; i < p; ++i) {
+        double s = M[i][j];
+        for (int k = 0; k < j; ++k) s -= Ls[i][k] * Ls[j][k];
+        Ls[i][j] = s / d;
+      }
+    }
+    if (st == 0 || reg <= 0.0) break;   // second attempt only when the caller asked for the singular fallback
+  }
+  if (status) status[q] = st;
+  for (int i = 0; i < p; ++i) {
+    bfb[(long long)q * p + i] = Ls[0][i];
+    for (int c = 0; c < m; ++c) A_socp[((long long)q * p + i) * m + c] = Ls[c + 1][i];
+  }
+}
+
 // ---- model-handle helper kernels -----------------------------------------------------------------------
 __global__ void prep_train_kernel(const double* __restrict__ U, const double* __restrict__ Xdot, int N, int Npad, int n,
                                   int p, const double* __restrict__ Bm, const double* __restrict__ C,
@@ -145,6 +184,16 @@ extern "C" int bcbf_cbc1_terms(const double* Mk, const double* Bk, const double*
                n, p, Q);
   cbc1_terms_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(Mk, Bk, Amat, grad_h, h, Fbar, gamma, n, p, Q, bfe, e, Asq,
                                                           A_socp, bfb, status);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_socp_factor(const double* Asq, int p, int Q, double reg, double* A_socp, double* bfb, int* status,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(Asq && A_socp && bfb, "bcbf_socp_factor: null pointer");
+  BCBF_REQUIRE(p >= 2 && p <= BCBF_MAX_P_DIM && Q >= 1, "bcbf_socp_factor: p=%d Q=%d", p, Q);
+  socp_factor_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(Asq, p, Q, reg, A_socp, bfb, status);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }

@@ -233,3 +233,25 @@ extern "C" int bcbf_trmm_lower(const double* A, int lda, int Npad, int trans, co
   }
   return BCBF_OK;
 }
+
+// General row-major C(M,N) = alpha * op(A) op(B) + beta * C on the DMMA GEMM (host glue for the small-batch API
+// paths: v^T v', kb*^T alpha, Linv^T Linv).  op(A) is M x K: transa = 0 -> A stored (M,K); 1 -> stored (K,M).
+// op(B) is K x N: transb = 0 -> B stored (K,N); 1 -> stored (N,K).
+extern "C" int bcbf_gemm(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda,
+                         const double* B, int ldb, double beta, double* C, int ldc, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(A && B && C, "bcbf_gemm: null pointer");
+  BCBF_REQUIRE(M > 0 && N > 0 && K > 0 && M % 2 == 0 && N % 2 == 0 && K % 2 == 0,
+               "bcbf_gemm: M=%d N=%d K=%d must be positive and even (pad with zeros)", M, N, K);
+  BCBF_REQUIRE(lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0, "bcbf_gemm: leading dimensions must be even");
+  BCBF_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
+               "bcbf_gemm: operands must be 16-byte aligned");
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.tri = kTriNone;
+  if (!transa && !transb) BCBF_CUDA((launch_gemm<true, false>(g, 1, stream)));
+  else if (!transa && transb) BCBF_CUDA((launch_gemm<true, true>(g, 1, stream)));
+  else if (transa && !transb) BCBF_CUDA((launch_gemm<false, false>(g, 1, stream)));
+  else BCBF_CUDA((launch_gemm<false, true>(g, 1, stream)));
+  return BCBF_OK;
+}

@@ -1,0 +1,128 @@
+"""MVGP kernel classes with the reference's names and call signatures
+(bayes_cbf/matrix_variate_multitask_kernel.py:18-49, 99-204), evaluated densely on the GPU.
+
+Covariance of the heterogeneous observation model (train rows, mask 1, observe F(x)[1;u]: n outputs; test rows,
+mask 0, observe F(x): p*n outputs), rows sorted train-first, output index order (point, q in p, r in n), r fastest:
+
+    [ (K11 o UH1 B UH2^T) (x) A          ((K12 (x) 1_p^T) o (UH1 B)) (x) A ]
+    [            (.)^T                       (K22 (x) B) (x) A             ]
+
+Every block is one launch of the fused control-affine Gram kernel (`bcbf_gram_ca`) followed by the Kronecker
+expansion with A.
+"""
+import operator
+from functools import reduce
+
+import torch
+
+from . import ops
+from .gp_modules import Evaluated, IndexKernel, Kernel
+from .misc import torch_kron
+
+
+def prod(L):
+    return reduce(operator.mul, L, 1)
+
+
+class MatrixVariateIndexKernel(Kernel):
+    """covar_matrix = V (x) U for U (n,n) row covariance and V (p,p) column covariance (reference :18-49)."""
+
+    def __init__(self, U: IndexKernel, V: IndexKernel):
+        super().__init__()
+        self.U = U
+        self.V = V
+        self.matshape = (self.U.raw_var.shape[-1], self.V.raw_var.shape[-1])
+
+    @property
+    def covar_matrix(self):
+        return Evaluated(torch_kron(self.V.covar_matrix.evaluate(), self.U.covar_matrix.evaluate(), batch_dims=0))
+
+    def forward(self, i1, i2, **params):
+        assert i1.dtype in (torch.int64, torch.int32) and i2.dtype in (torch.int64, torch.int32)
+        C = self.covar_matrix.evaluate()
+        return C[i1.reshape(-1)][:, i2.reshape(-1)]
+
+
+class MatrixVariateKernel(Kernel):
+    @property
+    def num_tasks(self):
+        return prod(self.task_covar_module.matshape)
+
+    def __init__(self, task_covar_module, data_covar_module, decoder, **kwargs):
+        super().__init__()
+        self.task_covar_module = task_covar_module
+        self.data_covar_module = data_covar_module
+        self.decoder = decoder
+
+
+def _train_end(M1s):
+    idxs = torch.nonzero(M1s - torch.ones_like(M1s))
+    return int(torch.min(idxs).item()) if idxs.numel() else M1s.size(-1)
+
+
+class HetergeneousMatrixVariateKernel(MatrixVariateKernel):
+    def num_outputs_per_input(self, mxu1, mxu2):
+        M1, X1, _ = self.decoder.decode(mxu1)
+        M1s = M1[..., 0]
+        end = _train_end(M1s)
+        train_size = end * X1.shape[-1]
+        test_size = (M1s.size(-1) - end) * prod(self.task_covar_module.matshape)
+        return (train_size + test_size) / M1s.size(-1)
+
+    # ---- the three block types (reference kernel1 / kernel2 / correlation_kernel_12, :112-134) -------------------
+    def _hyper(self, ref):
+        dk = self.data_covar_module
+        base = getattr(dk, 'base_kernel', dk)
+        n = ref.shape[-1]
+        ls = base.lengthscale.reshape(-1).double().expand(n).contiguous().detach()
+        s = float(dk.outputscale.detach()) if hasattr(dk, 'outputscale') else 1.0
+        A = self.task_covar_module.U.covar_matrix.evaluate()
+        B = self.task_covar_module.V.covar_matrix.evaluate()
+        return ls, s, A, B
+
+    @staticmethod
+    def _onehot_cols(X, p):
+        """(X repeated p times point-major, identity rows) so that gram_ca yields frakB columns (point, q)."""
+        Xr = X.repeat_interleave(p, dim=0).contiguous()
+        E = torch.eye(p, dtype=X.dtype, device=X.device).repeat(X.shape[0], 1).contiguous()
+        return Xr, E
+
+    def kernel1(self, X1, UH1, X2, UH2):
+        ls, s, A, B = self._hyper(X1)
+        Kb = ops.gram_ca(X1, X2, ls, s, UH1, UH2, B.double().contiguous())
+        return torch_kron(Kb.to(A.dtype), A, batch_dims=0)
+
+    def kernel2(self, X1, X2):
+        ls, s, A, B = self._hyper(X1)
+        K = ops.gram_ca(X1, X2, ls, s)
+        return torch_kron(torch_kron(K.to(A.dtype), B, batch_dims=0), A, batch_dims=0)
+
+    def correlation_kernel_12(self, X1, UH1, X2):
+        ls, s, A, B = self._hyper(X1)
+        p = B.shape[0]
+        X2r, E = self._onehot_cols(X2, p)
+        K12 = ops.gram_ca(X1, X2r, ls, s, UH1, E, B.double().contiguous())
+        return torch_kron(K12.to(A.dtype), A, batch_dims=0)
+
+    def mask_dependent_covar(self, M1s, U1, M2s, U2, X1, X2):
+        e1, e2 = _train_end(M1s), _train_end(M2s)
+        assert (M1s[e1:] == 0).all() and (M2s[e2:] == 0).all(), "rows must be sorted train-first"
+        d = lambda t: t.double().contiguous()
+        X1a, X1b, X2a, X2b = d(X1[:e1]), d(X1[e1:]), d(X2[:e2]), d(X2[e2:])
+        UH1a, UH2a = d(U1[:e1]), d(U2[:e2])
+        k11 = self.kernel1(X1a, UH1a, X2a, UH2a) if (e1 and e2) else None
+        k22 = self.kernel2(X1b, X2b) if (X1b.shape[0] and X2b.shape[0]) else None
+        if k11 is not None and k22 is not None:
+            k12 = self.correlation_kernel_12(X1a, UH1a, X2b)
+            k21 = self.correlation_kernel_12(X2a, UH2a, X1b).transpose(0, 1)
+            return torch.cat([torch.cat([k11, k12], dim=1), torch.cat([k21, k22], dim=1)], dim=0)
+        return k22 if k11 is None else k11
+
+    def forward(self, mxu1, mxu2, diag=False, last_dim_is_batch=False, **params):
+        assert not torch.isnan(mxu1).any() and not torch.isnan(mxu2).any()
+        if last_dim_is_batch:
+            raise RuntimeError("HetergeneousMatrixVariateKernel does not accept the last dimension to be treated as a batch dimension.")
+        M1, X1, U1 = self.decoder.decode(mxu1)
+        M2, X2, U2 = self.decoder.decode(mxu2)
+        res = self.mask_dependent_covar(M1[..., 0], U1, M2[..., 0], U2, X1, X2).to(mxu1.dtype)
+        return torch.diagonal(res) if diag else res

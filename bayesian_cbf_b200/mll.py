@@ -1,0 +1,88 @@
+"""Log marginal likelihood of the MVGP and its hyper-parameter gradients on the GPU — what `fit` maximises.
+
+The reference hands `MultivariateNormal(M(XU), Kb (x) A)` to gpytorch's `ExactMarginalLogLikelihood`
+(control_affine_model.py:309-321) and back-propagates through gpytorch's lazy-tensor algebra.  With the Kronecker
+identity (verified equal to the (N n)-dimensional density in oracle/mvgp_oracle.py:mll_dense)
+
+    log N(vec Xdot; vec(UH C), Kb (x) A) = -1/2 [ tr(A^-1 Y^T Kb^-1 Y) + n logdet Kb + N logdet A + N n log 2 pi ]
+
+and the closed-form adjoints
+
+    d/dKb = 1/2 (alpha A^-1 alpha^T - n Kb^-1),   d/dA = 1/2 (A^-1 Y^T alpha A^-1 - N A^-1),   d/dC = UH^T alpha A^-1
+
+(alpha = Kb^-1 Y), one value+gradient evaluation is: fused Gram -> blocked Cholesky -> triangular inverse ->
+Kb^-1 = L^-T L^-1 (DMMA GEMM) -> one fused reduction over the N x N adjoint (`bcbf_gram_train_backward`).
+The n x n / p x p pieces are host-side glue.  Parity: unpinned in the reference (gpytorch-internal);
+tests compare against torch autograd of the dense density.
+"""
+import math
+
+import torch
+
+from . import ops
+from ._lib import NotPositiveDefiniteError
+
+
+class _MVGPLogMarginal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ls, s, A, B, C, X, UH, Xdot):
+        N, n = X.shape
+        p = UH.shape[1]
+        nout = Xdot.shape[1]
+        dev = X.device
+        ls_d, B_d = ls.detach().contiguous(), B.detach().contiguous()
+        s_f = float(s)
+        Y = (Xdot - UH @ C.detach()).contiguous()
+        ones = torch.ones(N, dtype=torch.float64, device=dev)
+        jitter = 0.0
+        L = dinv = None
+        for attempt in range(7):          # psd-safe escalation like gpytorch's psd_safe_cholesky (1e-8 * 10^t)
+            Kb = ops.gram_train(X, UH, B_d, ls_d, s_f)
+            try:
+                L, dinv = ops.potrf_(Kb, N, ones if jitter > 0 else None, jitter)
+                break
+            except NotPositiveDefiniteError:
+                if attempt == 6:
+                    raise
+                jitter = 1e-8 if jitter == 0.0 else jitter * 10
+        Npad = L.shape[0]
+        Linv = ops.trtri(L, dinv)
+        Ypad = torch.zeros(Npad, nout, dtype=torch.float64, device=dev)
+        Ypad[:N] = Y
+        z = ops.trmm_lower(Linv, Ypad)                              # L^-1 Y
+        alpha = ops.trmm_lower(Linv, z.contiguous(), trans=True)    # Kb^-1 Y
+        alpha = alpha[:N].contiguous()
+        La = torch.linalg.cholesky(A.detach())                       # n x n glue
+        Ai = torch.cholesky_inverse(La)
+        YtA = z[:N].transpose(0, 1) @ z[:N]                          # Y^T Kb^-1 Y  (n x n)
+        quad = torch.trace(Ai @ YtA)
+        logdetK = 2.0 * torch.log(torch.diagonal(L)[:N]).sum()
+        logdetA = 2.0 * torch.log(torch.diagonal(La)).sum()
+        value = -0.5 * (quad + nout * logdetK + N * logdetA + N * nout * math.log(2 * math.pi))
+        # ---- gradients (always needed by fit; computed eagerly) -----------------------------------------------
+        Pinv = ops.gemm(Linv, Linv, transa=True)                     # Kb^-1 = L^-T L^-1  (Npad, Npad)
+        alphaAi = (alpha @ Ai).contiguous()
+        g_s, g_ls, g_B = ops.gram_train_backward(X, UH, B_d, ls_d, s_f, Pinv.contiguous(), alphaAi, alpha)
+        g_A = 0.5 * (Ai @ YtA @ Ai - N * Ai)
+        g_C = UH.transpose(0, 1) @ alphaAi
+        ctx.save_for_backward(g_ls.clone(), g_s.clone(), g_A, g_B.clone(), g_C)
+        ctx.jitter = jitter
+        return value
+
+    @staticmethod
+    def backward(ctx, g):
+        g_ls, g_s, g_A, g_B, g_C = ctx.saved_tensors
+        return g * g_ls, g * g_s, g * g_A, g * g_B, g * g_C, None, None, None
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("mvgp_log_marginal runs on a CUDA device only (no CPU fallback)")
+
+
+def mvgp_log_marginal(lengthscale, outputscale, A, B, C, X, UH, Xdot):
+    """log N(vec Xdot; vec(UH C), Kb (x) A); float64 CUDA tensors; differentiable w.r.t. the five hyper-parameters."""
+    _need_cuda(lengthscale, A, B, C, X, UH, Xdot)
+    return _MVGPLogMarginal.apply(lengthscale.reshape(-1), outputscale.reshape(()), A, B, C, X.contiguous(),
+                                  UH.contiguous(), Xdot.contiguous())

@@ -14,7 +14,7 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _req(*tensors):
+def _req(*tensors, contiguous=True):
     for t in tensors:
         if t is None:
             continue
@@ -22,7 +22,7 @@ def _req(*tensors):
             raise RuntimeError("bayesian_cbf_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
         if t.dtype is not torch.float64:
             raise RuntimeError("bayesian_cbf_b200 ops compute in float64; got %s" % t.dtype)
-        if not t.is_contiguous():
+        if contiguous and not t.is_contiguous():
             raise RuntimeError("bayesian_cbf_b200 ops need contiguous tensors")
 
 
@@ -57,6 +57,52 @@ def cross_gram(X, Xq, lengthscale, outputscale, Npad=None, ldks=None):
     check(_lib.load().bcbf_cross_gram(_ptr(X), _ptr(Xq), _ptr(lengthscale), float(outputscale), N, Q, n, _ptr(Ks),
                                       ldks, Npad, _stream()))
     return Ks
+
+
+def gram_ca(X1, X2, lengthscale, outputscale, UH1=None, UH2=None, B=None, rows_pad=None):
+    """out[i, j] = k(x1_i, x2_j) * (uh1_i^T B uh2_j)  (a, c) — kb*, kb** and, with one-hot uh2, frakB.
+    UH1 = UH2 = None gives the plain data kernel.  rows_pad > a appends zero rows (factor-sized operands)."""
+    _req(X1, X2, lengthscale, UH1, UH2, B)
+    a, n = X1.shape
+    c = X2.shape[0]
+    p = 0 if UH1 is None else UH1.shape[1]
+    ld = (c + 1) // 2 * 2
+    if rows_pad is None or rows_pad == a:
+        buf = torch.empty(a, ld, dtype=torch.float64, device=X1.device)
+    else:
+        buf = torch.zeros(rows_pad, ld, dtype=torch.float64, device=X1.device)
+    check(_lib.load().bcbf_gram_ca(_ptr(X1), _ptr(UH1), a, _ptr(X2), _ptr(UH2), c, _ptr(B), _ptr(lengthscale),
+                                   float(outputscale), n, p, _ptr(buf), ld, _stream()))
+    return buf[:, :c]
+
+
+def _even_pad(t, rows, cols):
+    """Zero-padded contiguous copy of a 2-D tensor with the requested (even) extents; no copy when it fits."""
+    if t.shape == (rows, cols) and t.is_contiguous() and t.data_ptr() % 16 == 0:
+        return t
+    out = torch.zeros(rows, cols, dtype=torch.float64, device=t.device)
+    out[:t.shape[0], :t.shape[1]] = t
+    return out
+
+
+def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None):
+    """alpha * op(A) @ op(B) + beta * C on the FP64 tensor-core GEMM (bcbf_gemm).  2-D float64 CUDA tensors of any
+    shape: operands are zero-padded to even extents as the kernel requires."""
+    _req(A, B, C, contiguous=False)
+    M, K = (A.shape[1], A.shape[0]) if transa else A.shape
+    K2, N = (B.shape[1], B.shape[0]) if transb else B.shape
+    if K != K2:
+        raise RuntimeError("gemm: inner dimensions differ (%d vs %d)" % (K, K2))
+    e = lambda v: (v + 1) // 2 * 2
+    Me, Ne, Ke = e(M), e(N), e(K)
+    Ap = _even_pad(A, *((Ke, Me) if transa else (Me, Ke)))
+    Bp = _even_pad(B, *((Ne, Ke) if transb else (Ke, Ne)))
+    Cp = torch.zeros(Me, Ne, dtype=torch.float64, device=A.device)
+    if C is not None and beta != 0.0:
+        Cp[:M, :N] = C
+    check(_lib.load().bcbf_gemm(int(transa), int(transb), Me, Ne, Ke, float(alpha), _ptr(Ap), Ap.stride(0), _ptr(Bp),
+                                Bp.stride(0), float(beta), _ptr(Cp), Cp.stride(0), _stream()))
+    return Cp[:M, :N]
 
 
 def rbf_blocks(X1, X2, lengthscale, outputscale, grad=False, hess=False):
@@ -97,7 +143,8 @@ def trtri(L, dinv):
 
 def trmm_lower(A, Bm, trans=False, alpha=1.0):
     """C = alpha * op(A) @ Bm with A (Npad,Npad) lower triangular; Bm (Npad, ncols)."""
-    _req(A, Bm)
+    _req(A)
+    _req(Bm, contiguous=False)
     Npad = A.shape[0]
     ncols = Bm.shape[1]
     ld = (ncols + 1) // 2 * 2
@@ -160,3 +207,36 @@ def cbc1_terms(Mk, Bk, A, grad_h, h, gamma, Fbar=None):
                                       p, Q, _ptr(bfe), _ptr(e), _ptr(Asq), _ptr(A_socp), _ptr(bfb), _ptr(status),
                                       _stream()))
     return bfe, e, Asq, A_socp, bfb, status
+
+
+def gram_train_backward(X, UH, B, lengthscale, outputscale, Pinv, alphaAi, alpha):
+    """sum_ij Gbar_ij dKb_ij/dtheta with Gbar = 1/2 (alphaAi alpha^T - nout P): returns (g_outputscale (),
+    g_lengthscale (n,), g_B (p,p)).  Pinv (>=N, ldp) is Kb^-1; alphaAi, alpha (N, nout) contiguous."""
+    _req(X, UH, B, lengthscale, Pinv, alphaAi, alpha)
+    N, n = X.shape
+    p = UH.shape[1]
+    nout = alpha.shape[1]
+    lib = _lib.load()
+    import ctypes
+    oe, mn, mp = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib.bcbf_gram_backward_layout(ctypes.byref(oe), ctypes.byref(mn), ctypes.byref(mp))
+    nblk = ((N + 63) // 64) ** 2
+    partial = torch.empty(nblk * oe.value, dtype=torch.float64, device=X.device)
+    out = torch.empty(oe.value, dtype=torch.float64, device=X.device)
+    check(lib.bcbf_gram_train_backward(_ptr(X), _ptr(UH), _ptr(B), _ptr(lengthscale), float(outputscale), N, n, p,
+                                       _ptr(Pinv), Pinv.stride(0), _ptr(alphaAi), _ptr(alpha), alpha.stride(0), nout,
+                                       _ptr(partial), partial.numel(), _ptr(out), _stream()))
+    gB = out[1 + mn.value:1 + mn.value + mp.value * mp.value].reshape(mp.value, mp.value)[:p, :p]
+    return out[0], out[1:1 + n], gB
+
+
+def socp_factor(Asq, reg=0.0):
+    """Batched Asq (Q,p,p) = Ls Ls^T -> (A_socp (Q,p,m), bfb (Q,p), status (Q,))."""
+    _req(Asq)
+    Q, p, _ = Asq.shape
+    f64 = dict(dtype=torch.float64, device=Asq.device)
+    A_socp = torch.empty(Q, p, p - 1, **f64)
+    bfb = torch.empty(Q, p, **f64)
+    status = torch.empty(Q, dtype=torch.int32, device=Asq.device)
+    check(_lib.load().bcbf_socp_factor(_ptr(Asq), p, Q, float(reg), _ptr(A_socp), _ptr(bfb), _ptr(status), _stream()))
+    return A_socp, bfb, status

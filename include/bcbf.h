@@ -64,6 +64,15 @@ int bcbf_gram_train(const double* X, const double* UH, const double* Bmat, const
 int bcbf_cross_gram(const double* X, const double* Xq, const double* lengthscale, double outputscale, int N,
                     int Q, int n, double* Kstar, int ldks, int Npad, void* stream);
 
+/* General control-affine Gram between two point sets (no padding):
+ *   out[i, j] = k(x1_i, x2_j) * (uh1_i^T B uh2_j)        (a, c; ld >= c)
+ * Replaces kb* = k_xs(Xtrain, Xtest) * (UHtrain @ B @ UHtest.t()) and kb** = k_ss(Xtest, Xtestp) * (UHtest @ B @
+ * UHtestp.t()) of custom_predict (control_affine_model.py:536, :549-553) and, with one-hot uh2 rows, the
+ * frakB(x) matrix of the Exact class (:1051).  UH1 = UH2 = NULL gives the plain data kernel k(X1, X2).    */
+int bcbf_gram_ca(const double* X1, const double* UH1, int a, const double* X2, const double* UH2, int c,
+                 const double* Bmat, const double* lengthscale, double outputscale, int n, int p, double* out,
+                 int ld, void* stream);
+
 /* General k(X1, X2) (a x c) dense, plus optional closed-form derivative blocks
  *   dK[i,j,:]   = d k(x1_i, x2_j) / d x1_i                      (a,c,n)     [may be NULL]
  *   d2K[i,j,:,:] = d^2 k(x1_i, x2_j) / d x1_i d x2_j^T           (a,c,n,n)   [may be NULL]
@@ -71,6 +80,19 @@ int bcbf_cross_gram(const double* X, const double* Xq, const double* lengthscale
  * (control_affine_model.py:465-477, misc.py:236-245).                                                   */
 int bcbf_rbf_blocks(const double* X1, const double* X2, const double* lengthscale, double outputscale, int a,
                     int c, int n, double* K, double* dK, double* d2K, void* stream);
+
+/* Hyper-parameter gradient of the train Gram matrix (backward of bcbf_gram_train; the fit path).
+ * With P = Kb^-1 (N,N; ldp), alpha = P Y (N,nout; lda) and alphaAi = alpha A^-1, the adjoint of the MVGP log marginal
+ * likelihood w.r.t. Kb is Gbar = 1/2 (alphaAi alpha^T - nout P)  (SURVEY 8a-13); this accumulates
+ *     out[0] = sum Gbar dKb/d outputscale,  out[1+d] = sum Gbar dKb/d lengthscale_d  (d < n),
+ *     out[1+BCBF_MAX_N_DIM + a*BCBF_MAX_P_DIM + b] = sum Gbar dKb/dB_ab
+ * deterministically (per-tile partials in `partial`, >= ceil(N/64)^2 * out_elems doubles, then a fixed-order sum).
+ * Replaces autograd through ExactMarginalLogLikelihood (control_affine_model.py:309-325).                        */
+int bcbf_gram_train_backward(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                             double outputscale, int N, int n, int p, const double* Pinv, int ldp,
+                             const double* alphaAi, const double* alpha, int lda, int nout, double* partial,
+                             long long partial_elems, double* out, void* stream);
+int bcbf_gram_backward_layout(int* out_elems, int* max_n, int* max_p);
 
 /* ------------------------------------------------------------------------------------------------
  * (2) Blocked FP64 Cholesky  A + scale*diag(jitter) = L L^T, in place, lower (upper triangle is zeroed).
@@ -96,6 +118,13 @@ int bcbf_trtri(const double* L, const double* dinv, double* Linv, double* scratc
  * Used for  v = Linv @ kb*,  alpha = Linv^T (Linv Y).                                                  */
 int bcbf_trmm_lower(const double* A, int lda, int Npad, int trans, const double* B, int ldb, int ncols,
                     double alpha, double beta, double* C, int ldc, void* stream);
+
+/* Row-major C(M,N) = alpha * op(A) op(B) + beta * C on the FP64 tensor-core GEMM.  op(A) is M x K: transa = 0 ->
+ * A stored (M,K), 1 -> stored (K,M);  op(B) is K x N: transb = 0 -> stored (K,N), 1 -> stored (N,K).  M, N, K and
+ * the leading dimensions must be even and the pointers 16-byte aligned (callers zero-pad).  Replaces the dense
+ * products of custom_predict: kb*^T alpha (:547), v^T v' (:586), kb*^T.reshape(bp,N) @ Bdagger (:1079-1088).   */
+int bcbf_gemm(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
+              int ldb, double beta, double* C, int ldc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (3) Batched posterior of F(x) over many query states (matrix form).
@@ -133,6 +162,13 @@ int bcbf_posterior_fu(const double* Linv, int ld, int Npad, const double* Kstar,
 int bcbf_cbc1_terms(const double* Mk, const double* Bk, const double* Amat, const double* grad_h, const double* h,
                     const double* Fbar, double gamma, int n, int p, int Q, double* bfe, double* e, double* Asq,
                     double* A_socp, double* bfb, int* status, void* stream);
+
+/* Batched  Asq (Q,p,p) = Ls Ls^T,  A_socp = Ls^T[:,1:] (Q,p,m),  bfb = Ls^T[:,0] (Q,p): the Cholesky inside
+ * convert_cbc_terms_to_socp_terms (controllers.py:446-451, unicycle_move_to_pose.py:861).  reg > 0 enables the
+ * reference's singular fallback (retry once with Asq + reg I; controllers.py:447-449 uses 1e-3).
+ * status (Q, may be NULL) = 0 or 1 + index of the non-positive pivot of the last attempt.                   */
+int bcbf_socp_factor(const double* Asq, int p, int Q, double reg, double* A_socp, double* bfb, int* status,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Model handle: owns device memory for one fitted MVGP; HOST-pointer interface (pinned or pageable).
