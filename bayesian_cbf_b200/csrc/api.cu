@@ -442,7 +442,7 @@ extern "C" int bcbf_model_query_device(bcbf_model* m, const double* Xq, const do
   BCBF_REQUIRE(m && Xq, "bcbf_model_query_device: null pointer");
   if (!m->fitted) { set_last_error("bcbf_model_query_device: model is not fitted"); return BCBF_ERR_NOT_FITTED; }
   BCBF_CUDA(cudaSetDevice(m->device));
-  cudaStream_t s = stream_ ? static_cast<cudaStream_t>(stream_) : m->stream;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);  // exactly the caller's stream (NULL = the default stream)
   const int n = m->hyp.n, p = m->hyp.p, mm = p - 1;
   const int QB = query_batch(p);
   int rc = ensure_query_capacity(m, Q < QB ? Q : QB);

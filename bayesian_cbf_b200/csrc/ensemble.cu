@@ -1,0 +1,276 @@
+// Ensembles of small independent MVGPs (one per rollout; BASELINE configs[4]: 4096 rollouts, N <= 200 training points
+// each, one query state per control step).  Every rollout has its own training set, hyper-parameters and factor.
+//
+//   ens_gram_kernel      Kb_r = k_r(X_r, X_r) o (UH_r B_r UH_r^T), padded to Npad with the identity    (batched Gram)
+//   ens_prep_kernel      G_r = UH_r B_r,  Y_r = Xdot_r - UH_r C_r
+//   ens_w_kernel         W_r = alpha_r (.) G_r
+//   ens_posterior_kernel one CTA per rollout: k*(x_r), frakB = k* G, M_k = C^T + k*^T W,  V = L^-1 frakB streamed row by
+//                        row from HBM (lower triangle only), B_k = s B - V^T V.
+// The per-step posterior is HBM-bound: 4 N^2 bytes of L^-1 per rollout (its own factor, no reuse between rollouts)
+// against N^2 p flops — 160 KB vs 0.12 MFLOP at N = 200.  Factorisation / inverse / alpha reuse the batched DMMA
+// kernels of factor.cu.  Replaces, per rollout and control step, the b = 1 custom_predict calls of
+// ControllerCLFBayesian.control (unicycle_move_to_pose.py:880-920 -> control_affine_model.py:931-961, 983-1096).
+#include "../../include/bcbf.h"
+#include "common.cuh"
+
+namespace bcbf {
+
+constexpr int kEN = BCBF_MAX_N_DIM, kEP = BCBF_MAX_P_DIM;
+
+__global__ void __launch_bounds__(256)
+ens_gram_kernel(const double* __restrict__ X, const double* __restrict__ UH, const double* __restrict__ ls,
+                const double* __restrict__ scale, const double* __restrict__ Bm, int N, int Npad, int n, int p,
+                double* __restrict__ Kb) {
+  constexpr int T = 64;
+  __shared__ double xr[T][kEN + 1], xc[T][kEN + 1], gr[T][kEP], uc[T][kEP], il[kEN], Bs[kEP * kEP];
+  const int r = blockIdx.z, tid = threadIdx.x;
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  X += (long long)r * N * n;
+  UH += (long long)r * N * p;
+  Kb += (long long)r * Npad * Npad;
+  if (tid < n) il[tid] = 1.0 / ls[(long long)r * n + tid];
+  if (tid < p * p) Bs[tid] = Bm[(long long)r * p * p + tid];
+  __syncthreads();
+  for (int idx = tid; idx < T * n; idx += 256) {
+    int i = idx / n, d = idx % n;
+    xr[i][d] = (r0 + i < N) ? X[(long long)(r0 + i) * n + d] * il[d] : 0.0;
+    xc[i][d] = (c0 + i < N) ? X[(long long)(c0 + i) * n + d] * il[d] : 0.0;
+  }
+  for (int idx = tid; idx < T * p; idx += 256) {
+    int i = idx / p, q = idx % p;
+    double g = 0.0;
+    if (r0 + i < N)
+      for (int t = 0; t < p; ++t) g += UH[(long long)(r0 + i) * p + t] * Bs[t * p + q];
+    gr[i][q] = g;
+    uc[i][q] = (c0 + i < N) ? UH[(long long)(c0 + i) * p + q] : 0.0;
+  }
+  __syncthreads();
+  const double s = scale[r];
+  const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = ty * 4 + i, row = r0 + rl;
+    if (row >= Npad) continue;
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cl = tx * 4 + j, col = c0 + cl;
+      double out = 0.0;
+      if (row < N && col < N) {
+        double d2 = 0.0;
+        for (int d = 0; d < n; ++d) {
+          double df = xr[rl][d] - xc[cl][d];
+          d2 = fma(df, df, d2);
+        }
+        double ub = 0.0;
+        for (int q = 0; q < p; ++q) ub = fma(gr[rl][q], uc[cl][q], ub);
+        out = s * exp(-0.5 * d2) * ub;
+      } else if (row == col) {
+        out = 1.0;
+      }
+      v[j] = out;
+    }
+    const int col = c0 + tx * 4;
+    if (col + 3 < Npad) {
+      double* dst = Kb + (long long)row * Npad + col;
+      *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+    }
+  }
+}
+
+__global__ void ens_prep_kernel(const double* __restrict__ UH, const double* __restrict__ Xdot,
+                                const double* __restrict__ Bm, const double* __restrict__ C, int R, int N, int Npad,
+                                int n, int p, int ldy, double* __restrict__ G, double* __restrict__ Y) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * Npad) return;
+  const int r = (int)(idx / Npad), i = (int)(idx % Npad);
+  double uh[kEP];
+  for (int j = 0; j < p; ++j) uh[j] = (i < N) ? UH[((long long)r * N + i) * p + j] : 0.0;
+  for (int j = 0; j < p; ++j) {
+    double g = 0.0;
+    for (int t = 0; t < p; ++t) g = fma(uh[t], Bm[((long long)r * p + t) * p + j], g);
+    G[idx * p + j] = g;
+  }
+  for (int c = 0; c < ldy; ++c) {
+    double y = 0.0;
+    if (i < N && c < n) {
+      y = Xdot[((long long)r * N + i) * n + c];
+      for (int t = 0; t < p; ++t) y -= uh[t] * C[((long long)r * p + t) * n + c];
+    }
+    Y[idx * ldy + c] = y;
+  }
+}
+
+__global__ void ens_w_kernel(const double* __restrict__ alpha, int ldy, const double* __restrict__ G, long long rows,
+                             int n, int p, double* __restrict__ W) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  for (int c = 0; c < n; ++c)
+    for (int j = 0; j < p; ++j) W[(i * n + c) * p + j] = alpha[i * ldy + c] * G[i * p + j];
+}
+
+// One CTA (256 threads) per rollout.
+__global__ void __launch_bounds__(256)
+ens_posterior_kernel(const double* __restrict__ Linv, const double* __restrict__ X, const double* __restrict__ G,
+                     const double* __restrict__ W, const double* __restrict__ ls, const double* __restrict__ scale,
+                     const double* __restrict__ Bm, const double* __restrict__ C, const double* __restrict__ xq, int N,
+                     int Npad, int n, int p, double* __restrict__ Mk, double* __restrict__ Bk) {
+  extern __shared__ __align__(16) double sm[];
+  double* ks = sm;                 // [Npad]  k*(x)
+  double* fb = ks + Npad;          // [Npad][p] frakB
+  __shared__ double red[8][kEN * kEP + kEP * kEP];
+  __shared__ double xs[kEN], il[kEN];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np = n * p, npair = p * (p + 1) / 2;
+  Linv += (long long)r * Npad * Npad;
+  X += (long long)r * N * n;
+  G += (long long)r * Npad * p;
+  W += (long long)r * Npad * np;
+  if (tid < n) {
+    il[tid] = 1.0 / ls[(long long)r * n + tid];
+    xs[tid] = xq[(long long)r * n + tid];
+  }
+  __syncthreads();
+  const double s = scale[r];
+  // ---- k*, frakB and the mean partial sums ------------------------------------------------------------------
+  double macc[kEN * kEP];
+#pragma unroll
+  for (int c = 0; c < kEN * kEP; ++c) macc[c] = 0.0;
+  for (int i = tid; i < Npad; i += 256) {
+    double kv = 0.0;
+    if (i < N) {
+      double d2 = 0.0;
+      for (int d = 0; d < n; ++d) {
+        double df = (X[(long long)i * n + d] - xs[d]) * il[d];
+        d2 = fma(df, df, d2);
+      }
+      kv = s * exp(-0.5 * d2);
+    }
+    ks[i] = kv;
+    for (int q = 0; q < p; ++q) fb[i * p + q] = kv * G[(long long)i * p + q];
+#pragma unroll
+    for (int c = 0; c < kEN * kEP; ++c)
+      if (c < np) macc[c] = fma(kv, W[(long long)i * np + c], macc[c]);
+  }
+  __syncthreads();
+  // ---- V = L^-1 frakB, row by row (warp per row, coalesced), S += V_i V_i^T -----------------------------------
+  double sacc[kEP * (kEP + 1) / 2];
+#pragma unroll
+  for (int e = 0; e < kEP * (kEP + 1) / 2; ++e) sacc[e] = 0.0;
+  for (int i0 = warp * 4; i0 < N; i0 += 32) {  // 4 rows per warp iteration: independent loads in flight
+    double v[4][kEP];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < kEP; ++q) v[u][q] = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u;
+      if (i < N) {
+        const double* row = Linv + (long long)i * Npad;
+        for (int k = lane; k <= i; k += 32) {
+          const double l = row[k];
+#pragma unroll
+          for (int q = 0; q < kEP; ++q)
+            if (q < p) v[u][q] = fma(l, fb[k * p + q], v[u][q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int q = 0; q < kEP; ++q)
+        if (q < p) v[u][q] = warp_sum(v[u][q]);
+      int e = 0;
+#pragma unroll
+      for (int q = 0; q < kEP; ++q)
+#pragma unroll
+        for (int t = q; t < kEP; ++t) {
+          if (t < p) sacc[e] = fma(v[u][q], v[u][t], sacc[e]);   // q < t < p; entries with q >= p stay zero
+          ++e;
+        }
+    }
+  }
+  // ---- block reductions (fixed order: deterministic) ------------------------------------------------------------
+#pragma unroll
+  for (int c = 0; c < kEN * kEP; ++c) {
+    double t = (c < np) ? warp_sum(macc[c]) : 0.0;
+    if (lane == 0) red[warp][c] = t;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int e = 0; e < kEP * (kEP + 1) / 2; ++e) red[warp][kEN * kEP + e] = sacc[e];  // identical on every lane
+  }
+  __syncthreads();
+  if (tid < np) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][tid];
+    const int c = tid / p, j = tid % p;  // Mk[c][j] = C[j][c] + ...
+    Mk[(long long)r * np + tid] = C[((long long)r * p + j) * n + c] + t;
+  }
+  if (tid < p * p) {
+    const int a = tid / p, b = tid % p, q = a < b ? a : b, t2 = a < b ? b : a;
+    // index of the (q, t2) pair in the kEP-wide upper-triangular enumeration used above
+    int e = 0;
+    for (int qq = 0; qq < q; ++qq) e += kEP - qq;
+    e += t2 - q;
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][kEN * kEP + e];
+    Bk[(long long)r * p * p + tid] = s * Bm[(long long)r * p * p + tid] - t;
+  }
+  (void)npair;
+}
+
+}  // namespace bcbf
+
+using namespace bcbf;
+
+extern "C" int bcbf_ens_gram(const double* X, const double* UH, const double* lengthscale, const double* outputscale,
+                             const double* Bmat, int R, int N, int n, int p, double* Kb, int Npad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(X && UH && lengthscale && outputscale && Bmat && Kb, "bcbf_ens_gram: null pointer");
+  BCBF_REQUIRE(R >= 1 && N >= 1 && Npad >= N && Npad % 4 == 0 && n >= 1 && n <= kEN && p >= 1 && p <= kEP,
+               "bcbf_ens_gram: R=%d N=%d Npad=%d n=%d p=%d", R, N, Npad, n, p);
+  dim3 grid(ceil_div(Npad, 64), ceil_div(Npad, 64), R);
+  ens_gram_kernel<<<grid, 256, 0, stream>>>(X, UH, lengthscale, outputscale, Bmat, N, Npad, n, p, Kb);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_ens_prep(const double* UH, const double* Xdot, const double* Bmat, const double* C, int R, int N,
+                             int Npad, int n, int p, int ldy, double* G, double* Y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(UH && Xdot && Bmat && C && G && Y, "bcbf_ens_prep: null pointer");
+  BCBF_REQUIRE(R >= 1 && N >= 1 && Npad >= N && ldy >= n && n <= kEN && p <= kEP, "bcbf_ens_prep: bad sizes");
+  ens_prep_kernel<<<ceil_div((long long)R * Npad, 128), 128, 0, stream>>>(UH, Xdot, Bmat, C, R, N, Npad, n, p, ldy, G, Y);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_ens_w(const double* alpha, int ldy, const double* G, int R, int Npad, int n, int p, double* W,
+                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(alpha && G && W && R >= 1 && Npad >= 1, "bcbf_ens_w: bad arguments");
+  ens_w_kernel<<<ceil_div((long long)R * Npad, 128), 128, 0, stream>>>(alpha, ldy, G, (long long)R * Npad, n, p, W);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_ens_posterior(const double* Linv, const double* X, const double* G, const double* W,
+                                  const double* lengthscale, const double* outputscale, const double* Bmat,
+                                  const double* C, const double* xq, int R, int N, int Npad, int n, int p, double* Mk,
+                                  double* Bk, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(Linv && X && G && W && lengthscale && outputscale && Bmat && C && xq && Mk && Bk,
+               "bcbf_ens_posterior: null pointer");
+  BCBF_REQUIRE(R >= 1 && N >= 1 && Npad >= N && n >= 1 && n <= kEN && p >= 1 && p <= kEP,
+               "bcbf_ens_posterior: R=%d N=%d Npad=%d n=%d p=%d", R, N, Npad, n, p);
+  const int smem = (int)sizeof(double) * Npad * (1 + p);
+  BCBF_REQUIRE(smem <= 200 * 1024, "bcbf_ens_posterior: Npad=%d too large for the per-rollout kernel", Npad);
+  BCBF_CUDA(cudaFuncSetAttribute(ens_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ens_posterior_kernel<<<R, 256, smem, stream>>>(Linv, X, G, W, lengthscale, outputscale, Bmat, C, xq, N, Npad, n, p,
+                                                 Mk, Bk);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}

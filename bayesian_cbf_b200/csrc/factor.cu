@@ -12,14 +12,35 @@ namespace bcbf {
 
 constexpr int kPad = kBlk + 1;  // 129: conflict-free row and column walks of the 128x128 smem block
 
+constexpr int kSB = 32;  // sub-panel width of the in-CTA factorisation
+
+// X(r,c) of the inverse under construction: strictly-lower entries live transposed in the upper triangle of `a`,
+// the diagonal in xd.
+__device__ __forceinline__ double inv_get(const double* a, const double* xd, int r, int c) {
+  return r == c ? xd[r] : (r > c ? a[c * kPad + r] : 0.0);
+}
+
+// One CTA factorises a 128x128 diagonal block in shared memory and inverts it.  Blocked by 32 columns:
+//   A1  the 32x32 diagonal sub-block is factorised by ONE WARP in registers (lane = row), pivots and multipliers
+//       exchanged with warp shuffles — no block barrier inside the 32-step chain;
+//   A2  the rows below are solved against it, one thread per row (forward substitution in registers);
+//   A3  the trailing sub-matrix gets the rank-32 update with 4x4 register tiles on all 256 threads;
+//   B   inverse: the four 32x32 diagonal blocks by four warps (lane = column), then the off-diagonal blocks level by
+//       level, X_ij = -X_ii (sum_k L_ik X_kj), as small register-tiled products.
+// 12 + 8 block barriers instead of 128 * 5.  Batched over blockIdx.x (ensemble of small factors).
 __global__ void __launch_bounds__(256, 1)
-potf2_inv_kernel(double* __restrict__ A, int ld, int k0, const double* __restrict__ jitter, int N, double jscale,
-                 double* __restrict__ dinv, int* __restrict__ info) {
+potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restrict__ jitter_, int N, double jscale,
+                 double* __restrict__ dinv_, int* __restrict__ info_, long long sA, long long sD, long long sJ) {
   extern __shared__ __align__(16) double sm[];
   double* a = sm;                 // [128][129]
-  double* xd = sm + kBlk * kPad;  // [128] reciprocal diagonal
+  double* xd = sm + kBlk * kPad;  // [128] diagonal of the inverse
+  double* T = xd + kBlk;          // [3][32][33] scratch for the off-diagonal inverse blocks
   __shared__ int failed;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* A = A_ + (long long)blockIdx.x * sA;
+  double* dinv = dinv_ + (long long)blockIdx.x * sD;
+  const double* jitter = jitter_ ? jitter_ + (long long)blockIdx.x * sJ : nullptr;
+  int* info = info_ + blockIdx.x;
   if (tid == 0) failed = 0;
   for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
     int r = idx >> 7, c = idx & 127;
@@ -31,26 +52,94 @@ potf2_inv_kernel(double* __restrict__ A, int ld, int k0, const double* __restric
     a[r * kPad + c] = v;
   }
   __syncthreads();
-  for (int j = 0; j < kBlk; ++j) {
-    const double ajj = a[j * kPad + j];
-    if (!(ajj > 0.0)) {  // also catches NaN; uniform across the CTA
-      if (tid == 0) {
-        atomicCAS(info, 0, k0 + j + 1);
+
+  // ======================= Phase A: L L^T = block =======================================================
+  for (int pnl = 0; pnl < kBlk / kSB; ++pnl) {
+    const int c0 = pnl * kSB;
+    if (warp == 0) {  // A1
+      double r[kSB];
+#pragma unroll
+      for (int k = 0; k < kSB; ++k) r[k] = (k <= lane) ? a[(c0 + lane) * kPad + c0 + k] : 0.0;
+      int bad = 0;
+#pragma unroll
+      for (int j = 0; j < kSB; ++j) {
+        double djj = __shfl_sync(0xffffffffu, r[j], j);
+        if (!(djj > 0.0)) {  // also catches NaN; uniform across the warp
+          if (bad == 0) bad = c0 + j + 1;
+          djj = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        const double dj = sqrt(djj);
+        if (lane == j) r[j] = dj;
+        else if (lane > j) r[j] = r[j] / dj;
+#pragma unroll
+        for (int k = 0; k < kSB; ++k) {
+          if (k > j) {  // compile-time after unrolling: constant register indices, no local memory
+            const double lkj = __shfl_sync(0xffffffffu, r[j], k);
+            if (lane >= k) r[k] = fma(-r[j], lkj, r[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kSB; ++k)
+        if (k <= lane) a[(c0 + lane) * kPad + c0 + k] = r[k];
+      if (lane == 0 && bad != 0) {
+        atomicCAS(info, 0, k0 + bad);
         failed = 1;
       }
-      break;
-    }
-    const double d = sqrt(ajj);
-    __syncthreads();  // everyone has read a[j][j]
-    if (tid < kBlk) {
-      if (tid > j) a[tid * kPad + j] /= d;
-      else if (tid == j) a[j * kPad + j] = d;
     }
     __syncthreads();
-    const int i = j + 1 + (tid >> 1);
-    if (i < kBlk) {
-      const double lij = a[i * kPad + j];
-      for (int k = j + 1 + (tid & 1); k <= i; k += 2) a[i * kPad + k] -= lij * a[k * kPad + j];
+    if (failed) break;
+    const int r0 = c0 + kSB, Tn = kBlk - r0;  // trailing extent
+    if (tid < Tn) {  // A2: row i of the panel  x L_D^T = a[i, c0:c0+32]
+      const int i = r0 + tid;
+      double x[kSB];
+#pragma unroll
+      for (int j = 0; j < kSB; ++j) {
+        double sacc = a[i * kPad + c0 + j];
+#pragma unroll
+        for (int k = 0; k < kSB; ++k)
+          if (k < j) sacc = fma(-x[k], a[(c0 + j) * kPad + c0 + k], sacc);
+        x[j] = sacc / a[(c0 + j) * kPad + c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < kSB; ++j) a[i * kPad + c0 + j] = x[j];
+    }
+    __syncthreads();
+    {  // A3: trailing (lower) -= P P^T with 4x4 register tiles
+      const int nt = Tn / 4, ntiles = nt * (nt + 1) / 2;
+      for (int t = tid; t < ntiles; t += 256) {
+        int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        const double* pa = a + (r0 + 4 * ti) * kPad + c0;
+        const double* pb = a + (r0 + 4 * tj) * kPad + c0;
+        double acc[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < kSB; ++k) {
+          double va[4], vb[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            va[e] = pa[e * kPad + k];
+            vb[e] = pb[e * kPad + k];
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vb[f], acc[e][f]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const int i = r0 + 4 * ti + e, j = r0 + 4 * tj + f;
+            if (j <= i) a[i * kPad + j] -= acc[e][f];
+          }
+      }
     }
     __syncthreads();
   }
@@ -65,25 +154,87 @@ potf2_inv_kernel(double* __restrict__ A, int ld, int k0, const double* __restric
     }
     return;
   }
-  // ---- X = L^{-1}: X[i][j] (i > j) is kept at a[j][i] (strict upper part), diagonal in xd -----------
-  if (tid < kBlk) xd[tid] = 1.0 / a[tid * kPad + tid];
-  __syncthreads();
-  {
-    const int j = tid >> 1, h = tid & 1;
-    for (int i = 1; i < kBlk; ++i) {
-      double s = 0.0;
-      if (j < i) {
-        // sum_{k=j}^{i-1} L[i][k] X[k][j],  X[j][j] = xd[j]
-        for (int k = j + h; k < i; k += 2) {
-          double xkj = (k == j) ? xd[j] : a[j * kPad + k];
-          s += a[i * kPad + k] * xkj;
-        }
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      __syncthreads();  // all reads of column i of the upper part (none yet) / row i done before the write
-      if (j < i && h == 0) a[j * kPad + i] = -s * xd[i];
-      __syncthreads();
+
+  // ======================= Phase B: X = L^{-1} ==========================================================
+  if (warp < kBlk / kSB) {  // B1: diagonal 32x32 blocks, lane = column j
+    const int b0 = warp * kSB, j = lane;
+    double x[kSB];
+#pragma unroll
+    for (int i = 0; i < kSB; ++i) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k < kSB; ++k)
+        if (k < i && k >= j) sacc = fma(a[(b0 + i) * kPad + b0 + k], x[k], sacc);
+      const double dii = 1.0 / a[(b0 + i) * kPad + b0 + i];
+      x[i] = (i == j) ? dii : (i > j ? -sacc * dii : 0.0);
     }
+    __syncwarp();  // every lane has finished reading the block's L entries (they are untouched anyway: upper side)
+#pragma unroll
+    for (int i = 0; i < kSB; ++i) {
+      if (i == j) xd[b0 + j] = x[i];
+      else if (i > j) a[(b0 + j) * kPad + b0 + i] = x[i];
+    }
+  }
+  __syncthreads();
+  for (int d = 1; d < kBlk / kSB; ++d) {  // B2: block (bi, bj) with bi - bj = d
+    const int nblk = kBlk / kSB - d;
+    // T_b = sum_{kb = bj}^{bi-1} L[bi, kb] X[kb, bj]      (32 x 32 each), 4x4 register tiles
+    for (int t = tid; t < nblk * 64; t += 256) {
+      const int b = t >> 6, tt = t & 63, ti = tt >> 3, tj = tt & 7;
+      const int bj = b, bi = b + d;
+      double acc[4][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+      for (int k = bj * kSB; k < bi * kSB; ++k) {
+        double va[4], vb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          va[e] = a[(bi * kSB + 4 * ti + e) * kPad + k];
+          vb[e] = inv_get(a, xd, k, bj * kSB + 4 * tj + e);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vb[f], acc[e][f]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) T[(b * kSB + 4 * ti + e) * (kSB + 1) + 4 * tj + f] = acc[e][f];
+    }
+    __syncthreads();
+    // X[bi, bj] = -X[bi, bi] T_b
+    for (int t = tid; t < nblk * 64; t += 256) {
+      const int b = t >> 6, tt = t & 63, ti = tt >> 3, tj = tt & 7;
+      const int bj = b, bi = b + d;
+      double acc[4][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+      for (int k = 0; k < kSB; ++k) {
+        double va[4], vb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          va[e] = inv_get(a, xd, bi * kSB + 4 * ti + e, bi * kSB + k);
+          vb[e] = T[(b * kSB + k) * (kSB + 1) + 4 * tj + e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vb[f], acc[e][f]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          const int r = bi * kSB + 4 * ti + e, c = bj * kSB + 4 * tj + f;  // r > c always (d >= 1)
+          a[c * kPad + r] = -acc[e][f];
+        }
+    }
+    __syncthreads();
   }
   for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
     int r = idx >> 7, c = idx & 127;
@@ -94,8 +245,9 @@ potf2_inv_kernel(double* __restrict__ A, int ld, int k0, const double* __restric
   }
 }
 
-__global__ void zero_upper_blocks_kernel(double* __restrict__ A, int ld, int nb) {
-  // one CTA per strictly-upper 128x128 block (bi < bj)
+__global__ void zero_upper_blocks_kernel(double* __restrict__ A, int ld, int nb, long long sA) {
+  // one CTA per strictly-upper 128x128 block (bi < bj); blockIdx.y = batch
+  A += (long long)blockIdx.y * sA;
   int t = blockIdx.x;
   int bj = (int)((sqrt(8.0 * t + 1.0) + 1.0) * 0.5);
   while ((long long)bj * (bj - 1) / 2 > t) --bj;
@@ -108,9 +260,10 @@ __global__ void zero_upper_blocks_kernel(double* __restrict__ A, int ld, int nb)
   }
 }
 
-__global__ void scatter_diag_blocks_kernel(const double* __restrict__ dinv, double* __restrict__ Linv, int ld) {
-  const double* src = dinv + (long long)blockIdx.x * kBlk * kBlk;
-  double* dst = Linv + (long long)blockIdx.x * kBlk * (ld + 1);
+__global__ void scatter_diag_blocks_kernel(const double* __restrict__ dinv, double* __restrict__ Linv, int ld,
+                                           long long sD, long long sL) {
+  const double* src = dinv + (long long)blockIdx.y * sD + (long long)blockIdx.x * kBlk * kBlk;
+  double* dst = Linv + (long long)blockIdx.y * sL + (long long)blockIdx.x * kBlk * (ld + 1);
   for (int idx = threadIdx.x; idx < kBlk * kBlk / 2; idx += blockDim.x) {
     int r = idx >> 6, c = (idx & 63) * 2;
     *reinterpret_cast<double2*>(dst + (long long)r * ld + c) = *reinterpret_cast<const double2*>(src + r * kBlk + c);
@@ -123,42 +276,78 @@ using namespace bcbf;
 
 extern "C" long long bcbf_dinv_elems(int Npad) { return (long long)(Npad / kBlk) * kBlk * kBlk; }
 
-extern "C" int bcbf_potrf(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale,
-                          double* dinv, int* info, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// R independent factorisations of equal size (R = 1: the single-matrix entry point).  Strides in elements:
+// sA between matrices, sD between dinv blocks sets, sJ between jitter vectors; info is int[R].
+static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale, double* dinv,
+                      int* info, int R, long long sA, long long sD, long long sJ, cudaStream_t stream) {
   BCBF_REQUIRE(A && dinv && info, "bcbf_potrf: null pointer");
   BCBF_REQUIRE(Npad > 0 && Npad % kBlk == 0 && ld >= Npad && ld % 2 == 0 && N <= Npad && N >= 0,
                "bcbf_potrf: Npad=%d must be a positive multiple of %d, ld=%d >= Npad and even, N=%d <= Npad", Npad,
                kBlk, ld, N);
   const int nb = Npad / kBlk;
-  const int smem = (kBlk * kPad + kBlk) * (int)sizeof(double);
+  const int smem = (kBlk * kPad + kBlk + 3 * kSB * (kSB + 1)) * (int)sizeof(double);
   BCBF_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  BCBF_CUDA(cudaMemsetAsync(info, 0, sizeof(int), stream));
-  for (int k = 0; k < nb; ++k) {
-    const int k0 = k * kBlk;
-    double* dk = dinv + (long long)k * kBlk * kBlk;
-    potf2_inv_kernel<<<1, 256, smem, stream>>>(A, ld, k0, jitter, N, jitter_scale, dk, info);
-    BCBF_LAUNCH_CHECK();
-    const int rows = Npad - (k0 + kBlk);
-    if (rows <= 0) break;
-    double* panel = A + (long long)(k0 + kBlk) * ld + k0;
-    GemmArgs g{};
-    // panel <- panel * Dinv_k^T       (L_ik = A_ik L_kk^{-T})
-    g.A = panel; g.lda = ld; g.B = dk; g.ldb = kBlk; g.C = panel; g.ldc = ld;
-    g.M = rows; g.N = kBlk; g.K = kBlk; g.alpha = 1.0; g.beta = 0.0; g.tri = kTriNone;
-    BCBF_CUDA((launch_gemm<true, true>(g, 1, stream)));
-    // trailing (lower tiles) -= panel panel^T
-    GemmArgs s{};
-    s.A = panel; s.lda = ld; s.B = panel; s.ldb = ld;
-    s.C = A + (long long)(k0 + kBlk) * (ld + 1); s.ldc = ld;
-    s.M = rows; s.N = rows; s.K = kBlk; s.alpha = -1.0; s.beta = 1.0; s.tri = kTriLowerOut;
-    BCBF_CUDA((launch_gemm<true, true>(s, 1, stream)));
+  BCBF_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * (size_t)R, stream));
+  // Two-level blocking: outer block columns of kOuter = 512; inside one, a right-looking sweep over 128-wide panels
+  // whose updates stay within the block column (K = 128, small); the bulk of the N^3/3 flops runs in ONE trailing
+  // SYRK per outer block with K = 512, where the DMMA GEMM's pipeline fill is amortised over 32 k-steps.
+  constexpr int kOuter = 4;  // in units of 128-blocks
+  for (int J = 0; J < nb; J += kOuter) {
+    const int jend = (J + kOuter < nb) ? J + kOuter : nb;  // exclusive, in blocks
+    for (int k = J; k < jend; ++k) {
+      const int k0 = k * kBlk;
+      double* dk = dinv + (long long)k * kBlk * kBlk;
+      potf2_inv_kernel<<<R, 256, smem, stream>>>(A, ld, k0, jitter, N, jitter_scale, dk, info, sA, sD, sJ);
+      BCBF_LAUNCH_CHECK();
+      const int rows = Npad - (k0 + kBlk);
+      if (rows <= 0) break;
+      double* panel = A + (long long)(k0 + kBlk) * ld + k0;
+      GemmArgs g{};
+      // panel <- panel * Dinv_k^T       (L_ik = A_ik L_kk^{-T})
+      g.A = panel; g.lda = ld; g.B = dk; g.ldb = kBlk; g.C = panel; g.ldc = ld;
+      g.M = rows; g.N = kBlk; g.K = kBlk; g.alpha = 1.0; g.beta = 0.0; g.tri = kTriNone;
+      g.sA = sA; g.sB = sD; g.sC = sA;
+      BCBF_CUDA((launch_gemm<true, true>(g, R, stream)));
+      // inside the outer block column: columns (k+1)*128 .. jend*128, all rows below  -= panel panel^T
+      const int w = (jend - (k + 1)) * kBlk;
+      if (w > 0) {
+        GemmArgs u{};
+        u.A = panel; u.lda = ld; u.B = panel; u.ldb = ld;
+        u.C = A + (long long)(k0 + kBlk) * (ld + 1); u.ldc = ld;
+        u.M = rows; u.N = w; u.K = kBlk; u.alpha = -1.0; u.beta = 1.0; u.tri = kTriNone;
+        u.sA = u.sB = u.sC = sA;
+        BCBF_CUDA((launch_gemm<true, true>(u, R, stream)));
+      }
+    }
+    const int c1 = jend * kBlk, rows = Npad - c1;
+    if (rows > 0) {
+      // trailing (lower tiles) -= P P^T,  P = A[c1:, J*128 : c1]   (K up to 512)
+      const double* P = A + (long long)c1 * ld + (long long)J * kBlk;
+      GemmArgs t{};
+      t.A = P; t.lda = ld; t.B = P; t.ldb = ld;
+      t.C = A + (long long)c1 * (ld + 1); t.ldc = ld;
+      t.M = rows; t.N = rows; t.K = c1 - J * kBlk; t.alpha = -1.0; t.beta = 1.0; t.tri = kTriLowerOut;
+      t.sA = t.sB = t.sC = sA;
+      BCBF_CUDA((launch_gemm<true, true>(t, R, stream)));
+    }
   }
   if (nb > 1) {
-    zero_upper_blocks_kernel<<<nb * (nb - 1) / 2, 256, 0, stream>>>(A, ld, nb);
+    zero_upper_blocks_kernel<<<dim3(nb * (nb - 1) / 2, R), 256, 0, stream>>>(A, ld, nb, sA);
     BCBF_LAUNCH_CHECK();
   }
   return BCBF_OK;
+}
+
+extern "C" int bcbf_potrf(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale,
+                          double* dinv, int* info, void* stream_) {
+  return potrf_impl(A, ld, Npad, N, jitter, jitter_scale, dinv, info, 1, 0, 0, 0, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int bcbf_potrf_batched(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale,
+                                  double* dinv, int* info, int R, void* stream_) {
+  BCBF_REQUIRE(R >= 1, "bcbf_potrf_batched: R=%d", R);
+  return potrf_impl(A, ld, Npad, N, jitter, jitter_scale, dinv, info, R, (long long)ld * Npad,
+                    bcbf_dinv_elems(Npad), N, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int bcbf_check_info(const int* info, void* stream_) {
@@ -173,14 +362,15 @@ extern "C" int bcbf_check_info(const int* info, void* stream_) {
   return BCBF_OK;
 }
 
-extern "C" int bcbf_trtri(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad,
-                          void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// R independent triangular inverses (stride sL between factor-sized matrices, sD between dinv block sets).
+static int trtri_impl(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad, int R,
+                      long long sL, long long sD, cudaStream_t stream) {
   BCBF_REQUIRE(L && dinv && Linv && scratch, "bcbf_trtri: null pointer");
   BCBF_REQUIRE(Npad > 0 && Npad % kBlk == 0 && ld >= Npad && ld % 2 == 0, "bcbf_trtri: bad Npad=%d / ld=%d", Npad, ld);
   const int nb = Npad / kBlk;
-  BCBF_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)ld * Npad, stream));
-  scatter_diag_blocks_kernel<<<nb, 256, 0, stream>>>(dinv, Linv, ld);
+  if (R == 1) BCBF_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)ld * Npad, stream));
+  else BCBF_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)sL * R, stream));
+  scatter_diag_blocks_kernel<<<dim3(nb, R), 256, 0, stream>>>(dinv, Linv, ld, sD, sL);
   BCBF_LAUNCH_CHECK();
   for (int hb = 1; hb < nb; hb *= 2) {
     const int h = hb * kBlk;
@@ -188,12 +378,23 @@ extern "C" int bcbf_trtri(const double* L, const double* dinv, double* Linv, dou
     const int npairs_full = Npad / (2 * h);                          // both halves complete
     const int rem = Npad - npairs_full * 2 * h;                      // leftover rows after the full pairs
     const int partial_rows = rem > h ? rem - h : 0;                  // clipped second half of the last pair
-    for (int pass = 0; pass < 2; ++pass) {
-      const int batch = pass == 0 ? npairs_full : (partial_rows > 0 ? 1 : 0);
+    // a single matrix batches over the pairs of a level; an ensemble batches over the matrices and loops the pairs
+    const int npass = (R == 1) ? 2 : npairs_full + (partial_rows > 0 ? 1 : 0);
+    for (int pass = 0; pass < npass; ++pass) {
+      int batch, M2;
+      long long r0, stride;
+      if (R == 1) {
+        batch = pass == 0 ? npairs_full : (partial_rows > 0 ? 1 : 0);
+        r0 = pass == 0 ? 0 : (long long)npairs_full * 2 * h;
+        M2 = pass == 0 ? h : partial_rows;
+        stride = (long long)2 * h * (ld + 1);
+      } else {
+        batch = R;
+        r0 = (long long)pass * 2 * h;
+        M2 = pass < npairs_full ? h : partial_rows;
+        stride = sL;
+      }
       if (batch == 0) continue;
-      const long long r0 = pass == 0 ? 0 : (long long)npairs_full * 2 * h;
-      const int M2 = pass == 0 ? h : partial_rows;
-      const long long stride = (long long)2 * h * (ld + 1);
       GemmArgs t{};  // T = L21 * X11
       t.A = L + (r0 + h) * ld + r0; t.lda = ld;
       t.B = Linv + r0 * (ld + 1); t.ldb = ld;
@@ -213,9 +414,39 @@ extern "C" int bcbf_trtri(const double* L, const double* dinv, double* Linv, dou
   return BCBF_OK;
 }
 
+extern "C" int bcbf_trtri(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad,
+                          void* stream_) {
+  return trtri_impl(L, dinv, Linv, scratch, ld, Npad, 1, 0, 0, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int bcbf_trtri_batched(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad,
+                                  int R, void* stream_) {
+  BCBF_REQUIRE(R >= 1, "bcbf_trtri_batched: R=%d", R);
+  return trtri_impl(L, dinv, Linv, scratch, ld, Npad, R, (long long)ld * Npad, bcbf_dinv_elems(Npad),
+                    static_cast<cudaStream_t>(stream_));
+}
+
+static int trmm_impl(const double* A, int lda, int Npad, int trans, const double* B, int ldb, int ncols, double alpha,
+                     double beta, double* C, int ldc, int R, long long sA, long long sB, long long sC,
+                     cudaStream_t stream);
+
 extern "C" int bcbf_trmm_lower(const double* A, int lda, int Npad, int trans, const double* B, int ldb, int ncols,
                                double alpha, double beta, double* C, int ldc, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return trmm_impl(A, lda, Npad, trans, B, ldb, ncols, alpha, beta, C, ldc, 1, 0, 0, 0,
+                   static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int bcbf_trmm_lower_batched(const double* A, int lda, int Npad, int trans, const double* B, int ldb,
+                                       int ncols, double alpha, double beta, double* C, int ldc, int R,
+                                       void* stream_) {
+  BCBF_REQUIRE(R >= 1, "bcbf_trmm_lower_batched: R=%d", R);
+  return trmm_impl(A, lda, Npad, trans, B, ldb, ncols, alpha, beta, C, ldc, R, (long long)lda * Npad,
+                   (long long)ldb * Npad, (long long)ldc * Npad, static_cast<cudaStream_t>(stream_));
+}
+
+static int trmm_impl(const double* A, int lda, int Npad, int trans, const double* B, int ldb, int ncols, double alpha,
+                     double beta, double* C, int ldc, int R, long long sA, long long sB, long long sC,
+                     cudaStream_t stream) {
   BCBF_REQUIRE(A && B && C, "bcbf_trmm_lower: null pointer");
   BCBF_REQUIRE(Npad > 0 && Npad % kBlk == 0 && lda >= Npad && lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0 &&
                    ncols > 0 && ncols % 2 == 0 && ldb >= ncols && ldc >= ncols,
@@ -224,12 +455,13 @@ extern "C" int bcbf_trmm_lower(const double* A, int lda, int Npad, int trans, co
   GemmArgs g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
   g.M = Npad; g.N = ncols; g.K = Npad; g.alpha = alpha; g.beta = beta;
+  g.sA = sA; g.sB = sB; g.sC = sC;
   if (!trans) {
     g.tri = kTriALower;
-    BCBF_CUDA((launch_gemm<true, false>(g, 1, stream)));
+    BCBF_CUDA((launch_gemm<true, false>(g, R, stream)));
   } else {
     g.tri = kTriAUpper;
-    BCBF_CUDA((launch_gemm<false, false>(g, 1, stream)));
+    BCBF_CUDA((launch_gemm<false, false>(g, R, stream)));
   }
   return BCBF_OK;
 }

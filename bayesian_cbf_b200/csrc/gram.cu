@@ -212,13 +212,27 @@ __global__ void gram_backward_finalize_kernel(const double* __restrict__ partial
   if (lane == 0) out[t] = v;
 }
 
-static int fill_common(GramParams& P, const double* lengthscale_dev, double outputscale, int n, cudaStream_t stream) {
-  double ls[kMaxN];
-  // hyper-parameters are tiny: fetch them synchronously on the stream (device pointer by ABI convention)
-  cudaError_t e = cudaMemcpyAsync(ls, lengthscale_dev, sizeof(double) * n, cudaMemcpyDefault, stream);
-  if (e != cudaSuccess) return cuda_fail(e, "copy lengthscale", __FILE__, __LINE__);
+// Small parameter blocks (lengthscale, B) may live on the host or on the device.  Host pointers are read directly;
+// device pointers are fetched on the stream (one short synchronisation — the torch-tensor call path).
+static int fetch_small(double* dst, const double* src, int count, cudaStream_t stream) {
+  cudaPointerAttributes attr{};
+  cudaError_t e = cudaPointerGetAttributes(&attr, src);
+  if (e != cudaSuccess) { cudaGetLastError(); attr.type = cudaMemoryTypeUnregistered; }
+  if (attr.type == cudaMemoryTypeUnregistered || attr.type == cudaMemoryTypeHost) {
+    for (int i = 0; i < count; ++i) dst[i] = src[i];
+    return BCBF_OK;
+  }
+  e = cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "copy hyper-parameters", __FILE__, __LINE__);
   e = cudaStreamSynchronize(stream);
-  if (e != cudaSuccess) return cuda_fail(e, "sync lengthscale", __FILE__, __LINE__);
+  if (e != cudaSuccess) return cuda_fail(e, "sync hyper-parameters", __FILE__, __LINE__);
+  return BCBF_OK;
+}
+
+static int fill_common(GramParams& P, const double* lengthscale, double outputscale, int n, cudaStream_t stream) {
+  double ls[kMaxN];
+  int rc = fetch_small(ls, lengthscale, n, stream);
+  if (rc != BCBF_OK) return rc;
   for (int d = 0; d < n; ++d) P.inv_ls[d] = 1.0 / ls[d];
   P.scale = outputscale;
   P.n = n;
@@ -241,8 +255,7 @@ extern "C" int bcbf_gram_train(const double* X, const double* UH, const double* 
   GramParams P{};
   int rc = fill_common(P, lengthscale, outputscale, n, stream);
   if (rc != BCBF_OK) return rc;
-  BCBF_CUDA(cudaMemcpyAsync(P.Bm, Bmat, sizeof(double) * p * p, cudaMemcpyDefault, stream));
-  BCBF_CUDA(cudaStreamSynchronize(stream));
+  if ((rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
   P.X1 = X; P.X2 = X; P.UH = UH; P.UH2 = UH; P.a = N; P.c = N; P.p = p;
   P.out = Kb; P.ld = ld; P.rows_out = Npad; P.cols_out = Npad; P.pad_identity = 1; P.vec_ok = 1;
   dim3 grid(ceil_div(Npad, kGT), ceil_div(Npad, kGT));
@@ -280,10 +293,7 @@ extern "C" int bcbf_gram_ca(const double* X1, const double* UH1, int a, const do
   GramParams P{};
   int rc = fill_common(P, lengthscale, outputscale, n, stream);
   if (rc != BCBF_OK) return rc;
-  if (UH1) {
-    BCBF_CUDA(cudaMemcpyAsync(P.Bm, Bmat, sizeof(double) * p * p, cudaMemcpyDefault, stream));
-    BCBF_CUDA(cudaStreamSynchronize(stream));
-  }
+  if (UH1 && (rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
   P.X1 = X1; P.X2 = X2; P.UH = UH1; P.UH2 = UH2; P.a = a; P.c = c; P.p = UH1 ? p : 0;
   P.out = out; P.ld = ld; P.rows_out = a; P.cols_out = c; P.pad_identity = 0;
   dim3 grid(ceil_div(c, kGT), ceil_div(a, kGT));
@@ -323,8 +333,7 @@ extern "C" int bcbf_gram_train_backward(const double* X, const double* UH, const
   GramParams P{};
   int rc = fill_common(P, lengthscale, outputscale, n, stream);
   if (rc != BCBF_OK) return rc;
-  BCBF_CUDA(cudaMemcpyAsync(P.Bm, Bmat, sizeof(double) * p * p, cudaMemcpyDefault, stream));
-  BCBF_CUDA(cudaStreamSynchronize(stream));
+  if ((rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
   P.X1 = X; P.X2 = X; P.UH = UH; P.UH2 = UH; P.a = N; P.c = N; P.p = p;
   dim3 grid(ceil_div(N, kGT), ceil_div(N, kGT));
   const long long nblocks = (long long)grid.x * grid.y;

@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
 
   if (warp == kPMmaWarps) {
     // ================= producer: L^-1[I rows, k..k+32) -> As[128][36]; K*[k..k+32, q0..q0+TQ) -> Ks[32][TQ+4];
-    //                   G[k..k+32, :] -> Gs (packed) ===============================================================
+    //                   G[k..k+32, :] -> Gs (packed).  16-byte cp.async (LDGSTS) only; completion of a lane's copies
+    //                   arrives on full[s] (cp.async.mbarrier.arrive).  Measured alternative: one 256-byte
+    //                   cp.async.bulk (TMA unit, UBLKCP) per tile row — 161 small bulk copies per stage made the producer
+    //                   the bottleneck (25.6 vs 32.3 TFLOP/s), so the LDGSTS path is kept. ======
     int slot = 0;
     unsigned phase = 0;
     const double* gK0 = a.Kstar + q0;
@@ -306,7 +309,19 @@ post_mean_partial_kernel(const double* __restrict__ Kstar, int ldks, const doubl
     for (int idx = threadIdx.x; idx < rows * nc; idx += kMeanThreads) Wsm[idx / nc][idx % nc] = W[(long long)(ib + idx / nc) * nc + idx % nc];
     __syncthreads();
     if (q < Q) {
-      for (int r = 0; r < rows; ++r) {
+      // 8 independent K* loads in flight per thread (the loop is latency-bound otherwise)
+      int r = 0;
+      for (; r + 8 <= rows; r += 8) {
+        double kv8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kv8[u] = Kstar[(long long)(ib + r + u) * ldks + q];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int c = 0; c < BCBF_MAX_N_DIM * BCBF_MAX_P_DIM; ++c)
+            if (c < nc) acc[c] = fma(kv8[u], Wsm[r + u][c], acc[c]);
+      }
+      for (; r < rows; ++r) {
         const double kvv = Kstar[(long long)(ib + r) * ldks + q];
 #pragma unroll
         for (int c = 0; c < BCBF_MAX_N_DIM * BCBF_MAX_P_DIM; ++c)
@@ -452,7 +467,7 @@ static int run_mean(const double* Kstar, int ldks, const double* W, const double
                     double* Mk, cudaStream_t stream) {
   const int nc = n * p;
   const int qblocks = ceil_div(Q, kMeanThreads);
-  int nsplit = 296 / qblocks;
+  int nsplit = (148 * 16) / qblocks;  // ~16 CTAs of 128 threads per SM: enough loads in flight to stream K* at HBM rate
   if (nsplit < 1) nsplit = 1;
   int max_split = ceil_div(N, kMeanRows);
   if (nsplit > max_split) nsplit = max_split;

@@ -171,6 +171,33 @@ int bcbf_socp_factor(const double* Asq, int p, int Q, double reg, double* A_socp
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (4) Ensembles of R small independent MVGPs — one per rollout, each with its own training set (N points, equal N),
+ * hyper-parameters and factor (BASELINE configs[4]).  All arrays are device pointers, rollout-major:
+ *   X (R,N,n)  UH (R,N,p)  Xdot (R,N,n)  lengthscale (R,n)  outputscale (R)  Bmat (R,p,p)  C (R,p,n)
+ *   factor-sized arrays (R,Npad,Npad) with ld = Npad;  dinv (R, bcbf_dinv_elems(Npad));  info int[R].
+ * Batched twins of (1)-(2): every rollout's Gram / Cholesky / inverse / alpha in the same launches.
+ * Per control step each rollout evaluates custom_predict at ONE state (unicycle_move_to_pose.py:880-920 ->
+ * control_affine_model.py:931-961, 983-1096); bcbf_ens_posterior does that for all rollouts in one launch, streaming
+ * each rollout's own L^-1 (lower triangle, 4 N^2 bytes) from HBM: the bandwidth-bound regime of SURVEY 8d.       */
+int bcbf_ens_gram(const double* X, const double* UH, const double* lengthscale, const double* outputscale,
+                  const double* Bmat, int R, int N, int n, int p, double* Kb, int Npad, void* stream);
+int bcbf_potrf_batched(double* A, int ld, int Npad, int N, const double* jitter /* (R,N) or NULL */,
+                       double jitter_scale, double* dinv, int* info, int R, void* stream);
+int bcbf_trtri_batched(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad, int R,
+                       void* stream);
+int bcbf_trmm_lower_batched(const double* A, int lda, int Npad, int trans, const double* B, int ldb, int ncols,
+                            double alpha, double beta, double* C, int ldc, int R, void* stream);
+/* G = UH B (R,Npad,p; pad rows 0),  Y = Xdot - UH C (R,Npad,ldy; pad 0)            (control_affine_model.py:525-532) */
+int bcbf_ens_prep(const double* UH, const double* Xdot, const double* Bmat, const double* C, int R, int N, int Npad,
+                  int n, int p, int ldy, double* G, double* Y, void* stream);
+/* W[r,i,c*p+j] = alpha[r,i,c] * G[r,i,j]   (R,Npad,n*p) */
+int bcbf_ens_w(const double* alpha, int ldy, const double* G, int R, int Npad, int n, int p, double* W, void* stream);
+/* xq (R,n): one query state per rollout -> Mk (R,n,p), Bk (R,p,p) (no output jitter).                               */
+int bcbf_ens_posterior(const double* Linv, const double* X, const double* G, const double* W,
+                       const double* lengthscale, const double* outputscale, const double* Bmat, const double* C,
+                       const double* xq, int R, int N, int Npad, int n, int p, double* Mk, double* Bk, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Model handle: owns device memory for one fitted MVGP; HOST-pointer interface (pinned or pageable).
  * This is what a non-torch caller (and bench.py's e2e leg) binds.
  */
