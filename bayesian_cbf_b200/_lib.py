@@ -71,6 +71,7 @@ _SIGNATURES = {
                                         _P]),
     'bcbf_ens_prep': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     'bcbf_ens_w': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    'bcbf_ens_transpose': (c_int, [_P, _P, c_int, c_int, _P]),
     'bcbf_ens_posterior': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     'bcbf_model_create': (c_int, [POINTER(c_void_p), c_int]),
     'bcbf_model_destroy': (None, [c_void_p]),

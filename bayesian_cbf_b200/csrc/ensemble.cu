@@ -4,8 +4,8 @@
 //   ens_gram_kernel      Kb_r = k_r(X_r, X_r) o (UH_r B_r UH_r^T), padded to Npad with the identity    (batched Gram)
 //   ens_prep_kernel      G_r = UH_r B_r,  Y_r = Xdot_r - UH_r C_r
 //   ens_w_kernel         W_r = alpha_r (.) G_r
-//   ens_posterior_kernel one CTA per rollout: k*(x_r), frakB = k* G, M_k = C^T + k*^T W,  V = L^-1 frakB streamed row by
-//                        row from HBM (lower triangle only), B_k = s B - V^T V.
+//   ens_posterior_kernel one CTA per rollout: k*(x_r), frakB = k* G, M_k = C^T + k*^T W,  V = L^-1 frakB streamed from HBM
+//                        (transposed storage, lower triangle only, coalesced), B_k = s B - V^T V.
 // The per-step posterior is HBM-bound: 4 N^2 bytes of L^-1 per rollout (its own factor, no reuse between rollouts)
 // against N^2 p flops — 160 KB vs 0.12 MFLOP at N = 200.  Factorisation / inverse / alpha reuse the batched DMMA
 // kernels of factor.cu.  Replaces, per rollout and control step, the b = 1 custom_predict calls of
@@ -110,20 +110,22 @@ __global__ void ens_w_kernel(const double* __restrict__ alpha, int ldy, const do
     for (int j = 0; j < p; ++j) W[(i * n + c) * p + j] = alpha[i * ldy + c] * G[i * p + j];
 }
 
-// One CTA (256 threads) per rollout.
+// One CTA (256 threads) per rollout, one thread per training row.  The factor inverse is stored TRANSPOSED
+// (LinvT[k][i] = L^-1[i][k]) so that at step k the threads i >= k of a warp read one contiguous segment of row k:
+// every byte of the lower triangle is fetched once, coalesced, and each thread keeps its own running V_i (p values) —
+// no per-row warp reduction.  Only the final p(p+1)/2 + n p sums are reduced across the CTA (fixed order).
 __global__ void __launch_bounds__(256)
-ens_posterior_kernel(const double* __restrict__ Linv, const double* __restrict__ X, const double* __restrict__ G,
+ens_posterior_kernel(const double* __restrict__ LinvT, const double* __restrict__ X, const double* __restrict__ G,
                      const double* __restrict__ W, const double* __restrict__ ls, const double* __restrict__ scale,
                      const double* __restrict__ Bm, const double* __restrict__ C, const double* __restrict__ xq, int N,
                      int Npad, int n, int p, double* __restrict__ Mk, double* __restrict__ Bk) {
   extern __shared__ __align__(16) double sm[];
-  double* ks = sm;                 // [Npad]  k*(x)
-  double* fb = ks + Npad;          // [Npad][p] frakB
-  __shared__ double red[8][kEN * kEP + kEP * kEP];
+  double* fb = sm;                 // [Npad][kEP] frakB rows (k* G), padded to 4 columns
+  __shared__ double red[8][kEN * kEP + kEP * (kEP + 1) / 2];
   __shared__ double xs[kEN], il[kEN];
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int np = n * p, npair = p * (p + 1) / 2;
-  Linv += (long long)r * Npad * Npad;
+  const int np = n * p;
+  LinvT += (long long)r * Npad * Npad;
   X += (long long)r * N * n;
   G += (long long)r * Npad * p;
   W += (long long)r * Npad * np;
@@ -131,13 +133,12 @@ ens_posterior_kernel(const double* __restrict__ Linv, const double* __restrict__
     il[tid] = 1.0 / ls[(long long)r * n + tid];
     xs[tid] = xq[(long long)r * n + tid];
   }
+  for (int i = tid; i < 8 * (kEN * kEP + kEP * (kEP + 1) / 2); i += 256) (&red[0][0])[i] = 0.0;
   __syncthreads();
   const double s = scale[r];
-  // ---- k*, frakB and the mean partial sums ------------------------------------------------------------------
-  double macc[kEN * kEP];
-#pragma unroll
-  for (int c = 0; c < kEN * kEP; ++c) macc[c] = 0.0;
-  for (int i = tid; i < Npad; i += 256) {
+  // ---- k*, frakB and the mean partial sums (rows strided over the CTA) --------------------------------------------
+  for (int i0 = 0; i0 < Npad; i0 += 256) {
+    const int i = i0 + tid;
     double kv = 0.0;
     if (i < N) {
       double d2 = 0.0;
@@ -147,60 +148,72 @@ ens_posterior_kernel(const double* __restrict__ Linv, const double* __restrict__
       }
       kv = s * exp(-0.5 * d2);
     }
-    ks[i] = kv;
-    for (int q = 0; q < p; ++q) fb[i * p + q] = kv * G[(long long)i * p + q];
+    if (i < Npad) {
 #pragma unroll
-    for (int c = 0; c < kEN * kEP; ++c)
-      if (c < np) macc[c] = fma(kv, W[(long long)i * np + c], macc[c]);
+      for (int q = 0; q < kEP; ++q) fb[i * kEP + q] = (q < p) ? kv * G[(long long)i * p + q] : 0.0;
+    }
+    for (int c0 = 0; c0 < np; c0 += 4) {  // mean: 4 columns of W at a time, warp tree, one smem slot per warp
+      double m4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        double t = (i < N && c0 + e < np) ? kv * W[(long long)i * np + c0 + e] : 0.0;
+        m4[e] = warp_sum(t);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c0 + e < np) red[warp][c0 + e] += m4[e];
+      }
+    }
   }
   __syncthreads();
-  // ---- V = L^-1 frakB, row by row (warp per row, coalesced), S += V_i V_i^T -----------------------------------
+  // ---- V_i = sum_{k <= i} L^-1[i][k] frakB[k],  S += V_i V_i^T ---------------------------------------------------
   double sacc[kEP * (kEP + 1) / 2];
 #pragma unroll
   for (int e = 0; e < kEP * (kEP + 1) / 2; ++e) sacc[e] = 0.0;
-  for (int i0 = warp * 4; i0 < N; i0 += 32) {  // 4 rows per warp iteration: independent loads in flight
-    double v[4][kEP];
+  for (int i0 = 0; i0 < N; i0 += 256) {
+    const int i = i0 + tid;
+    const bool live = i < N;
+    const int kmax = min(N - 1, i0 + (warp + 1) * 32 - 1);  // last row of this warp: uniform loop bound per warp
+    double v[kEP];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int q = 0; q < kEP; ++q) v[q] = 0.0;
+    const double* col = LinvT + i;
+    int k = 0;
+    for (; k + 8 <= kmax + 1; k += 8) {  // 8 independent loads in flight per thread
+      double l4[8];
 #pragma unroll
-      for (int q = 0; q < kEP; ++q) v[u][q] = 0.0;
+      for (int u = 0; u < 8; ++u) l4[u] = (live && k + u <= i) ? __ldg(col + (long long)(k + u) * Npad) : 0.0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u;
-      if (i < N) {
-        const double* row = Linv + (long long)i * Npad;
-        for (int k = lane; k <= i; k += 32) {
-          const double l = row[k];
-#pragma unroll
-          for (int q = 0; q < kEP; ++q)
-            if (q < p) v[u][q] = fma(l, fb[k * p + q], v[u][q]);
-        }
+      for (int u = 0; u < 8; ++u) {
+        const double4 f = *reinterpret_cast<const double4*>(fb + (k + u) * kEP);
+        v[0] = fma(l4[u], f.x, v[0]);
+        v[1] = fma(l4[u], f.y, v[1]);
+        v[2] = fma(l4[u], f.z, v[2]);
+        v[3] = fma(l4[u], f.w, v[3]);
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int q = 0; q < kEP; ++q)
-        if (q < p) v[u][q] = warp_sum(v[u][q]);
-      int e = 0;
-#pragma unroll
-      for (int q = 0; q < kEP; ++q)
-#pragma unroll
-        for (int t = q; t < kEP; ++t) {
-          if (t < p) sacc[e] = fma(v[u][q], v[u][t], sacc[e]);   // q < t < p; entries with q >= p stay zero
-          ++e;
-        }
+    for (; k <= kmax; ++k) {
+      const double l = (live && k <= i) ? col[(long long)k * Npad] : 0.0;
+      const double4 f = *reinterpret_cast<const double4*>(fb + k * kEP);
+      v[0] = fma(l, f.x, v[0]);
+      v[1] = fma(l, f.y, v[1]);
+      v[2] = fma(l, f.z, v[2]);
+      v[3] = fma(l, f.w, v[3]);
     }
-  }
-  // ---- block reductions (fixed order: deterministic) ------------------------------------------------------------
+    int e = 0;
 #pragma unroll
-  for (int c = 0; c < kEN * kEP; ++c) {
-    double t = (c < np) ? warp_sum(macc[c]) : 0.0;
-    if (lane == 0) red[warp][c] = t;
-  }
-  if (lane == 0) {
+    for (int q = 0; q < kEP; ++q)
 #pragma unroll
-    for (int e = 0; e < kEP * (kEP + 1) / 2; ++e) red[warp][kEN * kEP + e] = sacc[e];  // identical on every lane
+      for (int t = q; t < kEP; ++t) {
+        sacc[e] = fma(v[q], v[t], sacc[e]);  // columns >= p of frakB are zero
+        ++e;
+      }
+  }
+#pragma unroll
+  for (int e = 0; e < kEP * (kEP + 1) / 2; ++e) {
+    const double t = warp_sum(sacc[e]);
+    if (lane == 0) red[warp][kEN * kEP + e] = t;
   }
   __syncthreads();
   if (tid < np) {
@@ -211,15 +224,25 @@ ens_posterior_kernel(const double* __restrict__ Linv, const double* __restrict__
   }
   if (tid < p * p) {
     const int a = tid / p, b = tid % p, q = a < b ? a : b, t2 = a < b ? b : a;
-    // index of the (q, t2) pair in the kEP-wide upper-triangular enumeration used above
-    int e = 0;
+    int e = 0;  // index of the (q, t2) pair in the kEP-wide upper-triangular enumeration used above
     for (int qq = 0; qq < q; ++qq) e += kEP - qq;
     e += t2 - q;
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += red[w][kEN * kEP + e];
     Bk[(long long)r * p * p + tid] = s * Bm[(long long)r * p * p + tid] - t;
   }
-  (void)npair;
+}
+
+// LinvT[r][k][i] = Linv[r][i][k]  (32x32 smem tiles)
+__global__ void ens_transpose_kernel(const double* __restrict__ A, double* __restrict__ At, int Npad) {
+  __shared__ double t[32][33];
+  A += (long long)blockIdx.z * Npad * Npad;
+  At += (long long)blockIdx.z * Npad * Npad;
+  const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) t[j][threadIdx.x] = A[(long long)(y0 + j) * Npad + x];
+  __syncthreads();
+  const int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) At[(long long)(yo0 + j) * Npad + xo] = t[threadIdx.x][j];
 }
 
 }  // namespace bcbf
@@ -257,6 +280,14 @@ extern "C" int bcbf_ens_w(const double* alpha, int ldy, const double* G, int R, 
   return BCBF_OK;
 }
 
+extern "C" int bcbf_ens_transpose(const double* A, double* At, int Npad, int R, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(A && At && A != At && Npad > 0 && Npad % 32 == 0 && R >= 1, "bcbf_ens_transpose: bad arguments");
+  ens_transpose_kernel<<<dim3(Npad / 32, Npad / 32, R), dim3(32, 8), 0, stream>>>(A, At, Npad);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
 extern "C" int bcbf_ens_posterior(const double* Linv, const double* X, const double* G, const double* W,
                                   const double* lengthscale, const double* outputscale, const double* Bmat,
                                   const double* C, const double* xq, int R, int N, int Npad, int n, int p, double* Mk,
@@ -266,7 +297,7 @@ extern "C" int bcbf_ens_posterior(const double* Linv, const double* X, const dou
                "bcbf_ens_posterior: null pointer");
   BCBF_REQUIRE(R >= 1 && N >= 1 && Npad >= N && n >= 1 && n <= kEN && p >= 1 && p <= kEP,
                "bcbf_ens_posterior: R=%d N=%d Npad=%d n=%d p=%d", R, N, Npad, n, p);
-  const int smem = (int)sizeof(double) * Npad * (1 + p);
+  const int smem = (int)sizeof(double) * Npad * kEP;
   BCBF_REQUIRE(smem <= 200 * 1024, "bcbf_ens_posterior: Npad=%d too large for the per-rollout kernel", Npad);
   BCBF_CUDA(cudaFuncSetAttribute(ens_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   ens_posterior_kernel<<<R, 256, smem, stream>>>(Linv, X, G, W, lengthscale, outputscale, Bmat, C, xq, N, Npad, n, p,

@@ -65,10 +65,12 @@ class MVGPEnsemble:
             idx = torch.nonzero(pending).reshape(-1)
             r = idx.numel()
             # gather the still-failing rollouts into a dense sub-batch
+            # NB: every gathered operand is bound to a name until the launch has been issued — a temporary whose
+            # data_ptr() is taken inline is freed at once and its block may be handed to the next temporary
             Xs, UHs = self.X[idx].contiguous(), self.UH[idx].contiguous()
+            lss, ss, Bs = self.ls[idx].contiguous(), self.s[idx].contiguous(), self.B[idx].contiguous()
             Ls = torch.empty(r, Npad, Npad, **f64)
-            check(lib.bcbf_ens_gram(_ptr(Xs), _ptr(UHs), _ptr(self.ls[idx].contiguous()), _ptr(self.s[idx].contiguous()),
-                                    _ptr(self.B[idx].contiguous()), r, N, n, p, _ptr(Ls), Npad, st))
+            check(lib.bcbf_ens_gram(_ptr(Xs), _ptr(UHs), _ptr(lss), _ptr(ss), _ptr(Bs), r, N, n, p, _ptr(Ls), Npad, st))
             eps = draw(t).to(dev)[idx] * (scale[idx] / perturb_init).unsqueeze(1)   # per-rollout factor folded in
             eps = eps.contiguous()
             dsub = torch.empty(r, dinv.shape[1], **f64)
@@ -101,6 +103,8 @@ class MVGPEnsemble:
         check(lib.bcbf_trmm_lower_batched(_ptr(self.Linv), Npad, Npad, 0, _ptr(Y), ldy, ldy, 1.0, 0.0, _ptr(z), ldy, R, st))
         check(lib.bcbf_trmm_lower_batched(_ptr(self.Linv), Npad, Npad, 1, _ptr(z), ldy, ldy, 1.0, 0.0, _ptr(self.alpha),
                                           ldy, R, st))
+        self.LinvT = torch.empty_like(self.Linv)      # row k = column k of L^-1: coalesced streaming in `posterior`
+        check(lib.bcbf_ens_transpose(_ptr(self.Linv), _ptr(self.LinvT), Npad, R, st))
         self.W = torch.empty(R, Npad, n * p, **f64)
         check(lib.bcbf_ens_w(_ptr(self.alpha), ldy, _ptr(self.G), R, Npad, n, p, _ptr(self.W), st))
         return self
@@ -111,7 +115,7 @@ class MVGPEnsemble:
         f64 = dict(dtype=torch.float64, device=self.device)
         Mk, Bk = out if out is not None else (torch.empty(self.R, self.n, self.p, **f64),
                                               torch.empty(self.R, self.p, self.p, **f64))
-        check(_lib.load().bcbf_ens_posterior(_ptr(self.Linv), _ptr(self.X), _ptr(self.G), _ptr(self.W), _ptr(self.ls),
+        check(_lib.load().bcbf_ens_posterior(_ptr(self.LinvT), _ptr(self.X), _ptr(self.G), _ptr(self.W), _ptr(self.ls),
                                              _ptr(self.s), _ptr(self.B), _ptr(self.C), _ptr(xq), self.R, self.N, self.Npad,
                                              self.n, self.p, _ptr(Mk), _ptr(Bk), torch.cuda.current_stream().cuda_stream))
         return Mk, Bk

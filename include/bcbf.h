@@ -192,8 +192,11 @@ int bcbf_ens_prep(const double* UH, const double* Xdot, const double* Bmat, cons
                   int n, int p, int ldy, double* G, double* Y, void* stream);
 /* W[r,i,c*p+j] = alpha[r,i,c] * G[r,i,j]   (R,Npad,n*p) */
 int bcbf_ens_w(const double* alpha, int ldy, const double* G, int R, int Npad, int n, int p, double* W, void* stream);
-/* xq (R,n): one query state per rollout -> Mk (R,n,p), Bk (R,p,p) (no output jitter).                               */
-int bcbf_ens_posterior(const double* Linv, const double* X, const double* G, const double* W,
+/* At[r] = A[r]^T for R square (Npad,Npad) matrices (Npad multiple of 32; out of place).                          */
+int bcbf_ens_transpose(const double* A, double* At, int Npad, int R, void* stream);
+/* xq (R,n): one query state per rollout -> Mk (R,n,p), Bk (R,p,p) (no output jitter).  LinvT is the TRANSPOSED
+ * inverse factor (bcbf_ens_transpose of bcbf_trtri_batched's output): row k holds L^-1[:, k].                     */
+int bcbf_ens_posterior(const double* LinvT, const double* X, const double* G, const double* W,
                        const double* lengthscale, const double* outputscale, const double* Bmat, const double* C,
                        const double* xq, int R, int N, int Npad, int n, int p, double* Mk, double* Bk, void* stream);
 
