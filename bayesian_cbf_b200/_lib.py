@@ -44,6 +44,7 @@ _SIGNATURES = {
     'bcbf_launch_count': (ctypes.c_ulonglong, []),
     'bcbf_profile_enable': (c_int, [c_int]),
     'bcbf_profile_read': (c_int, [POINTER(c_double), POINTER(c_int)]),
+    'bcbf_debug_counters': (c_int, [c_int, POINTER(ctypes.c_ulonglong * 8)]),
     'bcbf_dinv_elems': (c_longlong, [c_int]),
     'bcbf_gram_train': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     'bcbf_cross_gram': (c_int, [_P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),

@@ -110,18 +110,21 @@ __global__ void ens_w_kernel(const double* __restrict__ alpha, int ldy, const do
     for (int j = 0; j < p; ++j) W[(i * n + c) * p + j] = alpha[i * ldy + c] * G[i * p + j];
 }
 
-// One CTA (256 threads) per rollout, one thread per training row.  The factor inverse is stored TRANSPOSED
-// (LinvT[k][i] = L^-1[i][k]) so that at step k the threads i >= k of a warp read one contiguous segment of row k:
-// every byte of the lower triangle is fetched once, coalesced, and each thread keeps its own running V_i (p values) —
-// no per-row warp reduction.  Only the final p(p+1)/2 + n p sums are reduced across the CTA (fixed order).
-__global__ void __launch_bounds__(256)
+// One CTA (128 threads) per rollout; each thread owns TWO adjacent training rows.  The factor inverse is stored
+// TRANSPOSED (LinvT[k][i] = L^-1[i][k]) so that at step k the threads of a warp read one contiguous 512-byte segment of
+// row k with 16-byte loads: every byte of the lower triangle is fetched once, coalesced, 8 independent loads in flight
+// per thread, up to 6 CTAs per SM.  Each thread keeps its own running V_i (2 x p values) — no per-row reduction; only
+// the final p(p+1)/2 + n p sums are reduced across the CTA (fixed order: deterministic).
+constexpr int kEnsThreads = 128;
+__global__ void __launch_bounds__(kEnsThreads, 6)
 ens_posterior_kernel(const double* __restrict__ LinvT, const double* __restrict__ X, const double* __restrict__ G,
                      const double* __restrict__ W, const double* __restrict__ ls, const double* __restrict__ scale,
                      const double* __restrict__ Bm, const double* __restrict__ C, const double* __restrict__ xq, int N,
                      int Npad, int n, int p, double* __restrict__ Mk, double* __restrict__ Bk) {
   extern __shared__ __align__(16) double sm[];
   double* fb = sm;                 // [Npad][kEP] frakB rows (k* G), padded to 4 columns
-  __shared__ double red[8][kEN * kEP + kEP * (kEP + 1) / 2];
+  constexpr int NW = kEnsThreads / 32;
+  __shared__ double red[NW][kEN * kEP + kEP * (kEP + 1) / 2];
   __shared__ double xs[kEN], il[kEN];
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = n * p;
@@ -133,11 +136,11 @@ ens_posterior_kernel(const double* __restrict__ LinvT, const double* __restrict_
     il[tid] = 1.0 / ls[(long long)r * n + tid];
     xs[tid] = xq[(long long)r * n + tid];
   }
-  for (int i = tid; i < 8 * (kEN * kEP + kEP * (kEP + 1) / 2); i += 256) (&red[0][0])[i] = 0.0;
+  for (int i = tid; i < NW * (kEN * kEP + kEP * (kEP + 1) / 2); i += kEnsThreads) (&red[0][0])[i] = 0.0;
   __syncthreads();
   const double s = scale[r];
   // ---- k*, frakB and the mean partial sums (rows strided over the CTA) --------------------------------------------
-  for (int i0 = 0; i0 < Npad; i0 += 256) {
+  for (int i0 = 0; i0 < Npad; i0 += kEnsThreads) {
     const int i = i0 + tid;
     double kv = 0.0;
     if (i < N) {
@@ -168,57 +171,56 @@ ens_posterior_kernel(const double* __restrict__ LinvT, const double* __restrict_
   }
   __syncthreads();
   // ---- V_i = sum_{k <= i} L^-1[i][k] frakB[k],  S += V_i V_i^T ---------------------------------------------------
-  double sacc[kEP * (kEP + 1) / 2];
+  for (int i0 = 0; i0 < N; i0 += 2 * kEnsThreads) {
+    const int i = i0 + 2 * tid;                                   // rows i, i+1
+    const bool live = i < N;                                      // (Npad is even and row N.. of L^-1 is the identity
+                                                                  //  pad against zero frakB rows: harmless)
+    const int kmax = min(N - 1, i0 + 2 * ((warp + 1) * 32) - 1);  // last row of this warp: uniform bound per warp
+    double v0[kEP], v1[kEP];
 #pragma unroll
-  for (int e = 0; e < kEP * (kEP + 1) / 2; ++e) sacc[e] = 0.0;
-  for (int i0 = 0; i0 < N; i0 += 256) {
-    const int i = i0 + tid;
-    const bool live = i < N;
-    const int kmax = min(N - 1, i0 + (warp + 1) * 32 - 1);  // last row of this warp: uniform loop bound per warp
-    double v[kEP];
-#pragma unroll
-    for (int q = 0; q < kEP; ++q) v[q] = 0.0;
+    for (int q = 0; q < kEP; ++q) v0[q] = v1[q] = 0.0;
     const double* col = LinvT + i;
     int k = 0;
-    for (; k + 8 <= kmax + 1; k += 8) {  // 8 independent loads in flight per thread
-      double l4[8];
+    for (; k + 8 <= kmax + 1; k += 8) {
+      double2 l8[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) l4[u] = (live && k + u <= i) ? __ldg(col + (long long)(k + u) * Npad) : 0.0;
+      for (int u = 0; u < 8; ++u)
+        l8[u] = (live && k + u <= i + 1) ? __ldg(reinterpret_cast<const double2*>(col + (long long)(k + u) * Npad))
+                                         : make_double2(0.0, 0.0);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const double4 f = *reinterpret_cast<const double4*>(fb + (k + u) * kEP);
-        v[0] = fma(l4[u], f.x, v[0]);
-        v[1] = fma(l4[u], f.y, v[1]);
-        v[2] = fma(l4[u], f.z, v[2]);
-        v[3] = fma(l4[u], f.w, v[3]);
+        v0[0] = fma(l8[u].x, f.x, v0[0]); v0[1] = fma(l8[u].x, f.y, v0[1]);
+        v0[2] = fma(l8[u].x, f.z, v0[2]); v0[3] = fma(l8[u].x, f.w, v0[3]);
+        v1[0] = fma(l8[u].y, f.x, v1[0]); v1[1] = fma(l8[u].y, f.y, v1[1]);
+        v1[2] = fma(l8[u].y, f.z, v1[2]); v1[3] = fma(l8[u].y, f.w, v1[3]);
       }
     }
     for (; k <= kmax; ++k) {
-      const double l = (live && k <= i) ? col[(long long)k * Npad] : 0.0;
+      const double2 l = (live && k <= i + 1) ? __ldg(reinterpret_cast<const double2*>(col + (long long)k * Npad))
+                                              : make_double2(0.0, 0.0);
       const double4 f = *reinterpret_cast<const double4*>(fb + k * kEP);
-      v[0] = fma(l, f.x, v[0]);
-      v[1] = fma(l, f.y, v[1]);
-      v[2] = fma(l, f.z, v[2]);
-      v[3] = fma(l, f.w, v[3]);
+      v0[0] = fma(l.x, f.x, v0[0]); v0[1] = fma(l.x, f.y, v0[1]);
+      v0[2] = fma(l.x, f.z, v0[2]); v0[3] = fma(l.x, f.w, v0[3]);
+      v1[0] = fma(l.y, f.x, v1[0]); v1[1] = fma(l.y, f.y, v1[1]);
+      v1[2] = fma(l.y, f.z, v1[2]); v1[3] = fma(l.y, f.w, v1[3]);
     }
     int e = 0;
 #pragma unroll
     for (int q = 0; q < kEP; ++q)
 #pragma unroll
       for (int t = q; t < kEP; ++t) {
-        sacc[e] = fma(v[q], v[t], sacc[e]);  // columns >= p of frakB are zero
+        // columns >= p of frakB are zero; rows >= N give V = 0.  Reduced per 256-row chunk so that the pair sums are
+        // not live (20 registers) across the streaming loop.
+        const double pr = warp_sum(fma(v0[q], v0[t], v1[q] * v1[t]));
+        if (lane == 0) red[warp][kEN * kEP + e] += pr;
         ++e;
       }
-  }
-#pragma unroll
-  for (int e = 0; e < kEP * (kEP + 1) / 2; ++e) {
-    const double t = warp_sum(sacc[e]);
-    if (lane == 0) red[warp][kEN * kEP + e] = t;
   }
   __syncthreads();
   if (tid < np) {
     double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red[w][tid];
+    for (int w = 0; w < NW; ++w) t += red[w][tid];
     const int c = tid / p, j = tid % p;  // Mk[c][j] = C[j][c] + ...
     Mk[(long long)r * np + tid] = C[((long long)r * p + j) * n + c] + t;
   }
@@ -228,7 +230,7 @@ ens_posterior_kernel(const double* __restrict__ LinvT, const double* __restrict_
     for (int qq = 0; qq < q; ++qq) e += kEP - qq;
     e += t2 - q;
     double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red[w][kEN * kEP + e];
+    for (int w = 0; w < NW; ++w) t += red[w][kEN * kEP + e];
     Bk[(long long)r * p * p + tid] = s * Bm[(long long)r * p * p + tid] - t;
   }
 }
@@ -300,7 +302,7 @@ extern "C" int bcbf_ens_posterior(const double* Linv, const double* X, const dou
   const int smem = (int)sizeof(double) * Npad * kEP;
   BCBF_REQUIRE(smem <= 200 * 1024, "bcbf_ens_posterior: Npad=%d too large for the per-rollout kernel", Npad);
   BCBF_CUDA(cudaFuncSetAttribute(ens_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  ens_posterior_kernel<<<R, 256, smem, stream>>>(Linv, X, G, W, lengthscale, outputscale, Bmat, C, xq, N, Npad, n, p,
+  ens_posterior_kernel<<<R, kEnsThreads, smem, stream>>>(Linv, X, G, W, lengthscale, outputscale, Bmat, C, xq, N, Npad, n, p,
                                                  Mk, Bk);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;

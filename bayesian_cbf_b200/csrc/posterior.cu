@@ -25,7 +25,9 @@ constexpr int kPBK = 32;                        // k extent of one pipeline stag
 constexpr int kPA_Stride = kPBK + 4;            // A tile row stride in doubles (== 4 mod 16: conflict-free fragments)
 constexpr int kPA_Elems = 128 * kPA_Stride;     // 4608
 constexpr int kPMmaWarps = 8;                   // consumer warps: 2 (rows) x 4 (query groups), 64 x (P*H*8) each
-constexpr int kPProdWarps = 1;                  // producer warp: streams L^-1, K* and G tiles with cp.async
+constexpr int kPProdWarps = 4;                  // producer warps, one per SM sub-partition (warp id % 4): each streams a
+                                                // quarter of the L^-1 / K* tiles with cp.async so that no sub-partition's
+                                                // DMMA warps are slowed more than the others
 constexpr int kPThreads = 32 * (kPMmaWarps + kPProdWarps);
 
 // P = columns per query; H = 8-query fragments per warp; GMUL: B operand = K*[k,t] * G[k,q] formed in registers
@@ -56,6 +58,7 @@ struct PostArgs {
   int Q;
   double* Spart;         // [nsplit][Qpad][NPair] partial Gram sums
   int Qpad; int nsplit;
+  unsigned long long* dbg;  // optional pipeline counters (bcbf_debug_counters); NULL in production
 };
 
 // ---- mbarrier helpers (CTA-scope producer/consumer pipeline; no __syncthreads in the steady state) ------------------
@@ -98,10 +101,11 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
   const int split = blockIdx.y, nsplit = a.nsplit;
   constexpr int kStagesPerBlk = kBlk / kPBK;  // 4
 
+  const long long tk0 = a.dbg ? clock64() : 0;
   for (int i = tid; i < 2 * TQ * NPair; i += kPThreads) Ssm[i] = 0.0;
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full + s, 32);
+      mbar_init(full + s, 32 * kPProdWarps);
       mbar_init(empty + s, kPMmaWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -113,12 +117,13 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
   auto stK = [&](int s) { return smem + s * Cfg::StageElems + kPA_Elems; };
   auto stG = [&](int s) { return smem + s * Cfg::StageElems + kPA_Elems + Cfg::KElems; };
 
-  if (warp == kPMmaWarps) {
-    // ================= producer: L^-1[I rows, k..k+32) -> As[128][36]; K*[k..k+32, q0..q0+TQ) -> Ks[32][TQ+4];
+  if (warp >= kPMmaWarps) {
+    // ================= producers: L^-1[I rows, k..k+32) -> As[128][36]; K*[k..k+32, q0..q0+TQ) -> Ks[32][TQ+4];
     //                   G[k..k+32, :] -> Gs (packed).  16-byte cp.async (LDGSTS) only; completion of a lane's copies
     //                   arrives on full[s] (cp.async.mbarrier.arrive).  Measured alternative: one 256-byte
     //                   cp.async.bulk (TMA unit, UBLKCP) per tile row — 161 small bulk copies per stage made the producer
     //                   the bottleneck (25.6 vs 32.3 TFLOP/s), so the LDGSTS path is kept. ======
+    const int pw = warp - kPMmaWarps;
     int slot = 0;
     unsigned phase = 0;
     const double* gK0 = a.Kstar + q0;
@@ -126,32 +131,42 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
       const double* gI = a.Linv + (long long)I * kBlk * a.ld;
       const int nst = (I + 1) * kStagesPerBlk;
       for (int kt = 0; kt < nst; ++kt) {
+        long long tp0 = 0;
+        if (a.dbg) tp0 = clock64();
         mbar_wait(empty + slot, phase ^ 1u);
+        if (a.dbg && lane == 0 && pw == 0) {
+          atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - tp0));  // cycles the producer waited on empty
+          atomicAdd(a.dbg + 4, 1ull);
+          tp0 = clock64();
+        }
         {
-          double* s = stA(slot);
-          const double* g = gI + kt * kPBK + (long long)(lane >> 4) * a.ld + (lane & 15) * 2;
+          // this warp's quarter of the A tile: rows [pw*32, pw*32+32) x 16 chunks of 16 B; lane -> (row = it*2 + lane/16)
+          double* s = stA(slot) + (pw * (kBlk / kPProdWarps)) * kPA_Stride;
+          const double* g = gI + kt * kPBK + (long long)(pw * (kBlk / kPProdWarps) + (lane >> 4)) * a.ld + (lane & 15) * 2;
           double* sd = s + (lane >> 4) * kPA_Stride + (lane & 15) * 2;
-          // 128 rows x 16 chunks of 16 B: lane -> (row = it*2 + lane/16, chunk = lane%16)
 #pragma unroll 8
-          for (int it = 0; it < 64; ++it)
+          for (int it = 0; it < kBlk / kPProdWarps / 2; ++it)
             cp_async16(sd + it * 2 * kPA_Stride, g + (long long)it * 2 * a.ld, true);
         }
         {
-          double* s = stK(slot);
-          const double* g = gK0 + (long long)kt * kPBK * a.ldks;
-          constexpr int CPR = TQ / 2;  // 16-byte chunks per k row
+          // this warp's quarter of the K* tile: k rows [pw*8, pw*8+8)
+          constexpr int KR = kPBK / kPProdWarps;  // 8
+          constexpr int CPR = TQ / 2;             // 16-byte chunks per k row
+          double* s = stK(slot) + pw * KR * KS;
+          const double* g = gK0 + (long long)(kt * kPBK + pw * KR) * a.ldks;
 #pragma unroll 4
-          for (int it = 0; it < kPBK * CPR / 32; ++it) {
+          for (int it = 0; it < KR * CPR / 32; ++it) {
             const int ch = it * 32 + lane, k = ch / CPR, c2 = (ch % CPR) * 2;
             cp_async16(s + k * KS + c2, g + (long long)k * a.ldks + c2, true);
           }
         }
-        if (Cfg::GMUL) {
+        if (Cfg::GMUL && pw == kPProdWarps - 1) {
           double* s = stG(slot);
           const double* g = a.G + (long long)kt * kPBK * P;
           for (int ch = lane; ch < kPBK * P / 2; ch += 32) cp_async16(s + ch * 2, g + ch * 2, true);
         }
         mbar_arrive_cp_async(full + slot);
+        if (a.dbg && lane == 0 && pw == 0) atomicAdd(a.dbg + 5, (unsigned long long)(clock64() - tp0));  // cycles to issue a stage
         if (++slot == S) { slot = 0; phase ^= 1u; }
       }
     }
@@ -171,7 +186,18 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
     for (int I = split; I < nb; I += nsplit) {
       const int nst = (I + 1) * kStagesPerBlk;
       for (int kt = 0; kt < nst; ++kt) {
-        mbar_wait(full + slot, phase);
+        if (a.dbg) {
+          const long long t0 = clock64();
+          mbar_wait(full + slot, phase);
+          const long long dt = clock64() - t0;
+          if (lane == 0) {
+            atomicAdd(a.dbg + 0, (unsigned long long)dt);             // cycles consumer warps spent waiting on full
+            atomicAdd(a.dbg + 1, 1ull);                               // consumer stage count
+            if (dt > 300) atomicAdd(a.dbg + 2, 1ull);                 // stages that actually blocked
+          }
+        } else {
+          mbar_wait(full + slot, phase);
+        }
         const double* As = stA(slot) + (wm * 64 + lr) * kPA_Stride + lk;
         const double* Ks = stK(slot) + lk * KS + wn * QW + lr;
         const double* Gs = stG(slot) + lk * P;
@@ -240,6 +266,10 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
     }
   }
   __syncthreads();
+  if (a.dbg && tid == 0) {
+    atomicAdd(a.dbg + 6, (unsigned long long)(clock64() - tk0));  // CTA lifetime cycles
+    atomicAdd(a.dbg + 7, 1ull);
+  }
   for (int i = tid; i < TQ * NPair; i += kPThreads) {
     int t = i / NPair, e = i % NPair;
     double v = Ssm[(0 * TQ + t) * NPair + e] + Ssm[(1 * TQ + t) * NPair + e];
@@ -393,8 +423,11 @@ struct KernelProfile {
 };
 static KernelProfile g_prof;
 
+static unsigned long long* g_dbg = nullptr;  // 8 counters, enabled by bcbf_debug_counters(1, ...)
+
 template <class Cfg>
 static int launch_post_var(PostArgs a, cudaStream_t stream) {
+  a.dbg = g_dbg;
   BCBF_CUDA(cudaFuncSetAttribute(post_var_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SmemBytes));
   dim3 grid(a.Qpad / Cfg::TQ, a.nsplit);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -561,5 +594,25 @@ extern "C" int bcbf_profile_read(double* total_ms, int* launches) {
   }
   if (total_ms) *total_ms = tot;
   if (launches) *launches = (int)g_prof.spans.size();
+  return BCBF_OK;
+}
+
+// Pipeline counters of post_var_kernel (development aid; adds clock64/atomics to the kernel while enabled):
+//   [0] cycles consumer warps waited on `full`  [1] consumer (warp, stage) count  [2] waits > 300 cycles
+//   [3] cycles the producer waited on `empty`   [4] producer stage count          [5] cycles spent issuing copies
+//   [6] CTA lifetime cycles (sum)               [7] CTA count
+extern "C" int bcbf_debug_counters(int enable, unsigned long long out[8]) {
+  if (out != nullptr && g_dbg != nullptr) {
+    BCBF_CUDA(cudaDeviceSynchronize());
+    BCBF_CUDA(cudaMemcpy(out, g_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  if (enable && g_dbg == nullptr) {
+    BCBF_CUDA(cudaMalloc(&g_dbg, 8 * sizeof(unsigned long long)));
+  }
+  if (g_dbg != nullptr) BCBF_CUDA(cudaMemset(g_dbg, 0, 8 * sizeof(unsigned long long)));
+  if (!enable && g_dbg != nullptr) {
+    BCBF_CUDA(cudaFree(g_dbg));
+    g_dbg = nullptr;
+  }
   return BCBF_OK;
 }

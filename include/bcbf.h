@@ -43,6 +43,8 @@ unsigned long long bcbf_launch_count(void);
  * read synchronises and returns the summed device time and the number of launches since enable.            */
 int bcbf_profile_enable(int on);
 int bcbf_profile_read(double* total_ms, int* launches);
+/* Development aid: pipeline counters of post_var_kernel (producer / consumer barrier wait cycles); see posterior.cu. */
+int bcbf_debug_counters(int enable, unsigned long long out[8]);
 /* N rounded up to the block size the kernels tile by. */
 int bcbf_padded(int N);
 /* Bytes of scratch bcbf_potrf/bcbf_trtri need for a factor of padded size Npad. */
