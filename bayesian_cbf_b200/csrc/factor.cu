@@ -12,7 +12,10 @@ namespace bcbf {
 
 constexpr int kPad = kBlk + 1;  // 129: conflict-free row and column walks of the 128x128 smem block
 
-constexpr int kSB = 32;  // sub-panel width of the in-CTA factorisation
+constexpr int kSB = 16;  // sub-panel width of the in-CTA factorisation (16: the unrolled register code stays ~2k SASS
+                         // instructions and lives in the instruction cache; at 32 it was 30k and thrashed it)
+constexpr int kSBT = kSB / 4;             // 4x4 register tiles per sub-block edge
+constexpr int kTElems = (kBlk / kSB - 1) * kSB * (kSB + 1);  // scratch: up to 112 x 17 doubles
 
 // X(r,c) of the inverse under construction: strictly-lower entries live transposed in the upper triangle of `a`,
 // the diagonal in xd.
@@ -34,7 +37,7 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
   extern __shared__ __align__(16) double sm[];
   double* a = sm;                 // [128][129]
   double* xd = sm + kBlk * kPad;  // [128] diagonal of the inverse
-  double* T = xd + kBlk;          // [3][32][33] scratch for the off-diagonal inverse blocks
+  double* T = xd + kBlk;          // [kTElems] scratch: panel solve / off-diagonal inverse blocks, row stride kSB+1
   __shared__ int failed;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* A = A_ + (long long)blockIdx.x * sA;
@@ -42,25 +45,31 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
   const double* jitter = jitter_ ? jitter_ + (long long)blockIdx.x * sJ : nullptr;
   int* info = info_ + blockIdx.x;
   if (tid == 0) failed = 0;
-  for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
-    int r = idx >> 7, c = idx & 127;
-    double v = 0.0;
-    if (c <= r) {
-      v = A[(long long)(k0 + r) * ld + (k0 + c)];
-      if (c == r && jitter != nullptr && (k0 + r) < N) v += jscale * jitter[k0 + r];
-    }
-    a[r * kPad + c] = v;
+  // load the block: branch-free 16-byte loads, 8 in flight per thread; the upper triangle is masked to zero
+#pragma unroll 8
+  for (int it = 0; it < kBlk * kBlk / 2 / 256; ++it) {
+    const int idx2 = it * 256 + tid, r = idx2 >> 6, c = (idx2 & 63) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(A + (long long)(k0 + r) * ld + (k0 + c));
+    a[r * kPad + c] = (c <= r) ? v.x : 0.0;
+    a[r * kPad + c + 1] = (c + 1 <= r) ? v.y : 0.0;
   }
+  __syncthreads();
+  if (tid < kBlk && jitter != nullptr && (k0 + tid) < N) a[tid * kPad + tid] += jscale * jitter[k0 + tid];
   __syncthreads();
 
   // ======================= Phase A: L L^T = block =======================================================
   for (int pnl = 0; pnl < kBlk / kSB; ++pnl) {
     const int c0 = pnl * kSB;
-    if (warp == 0) {  // A1
+    if (warp == 0) {
+      // ---- A1: factor the 16x16 diagonal sub-block in REGISTERS (lane = row, lanes >= 16 idle): pivots and multipliers
+      //      travel by warp shuffle, no shared-memory round trip and no barrier on the dependent chain; one rsqrt per
+      //      pivot, no divisions.  Fully unrolled so that every register index is a compile-time constant.
       double r[kSB];
+      const int rl = lane & (kSB - 1);
 #pragma unroll
-      for (int k = 0; k < kSB; ++k) r[k] = (k <= lane) ? a[(c0 + lane) * kPad + c0 + k] : 0.0;
+      for (int k = 0; k < kSB; ++k) r[k] = (k <= rl) ? a[(c0 + rl) * kPad + c0 + k] : 0.0;
       int bad = 0;
+      double myinv = 0.0;  // 1 / L[lane][lane]
 #pragma unroll
       for (int j = 0; j < kSB; ++j) {
         double djj = __shfl_sync(0xffffffffu, r[j], j);
@@ -68,41 +77,87 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
           if (bad == 0) bad = c0 + j + 1;
           djj = __longlong_as_double(0x7ff8000000000000LL);
         }
-        const double dj = sqrt(djj);
-        if (lane == j) r[j] = dj;
-        else if (lane > j) r[j] = r[j] / dj;
+        const double inv = rsqrt(djj);
+        if (rl == j) { r[j] = djj * inv; myinv = inv; }   // sqrt(djj) to within an ulp
+        else if (rl > j) r[j] = r[j] * inv;
 #pragma unroll
         for (int k = 0; k < kSB; ++k) {
-          if (k > j) {  // compile-time after unrolling: constant register indices, no local memory
+          if (k > j) {  // compile-time after unrolling
             const double lkj = __shfl_sync(0xffffffffu, r[j], k);
-            if (lane >= k) r[k] = fma(-r[j], lkj, r[k]);
+            if (rl >= k) r[k] = fma(-r[j], lkj, r[k]);
           }
         }
       }
+      if (lane < kSB) {
 #pragma unroll
-      for (int k = 0; k < kSB; ++k)
-        if (k <= lane) a[(c0 + lane) * kPad + c0 + k] = r[k];
+        for (int k = 0; k < kSB; ++k)
+          if (k <= lane) a[(c0 + lane) * kPad + c0 + k] = r[k];
+      }
       if (lane == 0 && bad != 0) {
         atomicCAS(info, 0, k0 + bad);
         failed = 1;
+      }
+      // ---- A1b: invert it right away (lane = column j of X = L_D^-1), still in registers.  X is needed by the panel
+      //      solve below AND is the diagonal block of the final inverse.
+      double x[kSB];
+#pragma unroll
+      for (int i = 0; i < kSB; ++i) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < kSB; ++k) {
+          if (k < i) {
+            const double lik = __shfl_sync(0xffffffffu, r[k], i);   // L[i][k]
+            if (k >= rl) sacc = fma(lik, x[k], sacc);
+          }
+        }
+        const double dii = __shfl_sync(0xffffffffu, myinv, i);
+        x[i] = (i == rl) ? dii : (i > rl ? -sacc * dii : 0.0);
+      }
+      if (lane < kSB) {
+#pragma unroll
+        for (int i = 0; i < kSB; ++i) {
+          if (i == lane) xd[c0 + lane] = x[i];
+          else if (i > lane) a[(c0 + lane) * kPad + c0 + i] = x[i];   // X[i][j] (i > j) kept at a[j][i]
+        }
       }
     }
     __syncthreads();
     if (failed) break;
     const int r0 = c0 + kSB, Tn = kBlk - r0;  // trailing extent
-    if (tid < Tn) {  // A2: row i of the panel  x L_D^T = a[i, c0:c0+32]
-      const int i = r0 + tid;
-      double x[kSB];
+    {  // A2: panel <- panel * X^T  (P[i][j] = sum_{k <= j} A[i][c0+k] X[j][k]), 4 rows x 4 columns per thread
+      const int ntask = (Tn / 4) * kSBT;
+      for (int t = tid; t < ntask; t += 256) {
+        const int ti = t / kSBT, tj = t % kSBT;
+        double acc[4][4];
 #pragma unroll
-      for (int j = 0; j < kSB; ++j) {
-        double sacc = a[i * kPad + c0 + j];
+        for (int e = 0; e < 4; ++e)
 #pragma unroll
-        for (int k = 0; k < kSB; ++k)
-          if (k < j) sacc = fma(-x[k], a[(c0 + j) * kPad + c0 + k], sacc);
-        x[j] = sacc / a[(c0 + j) * kPad + c0 + j];
+          for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+        const int jmax = 4 * tj + 3;
+        for (int k = 0; k <= jmax; ++k) {
+          double va[4], vx[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            va[e] = a[(r0 + 4 * ti + e) * kPad + c0 + k];
+            vx[e] = inv_get(a, xd, c0 + 4 * tj + e, c0 + k);   // X[j][k], zero for k > j
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vx[f], acc[e][f]);
+        }
+        // every task reads A[i][c0 .. c0+jmax] of its own 4 rows only, but other tasks (other tj) read the same rows:
+        // stage the results and write after the barrier
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) T[(4 * ti + e) * (kSB + 1) + 4 * tj + f] = acc[e][f];
       }
-#pragma unroll
-      for (int j = 0; j < kSB; ++j) a[i * kPad + c0 + j] = x[j];
+      __syncthreads();
+      for (int t = tid; t < Tn * kSB; t += 256) {
+        const int i = t / kSB, j = t % kSB;
+        a[(r0 + i) * kPad + c0 + j] = T[i * (kSB + 1) + j];
+      }
     }
     __syncthreads();
     {  // A3: trailing (lower) -= P P^T with 4x4 register tiles
@@ -155,32 +210,12 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
     return;
   }
 
-  // ======================= Phase B: X = L^{-1} ==========================================================
-  if (warp < kBlk / kSB) {  // B1: diagonal 32x32 blocks, lane = column j
-    const int b0 = warp * kSB, j = lane;
-    double x[kSB];
-#pragma unroll
-    for (int i = 0; i < kSB; ++i) {
-      double sacc = 0.0;
-#pragma unroll
-      for (int k = 0; k < kSB; ++k)
-        if (k < i && k >= j) sacc = fma(a[(b0 + i) * kPad + b0 + k], x[k], sacc);
-      const double dii = 1.0 / a[(b0 + i) * kPad + b0 + i];
-      x[i] = (i == j) ? dii : (i > j ? -sacc * dii : 0.0);
-    }
-    __syncwarp();  // every lane has finished reading the block's L entries (they are untouched anyway: upper side)
-#pragma unroll
-    for (int i = 0; i < kSB; ++i) {
-      if (i == j) xd[b0 + j] = x[i];
-      else if (i > j) a[(b0 + j) * kPad + b0 + i] = x[i];
-    }
-  }
-  __syncthreads();
+  // ======================= Phase B: X = L^{-1}: the diagonal 32x32 blocks are already there (A1b) ===========
   for (int d = 1; d < kBlk / kSB; ++d) {  // B2: block (bi, bj) with bi - bj = d
     const int nblk = kBlk / kSB - d;
     // T_b = sum_{kb = bj}^{bi-1} L[bi, kb] X[kb, bj]      (32 x 32 each), 4x4 register tiles
-    for (int t = tid; t < nblk * 64; t += 256) {
-      const int b = t >> 6, tt = t & 63, ti = tt >> 3, tj = tt & 7;
+    for (int t = tid; t < nblk * kSBT * kSBT; t += 256) {
+      const int b = t / (kSBT * kSBT), tt = t % (kSBT * kSBT), ti = tt / kSBT, tj = tt % kSBT;
       const int bj = b, bi = b + d;
       double acc[4][4];
 #pragma unroll
@@ -206,8 +241,8 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
     }
     __syncthreads();
     // X[bi, bj] = -X[bi, bi] T_b
-    for (int t = tid; t < nblk * 64; t += 256) {
-      const int b = t >> 6, tt = t & 63, ti = tt >> 3, tj = tt & 7;
+    for (int t = tid; t < nblk * kSBT * kSBT; t += 256) {
+      const int b = t / (kSBT * kSBT), tt = t % (kSBT * kSBT), ti = tt / kSBT, tj = tt % kSBT;
       const int bj = b, bi = b + d;
       double acc[4][4];
 #pragma unroll
@@ -276,6 +311,35 @@ using namespace bcbf;
 
 extern "C" long long bcbf_dinv_elems(int Npad) { return (long long)(Npad / kBlk) * kBlk * kBlk; }
 
+// Look-ahead of the single-matrix factorisation: the serial sweep (single-CTA diagonal factorisations, panel solves) and
+// the update of the next block column run on an internal HIGH-priority stream; the bulk trailing update stays on the
+// caller's stream underneath it.  Stream priorities matter: both kernels want a whole SM's shared memory, and only a
+// higher-priority stream gets the SM that a retiring GEMM CTA frees.  One set per device, created on demand.
+struct LookAhead {
+  cudaStream_t side = nullptr;   // high priority: critical path
+  cudaEvent_t panels_done = nullptr, t2_done = nullptr, start = nullptr;
+};
+static LookAhead g_look[64];
+
+static LookAhead* get_lookahead() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  LookAhead& l = g_look[dev & 63];
+  if (l.side == nullptr) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically least = greatest priority
+    if (cudaStreamCreateWithPriority(&l.side, cudaStreamNonBlocking, hi) != cudaSuccess) { l.side = nullptr; return nullptr; }
+    if (cudaEventCreateWithFlags(&l.panels_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.start, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.t2_done, cudaEventDisableTiming) != cudaSuccess) {
+      cudaStreamDestroy(l.side);
+      l.side = nullptr;
+      return nullptr;
+    }
+  }
+  return &l;
+}
+
 // R independent factorisations of equal size (R = 1: the single-matrix entry point).  Strides in elements:
 // sA between matrices, sD between dinv blocks sets, sJ between jitter vectors; info is int[R].
 static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale, double* dinv,
@@ -285,19 +349,29 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
                "bcbf_potrf: Npad=%d must be a positive multiple of %d, ld=%d >= Npad and even, N=%d <= Npad", Npad,
                kBlk, ld, N);
   const int nb = Npad / kBlk;
-  const int smem = (kBlk * kPad + kBlk + 3 * kSB * (kSB + 1)) * (int)sizeof(double);
+  const int smem = (kBlk * kPad + kBlk + kTElems) * (int)sizeof(double);
   BCBF_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  BCBF_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * (size_t)R, stream));
+  BCBF_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * (size_t)R, stream));  // before the look-ahead fork below
   // Two-level blocking: outer block columns of kOuter = 512; inside one, a right-looking sweep over 128-wide panels
   // whose updates stay within the block column (K = 128, small); the bulk of the N^3/3 flops runs in ONE trailing
   // SYRK per outer block with K = 512, where the DMMA GEMM's pipeline fill is amortised over 32 k-steps.
   constexpr int kOuter = 4;  // in units of 128-blocks
+  // look-ahead only pays (and is only wired) for one large matrix; ensembles are already parallel over R
+  LookAhead* look = (R == 1 && nb > 2 * kOuter) ? get_lookahead() : nullptr;
+  cudaStream_t cs = stream;   // critical-path stream: sweep + next-block-column update
+  if (look) {
+    // order the critical stream after everything already queued on the caller's stream, and reset t2_done
+    BCBF_CUDA(cudaEventRecord(look->start, stream));
+    BCBF_CUDA(cudaStreamWaitEvent(look->side, look->start, 0));
+    BCBF_CUDA(cudaEventRecord(look->t2_done, stream));
+    cs = look->side;
+  }
   for (int J = 0; J < nb; J += kOuter) {
     const int jend = (J + kOuter < nb) ? J + kOuter : nb;  // exclusive, in blocks
     for (int k = J; k < jend; ++k) {
       const int k0 = k * kBlk;
       double* dk = dinv + (long long)k * kBlk * kBlk;
-      potf2_inv_kernel<<<R, 256, smem, stream>>>(A, ld, k0, jitter, N, jitter_scale, dk, info, sA, sD, sJ);
+      potf2_inv_kernel<<<R, 256, smem, cs>>>(A, ld, k0, jitter, N, jitter_scale, dk, info, sA, sD, sJ);
       BCBF_LAUNCH_CHECK();
       const int rows = Npad - (k0 + kBlk);
       if (rows <= 0) break;
@@ -307,7 +381,7 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
       g.A = panel; g.lda = ld; g.B = dk; g.ldb = kBlk; g.C = panel; g.ldc = ld;
       g.M = rows; g.N = kBlk; g.K = kBlk; g.alpha = 1.0; g.beta = 0.0; g.tri = kTriNone;
       g.sA = sA; g.sB = sD; g.sC = sA;
-      BCBF_CUDA((launch_gemm<true, true>(g, R, stream)));
+      BCBF_CUDA((launch_gemm<true, true>(g, R, cs)));
       // inside the outer block column: columns (k+1)*128 .. jend*128, all rows below  -= panel panel^T
       const int w = (jend - (k + 1)) * kBlk;
       if (w > 0) {
@@ -316,20 +390,48 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
         u.C = A + (long long)(k0 + kBlk) * (ld + 1); u.ldc = ld;
         u.M = rows; u.N = w; u.K = kBlk; u.alpha = -1.0; u.beta = 1.0; u.tri = kTriNone;
         u.sA = u.sB = u.sC = sA;
-        BCBF_CUDA((launch_gemm<true, true>(u, R, stream)));
+        BCBF_CUDA((launch_gemm<true, true>(u, R, cs)));
       }
     }
     const int c1 = jend * kBlk, rows = Npad - c1;
     if (rows > 0) {
       // trailing (lower tiles) -= P P^T,  P = A[c1:, J*128 : c1]   (K up to 512)
       const double* P = A + (long long)c1 * ld + (long long)J * kBlk;
-      GemmArgs t{};
-      t.A = P; t.lda = ld; t.B = P; t.ldb = ld;
-      t.C = A + (long long)c1 * (ld + 1); t.ldc = ld;
-      t.M = rows; t.N = rows; t.K = c1 - J * kBlk; t.alpha = -1.0; t.beta = 1.0; t.tri = kTriLowerOut;
-      t.sA = t.sB = t.sC = sA;
-      BCBF_CUDA((launch_gemm<true, true>(t, R, stream)));
+      const int Kp = c1 - J * kBlk;
+      const int strip = rows < kOuter * kBlk ? rows : kOuter * kBlk;   // columns the NEXT outer block will factor
+      if (look && rows > strip) {
+        // look-ahead: (t1) update only the next block column on the caller's stream, so that its serial sweep
+        // (single-CTA diagonal factorisations) can start at once, and (t2) update the rest on a low-priority side
+        // stream underneath it.  t1 of the next outer block waits for t2 (same region).
+        BCBF_CUDA(cudaStreamWaitEvent(cs, look->t2_done, 0));   // previous t2 (no-op the first time)
+        GemmArgs t1{};
+        t1.A = P; t1.lda = ld; t1.B = P; t1.ldb = ld;
+        t1.C = A + (long long)c1 * (ld + 1); t1.ldc = ld;
+        t1.M = rows; t1.N = strip; t1.K = Kp; t1.alpha = -1.0; t1.beta = 1.0; t1.tri = kTriNone;
+        BCBF_CUDA((launch_gemm<true, true>(t1, 1, cs)));
+        BCBF_CUDA(cudaEventRecord(look->panels_done, cs));
+        BCBF_CUDA(cudaStreamWaitEvent(stream, look->panels_done, 0));
+        const double* P2 = P + (long long)strip * ld;
+        GemmArgs t2{};
+        t2.A = P2; t2.lda = ld; t2.B = P2; t2.ldb = ld;
+        t2.C = A + (long long)(c1 + strip) * (ld + 1); t2.ldc = ld;
+        t2.M = rows - strip; t2.N = rows - strip; t2.K = Kp; t2.alpha = -1.0; t2.beta = 1.0; t2.tri = kTriLowerOut;
+        BCBF_CUDA((launch_gemm<true, true>(t2, 1, stream)));
+        BCBF_CUDA(cudaEventRecord(look->t2_done, stream));
+      } else {
+        if (look) BCBF_CUDA(cudaStreamWaitEvent(cs, look->t2_done, 0));
+        GemmArgs t{};
+        t.A = P; t.lda = ld; t.B = P; t.ldb = ld;
+        t.C = A + (long long)c1 * (ld + 1); t.ldc = ld;
+        t.M = rows; t.N = rows; t.K = Kp; t.alpha = -1.0; t.beta = 1.0; t.tri = kTriLowerOut;
+        t.sA = t.sB = t.sC = sA;
+        BCBF_CUDA((launch_gemm<true, true>(t, R, cs)));
+      }
     }
+  }
+  if (look) {  // rejoin: everything the critical stream did becomes visible to the caller's stream
+    BCBF_CUDA(cudaEventRecord(look->panels_done, cs));
+    BCBF_CUDA(cudaStreamWaitEvent(stream, look->panels_done, 0));
   }
   if (nb > 1) {
     zero_upper_blocks_kernel<<<dim3(nb * (nb - 1) / 2, R), 256, 0, stream>>>(A, ld, nb, sA);

@@ -74,7 +74,7 @@ def test_cross_gram_and_rbf_blocks():
             assert (d2K[i, j].cpu() - H).abs().max() < 1e-13
 
 
-@pytest.mark.parametrize('N', [100, 128, 300, 640, 1100])
+@pytest.mark.parametrize('N', [100, 128, 300, 640, 1100, 2100])
 def test_potrf_trtri(N):
     from bayesian_cbf_b200 import ops
     X, U, _, hyp, jit, _, _ = _mk(3, N, 3, 2, 4, box=3.0)
