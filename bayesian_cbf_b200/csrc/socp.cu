@@ -1,0 +1,242 @@
+// Batched tiny second-order-cone programs: the per-control-step safety program of the Bayesian CLF/CBF controller
+// (reference ControllerCLFBayesian.control, unicycle_move_to_pose.py:926-964, solved there with cvxpy + GUROBI on the host;
+// SURVEY 8f-1).  One thread per problem:
+//
+//     minimise   sum_i w_i (y_i - r_i)^2                      y in R^nv           (nv <= 4: [relaxation, u])
+//     subject to c_k^T y + d_k >= rho || A_k y + b_k ||_2      k = 0 .. K-1        (K <= 4 cones of dimension pc <= 4)
+//
+// Method: log-barrier interior point (barrier -log(t^2 - |z|^2) per cone), damped Newton with backtracking, preceded by
+// a phase-I problem in (y, s) that either finds a strictly feasible point or proves infeasibility — the "feasibility
+// decision" that ends a rollout in the reference (`raise ValueError(problem.status)`, :954-964).  All arithmetic in
+// float64, no data-dependent randomness: the CPU restatement in oracle/socp_oracle.py follows it step for step.
+#include "../../include/bcbf.h"
+#include "common.cuh"
+
+namespace bcbf {
+
+constexpr int kSV = 4, kSK = 4, kSP = 4;  // maxima: variables, cones, cone dimension
+constexpr int kSN = kSV + 1;              // phase I adds the slack s
+
+struct SocpProblem {
+  int nv, K, pc;
+  double rho;
+  double w[kSV], r[kSV];
+  double c[kSK][kSV], d[kSK];
+  double A[kSK][kSP][kSV], b[kSK][kSP];
+};
+
+// cone values at y (+ slack s added to every t): returns false if some cone is not strictly inside
+__device__ __forceinline__ bool socp_cones(const SocpProblem& P, const double* y, double s, double* t, double z[][kSP],
+                                           double* D) {
+  bool ok = true;
+  for (int k = 0; k < P.K; ++k) {
+    double tk = P.d[k] + s;
+    for (int i = 0; i < P.nv; ++i) tk = fma(P.c[k][i], y[i], tk);
+    double zz = 0.0;
+    for (int q = 0; q < P.pc; ++q) {
+      double v = P.b[k][q];
+      for (int i = 0; i < P.nv; ++i) v = fma(P.A[k][q][i], y[i], v);
+      v *= P.rho;
+      z[k][q] = v;
+      zz = fma(v, v, zz);
+    }
+    t[k] = tk;
+    D[k] = tk * tk - zz;
+    ok = ok && (tk > 0.0) && (D[k] > 0.0);
+  }
+  return ok;
+}
+
+// in-place Cholesky solve of the n x n SPD system H x = g (n <= kSN); returns false on a non-positive pivot
+__device__ __forceinline__ bool socp_solve(double H[][kSN], double* g, int n) {
+  for (int j = 0; j < n; ++j) {
+    double dj = H[j][j];
+    for (int k = 0; k < j; ++k) dj -= H[j][k] * H[j][k];
+    if (!(dj > 0.0)) return false;
+    dj = sqrt(dj);
+    H[j][j] = dj;
+    for (int i = j + 1; i < n; ++i) {
+      double v = H[i][j];
+      for (int k = 0; k < j; ++k) v -= H[i][k] * H[j][k];
+      H[i][j] = v / dj;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double v = g[i];
+    for (int k = 0; k < i; ++k) v -= H[i][k] * g[k];
+    g[i] = v / H[i][i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double v = g[i];
+    for (int k = i + 1; k < n; ++k) v -= H[k][i] * g[k];
+    g[i] = v / H[i][i];
+  }
+  return true;
+}
+
+// Barrier value, gradient and Hessian of  tau * f(x) - sum_k log D_k  in the variables x = (y [, s]).
+//   phase 1: f = s + eps1 * sum w (y-r)^2 ;  phase 2: f = sum w (y-r)^2
+__device__ __forceinline__ double socp_merit(const SocpProblem& P, const double* x, bool phase1, double tau, double eps1) {
+  double t[kSK], z[kSK][kSP], D[kSK];
+  if (!socp_cones(P, x, phase1 ? x[P.nv] : 0.0, t, z, D)) return __longlong_as_double(0x7ff0000000000000LL);
+  double f = 0.0;
+  for (int i = 0; i < P.nv; ++i) f = fma(P.w[i] * (x[i] - P.r[i]), (x[i] - P.r[i]), f);
+  double val = phase1 ? tau * (x[P.nv] + eps1 * f) : tau * f;
+  for (int k = 0; k < P.K; ++k) val -= log(D[k]);
+  return val;
+}
+
+__device__ __forceinline__ void socp_grad_hess(const SocpProblem& P, const double* x, bool phase1, double tau,
+                                               double eps1, double* g, double H[][kSN]) {
+  const int nv = P.nv, n = nv + (phase1 ? 1 : 0);
+  double t[kSK], z[kSK][kSP], D[kSK];
+  socp_cones(P, x, phase1 ? x[nv] : 0.0, t, z, D);
+  for (int i = 0; i < n; ++i) {
+    g[i] = 0.0;
+    for (int j = 0; j < n; ++j) H[i][j] = 0.0;
+  }
+  const double fs = phase1 ? tau * eps1 : tau;
+  for (int i = 0; i < nv; ++i) {
+    g[i] = 2.0 * fs * P.w[i] * (x[i] - P.r[i]);
+    H[i][i] = 2.0 * fs * P.w[i];
+  }
+  if (phase1) g[nv] = tau;
+  for (int k = 0; k < P.K; ++k) {
+    // u = (t, z),  q = t * dt/dx - sum_q z_q dz_q/dx ;  grad -= 2 q / D ;  Hess += 4 q q^T / D^2 - 2 (dt dt^T - dz^T dz) / D
+    double dt[kSN], q[kSN];
+    for (int i = 0; i < nv; ++i) dt[i] = P.c[k][i];
+    if (phase1) dt[nv] = 1.0;
+    for (int i = 0; i < n; ++i) {
+      double v = t[k] * dt[i];
+      if (i < nv)
+        for (int e = 0; e < P.pc; ++e) v -= z[k][e] * P.rho * P.A[k][e][i];
+      q[i] = v;
+    }
+    const double iD = 1.0 / D[k];
+    for (int i = 0; i < n; ++i) {
+      g[i] -= 2.0 * q[i] * iD;
+      for (int j = 0; j <= i; ++j) {
+        double zz = 0.0;
+        if (i < nv && j < nv)
+          for (int e = 0; e < P.pc; ++e) zz = fma(P.A[k][e][i], P.A[k][e][j], zz);
+        H[i][j] += 4.0 * q[i] * q[j] * iD * iD - 2.0 * (dt[i] * dt[j] - P.rho * P.rho * zz) * iD;
+      }
+    }
+  }
+}
+
+// One centering problem: damped Newton.  Returns the number of Newton steps taken; stops early in phase 1 as soon as the
+// slack is negative (a strictly feasible y has been found).
+__device__ __forceinline__ int socp_center(const SocpProblem& P, double* x, bool phase1, double tau, double eps1,
+                                           int max_newton) {
+  const int n = P.nv + (phase1 ? 1 : 0);
+  int it = 0;
+  for (; it < max_newton; ++it) {
+    if (phase1 && x[P.nv] < 0.0) break;
+    double g[kSN], H[kSN][kSN], dx[kSN];
+    socp_grad_hess(P, x, phase1, tau, eps1, g, H);
+    for (int i = 0; i < n; ++i) dx[i] = -g[i];
+    // tiny ridge keeps the factorisation safe when a direction is (numerically) unconstrained
+    for (int i = 0; i < n; ++i) H[i][i] += 1e-14 * (1.0 + fabs(H[i][i]));
+    if (!socp_solve(H, dx, n)) break;
+    double dec = 0.0;  // Newton decrement squared = -g^T dx
+    for (int i = 0; i < n; ++i) dec -= g[i] * dx[i];
+    if (!(dec > 1e-22)) break;   // also stops on NaN
+    const double f0 = socp_merit(P, x, phase1, tau, eps1);
+    double step = 1.0;
+    double xn[kSN];
+    bool moved = false;
+    for (int ls = 0; ls < 60; ++ls) {
+      for (int i = 0; i < n; ++i) xn[i] = fma(step, dx[i], x[i]);
+      const double f1 = socp_merit(P, xn, phase1, tau, eps1);
+      if (f1 <= f0 - 0.25 * step * dec) { moved = true; break; }
+      step *= 0.5;
+    }
+    if (!moved) break;
+    for (int i = 0; i < n; ++i) x[i] = xn[i];
+    if (dec * 0.5 < 1e-12) { ++it; break; }
+  }
+  return it;
+}
+
+__global__ void socp_solve_kernel(int Q, int nv, int K, int pc, double rho, const double* __restrict__ w, int w_stride,
+                                  const double* __restrict__ r, const double* __restrict__ c,
+                                  const double* __restrict__ d, const double* __restrict__ A,
+                                  const double* __restrict__ b, double tol, double* __restrict__ y_out,
+                                  int* __restrict__ status, int* __restrict__ iters) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Q) return;
+  SocpProblem P;
+  P.nv = nv; P.K = K; P.pc = pc; P.rho = rho;
+  for (int i = 0; i < nv; ++i) {
+    P.w[i] = w[(long long)p * w_stride + i];
+    P.r[i] = r ? r[(long long)p * nv + i] : 0.0;
+  }
+  for (int k = 0; k < K; ++k) {
+    P.d[k] = d[(long long)p * K + k];
+    for (int i = 0; i < nv; ++i) P.c[k][i] = c[((long long)p * K + k) * nv + i];
+    for (int e = 0; e < pc; ++e) {
+      P.b[k][e] = b[((long long)p * K + k) * pc + e];
+      for (int i = 0; i < nv; ++i) P.A[k][e][i] = A[(((long long)p * K + k) * pc + e) * nv + i];
+    }
+  }
+  double x[kSN];
+  for (int i = 0; i < nv; ++i) x[i] = P.r[i];
+  int total = 0, st = 0;
+  // ---- phase I: is y = r strictly feasible?  otherwise minimise the slack ----------------------------------------
+  {
+    double t[kSK], z[kSK][kSP], D[kSK];
+    if (!socp_cones(P, x, 0.0, t, z, D)) {
+      double s0 = 0.0, scale = 1.0;
+      for (int k = 0; k < K; ++k) {
+        double zz = 0.0;
+        for (int e = 0; e < pc; ++e) zz = fma(z[k][e], z[k][e], zz);
+        const double need = sqrt(zz) - (t[k]);   // t_k + s > |z_k|
+        s0 = fmax(s0, need);
+        scale = fmax(scale, fmax(fabs(t[k]), sqrt(zz)));
+      }
+      x[nv] = s0 + 0.1 * scale + 1e-3;
+      const double eps1 = 1e-6;
+      double tau = 1.0 / scale;
+      bool found = false;
+      for (int outer = 0; outer < 60; ++outer) {
+        total += socp_center(P, x, true, tau, eps1, 40);
+        if (x[nv] < 0.0) { found = true; break; }
+        if (2.0 * K / tau < tol * scale) break;   // gap closed with s >= 0: no strictly feasible point
+        tau *= 8.0;
+      }
+      if (!found) st = 1;
+    }
+  }
+  // ---- phase II ------------------------------------------------------------------------------------------------------
+  if (st == 0) {
+    double fscale = 1.0;
+    for (int i = 0; i < nv; ++i) fscale = fmax(fscale, P.w[i]);
+    double tau = 1.0 / fscale;
+    for (int outer = 0; outer < 80; ++outer) {
+      total += socp_center(P, x, false, tau, 0.0, 40);
+      if (2.0 * K / tau < tol) break;
+      tau *= 8.0;
+    }
+  }
+  for (int i = 0; i < nv; ++i) y_out[(long long)p * nv + i] = (st == 0) ? x[i] : __longlong_as_double(0x7ff8000000000000LL);
+  status[p] = st;
+  if (iters) iters[p] = total;
+}
+
+}  // namespace bcbf
+
+using namespace bcbf;
+
+extern "C" int bcbf_socp_solve(int Q, int nv, int K, int pc, double rho, const double* w, int w_per_problem,
+                               const double* r, const double* c, const double* d, const double* A, const double* b,
+                               double tol, double* y, int* status, int* iters, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(w && c && d && A && b && y && status, "bcbf_socp_solve: null pointer");
+  BCBF_REQUIRE(Q >= 1 && nv >= 1 && nv <= kSV && K >= 1 && K <= kSK && pc >= 1 && pc <= kSP && rho >= 0.0 && tol > 0.0,
+               "bcbf_socp_solve: Q=%d nv=%d (<=%d) K=%d (<=%d) pc=%d (<=%d)", Q, nv, kSV, K, kSK, pc, kSP);
+  socp_solve_kernel<<<ceil_div(Q, 64), 64, 0, stream>>>(Q, nv, K, pc, rho, w, w_per_problem ? nv : 0, r, c, d, A, b, tol, y,
+                                                        status, iters);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}

@@ -203,6 +203,18 @@ int bcbf_ens_posterior(const double* LinvT, const double* X, const double* G, co
                        const double* xq, int R, int N, int Npad, int n, int p, double* Mk, double* Bk, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (5) Batched tiny second-order-cone programs — the safety program of one control step, for Q rollouts at once:
+ *     minimise sum_i w_i (y_i - r_i)^2   s.t.   c_k^T y + d_k >= rho ||A_k y + b_k||_2,  k < K
+ * y (Q,nv) with nv <= 4 ([relaxation; u]), K <= 4 cones of dimension pc <= 4.  w is (nv) shared (w_per_problem = 0) or
+ * (Q,nv); r (Q,nv) or NULL (zeros); c (Q,K,nv), d (Q,K), A (Q,K,pc,nv), b (Q,K,pc).  status (Q): 0 optimal, 1 infeasible
+ * (then y = NaN) — the decision on which the reference raises ValueError(problem.status).  Replaces the cvxpy + GUROBI
+ * solve of ControllerCLFBayesian.control (unicycle_move_to_pose.py:926-964) / optimizers.py:91-116.
+ * Log-barrier interior point, float64, deterministic; tol = duality-gap tolerance on the objective (e.g. 1e-9).   */
+int bcbf_socp_solve(int Q, int nv, int K, int pc, double rho, const double* w, int w_per_problem, const double* r,
+                    const double* c, const double* d, const double* A, const double* b, double tol, double* y,
+                    int* status, int* iters /* may be NULL */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Model handle: owns device memory for one fitted MVGP; HOST-pointer interface (pinned or pageable).
  * This is what a non-torch caller (and bench.py's e2e leg) binds.
  */

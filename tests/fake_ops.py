@@ -147,7 +147,7 @@ def installed(monkeypatch):
     me = globals()
     for name in ('padded', 'query_pad', 'gram_train', 'cross_gram', 'gram_ca', 'rbf_blocks', 'potrf_', 'trtri',
                  'trmm_lower', 'gemm', 'posterior_blocks', 'contract_u', 'socp_factor', 'cbc1_terms',
-                 'gram_train_backward'):
+                 'gram_train_backward', 'socp_solve'):
         monkeypatch.setattr(ops, name, me[name])
     import bayesian_cbf_b200.mll as mll
     monkeypatch.setattr(mll, '_need_cuda', lambda *t: None)
@@ -155,3 +155,18 @@ def installed(monkeypatch):
     monkeypatch.setattr(gm, '_need_cuda', lambda t, what: None)
     monkeypatch.setattr(ctl, '_compute_device', lambda dev: dev)
     yield
+
+
+def socp_solve(w, c, d, A, b, rho, r=None, tol=1e-9):
+    from oracle import socp_oracle as S
+    Q, K, nv = c.shape
+    y = torch.empty(Q, nv, dtype=torch.float64)
+    status = torch.empty(Q, dtype=torch.int32)
+    iters = torch.empty(Q, dtype=torch.int32)
+    for p in range(Q):
+        wp = (w[p] if w.ndim == 2 else w).numpy()
+        rp = r[p].numpy() if r is not None else [0.0] * nv
+        yo, st, it = S.solve(wp, rp, c[p].numpy(), d[p].numpy(), A[p].numpy(), b[p].numpy(), float(rho), tol)
+        y[p] = torch.from_numpy(yo)
+        status[p], iters[p] = st, it
+    return y, status, iters

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""BASELINE configs[4] shape on one GPU: R independent `learning_helps_avoid_getting_stuck` rollouts
+(reference unicycle_move_to_pose.py:1948-1969: true Ackermann L=1, prior L=12 with kernel_diag_A=[1,1,1], learning on,
+2 obstacles, PiecewiseLinearPlanner, dt=0.001), each with its own MVGP refitted every `--train-every` steps on at most
+200 of its own samples.  Per control step and rollout: ensemble posterior (HBM-bound kernel) -> CBC/CLC cone terms ->
+batched SOCP.  Hyper-parameters are fixed.  Reports rollout-steps/s; one JSON line."""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--rollouts', type=int, default=512)
+    ap.add_argument('--steps', type=int, default=600)
+    ap.add_argument('--train-every', type=int, default=200)
+    ap.add_argument('--max-train', type=int, default=200)
+    a = ap.parse_args()
+    from bayesian_cbf_b200 import unicycle as U
+    R, dt, numSteps = a.rollouts, 0.001, 2000
+    x0 = [-3.0, -1.0, -math.pi / 4]
+    xg = [0.0, 0.0, math.pi / 4]
+    planner = U.PiecewiseLinearPlanner(x0, xg, numSteps, dt, frac_time_to_reach_goal=0.95)
+    cbfs = U.obstacles_at_mid_from_start_and_goal(x0, xg, term_weights=(0.7, 0.3))
+    learner = U.EnsembleLearner(R, dt, model_L=12.0, max_train=a.max_train, train_every_n_steps=a.train_every,
+                                lengthscale=(1.0, 1.0, 0.7), outputscale=1.0)
+    ctrl = U.BayesCBFController(planner, U.CLFCartesian(Kp=(0.9, 1.5, 0.0)), cbfs, [5.0, 5.0], model_L=12.0,
+                                clf_gamma=10.0, max_risk=0.01, posterior=learner.posterior)
+    g = torch.Generator().manual_seed(0)
+    X0 = (torch.tensor(x0, dtype=torch.float64).repeat(R, 1)
+          + 0.05 * (torch.rand(R, 3, generator=g, dtype=torch.float64) - 0.5)).cuda()
+    U.rollout(ctrl, X0, 5, dt, true_L=1.0)          # warm-up launches
+    learner.Xs, learner.Us = [], []
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = U.rollout(ctrl, X0, a.steps, dt, true_L=1.0, on_step=learner.record)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    alive = int(out['alive'].sum())
+    print(json.dumps(dict(metric='controlled rollout steps/sec (posterior + CBC terms + SOCP per step)',
+                          value=R * a.steps / wall, unit='rollout-steps/s', rollouts=R, steps=a.steps,
+                          ms_per_step=1e3 * wall / a.steps, refits=learner.refits, alive_at_end=alive,
+                          n_train_last=getattr(learner.ens, 'N', 0),
+                          config=dict(workload='ensemble of %d unicycle learning rollouts (BASELINE configs[4] shape), '
+                                               'refit every %d steps, max_train %d' % (R, a.train_every, a.max_train)),
+                          dtype='f64', data='synthetic')))
+
+
+if __name__ == '__main__':
+    main()
