@@ -15,27 +15,35 @@
 namespace bcbf {
 
 constexpr int kSV = 4, kSK = 4, kSP = 4;  // maxima: variables, cones, cone dimension
-constexpr int kSN = kSV + 1;              // phase I adds the slack s
 
+// Sizes are template parameters so that, for the instantiated shapes, every loop unrolls and the whole problem lives in
+// registers (one thread per problem; with run-time sizes the arrays fall to local memory and a Newton step costs ~10x).
+// NV / KC / PC = 0 selects the run-time-sized fallback (maxima kSV / kSK / kSP).
+template <int NV, int KC, int PC>
 struct SocpProblem {
-  int nv, K, pc;
+  static constexpr int MV = NV ? NV : kSV, MK = KC ? KC : kSK, MP = PC ? PC : kSP, MN = MV + 1;
+  int nv_, K_, pc_;
   double rho;
-  double w[kSV], r[kSV];
-  double c[kSK][kSV], d[kSK];
-  double A[kSK][kSP][kSV], b[kSK][kSP];
+  double w[MV], r[MV];
+  double c[MK][MV], d[MK];
+  double A[MK][MP][MV], b[MK][MP];
+  __device__ __forceinline__ int nv() const { return NV ? NV : nv_; }
+  __device__ __forceinline__ int K() const { return KC ? KC : K_; }
+  __device__ __forceinline__ int pc() const { return PC ? PC : pc_; }
 };
 
 // cone values at y (+ slack s added to every t): returns false if some cone is not strictly inside
-__device__ __forceinline__ bool socp_cones(const SocpProblem& P, const double* y, double s, double* t, double z[][kSP],
+template <class PT>
+__device__ __forceinline__ bool socp_cones(const PT& P, const double* y, double s, double* t, double z[][PT::MP],
                                            double* D) {
   bool ok = true;
-  for (int k = 0; k < P.K; ++k) {
+  for (int k = 0; k < P.K(); ++k) {
     double tk = P.d[k] + s;
-    for (int i = 0; i < P.nv; ++i) tk = fma(P.c[k][i], y[i], tk);
+    for (int i = 0; i < P.nv(); ++i) tk = fma(P.c[k][i], y[i], tk);
     double zz = 0.0;
-    for (int q = 0; q < P.pc; ++q) {
+    for (int q = 0; q < P.pc(); ++q) {
       double v = P.b[k][q];
-      for (int i = 0; i < P.nv; ++i) v = fma(P.A[k][q][i], y[i], v);
+      for (int i = 0; i < P.nv(); ++i) v = fma(P.A[k][q][i], y[i], v);
       v *= P.rho;
       z[k][q] = v;
       zz = fma(v, v, zz);
@@ -48,7 +56,8 @@ __device__ __forceinline__ bool socp_cones(const SocpProblem& P, const double* y
 }
 
 // in-place Cholesky solve of the n x n SPD system H x = g (n <= kSN); returns false on a non-positive pivot
-__device__ __forceinline__ bool socp_solve(double H[][kSN], double* g, int n) {
+template <int MN>
+__device__ __forceinline__ bool socp_solve(double H[][MN], double* g, int n) {
   for (int j = 0; j < n; ++j) {
     double dj = H[j][j];
     for (int k = 0; k < j; ++k) dj -= H[j][k] * H[j][k];
@@ -76,20 +85,22 @@ __device__ __forceinline__ bool socp_solve(double H[][kSN], double* g, int n) {
 
 // Barrier value, gradient and Hessian of  tau * f(x) - sum_k log D_k  in the variables x = (y [, s]).
 //   phase 1: f = s + eps1 * sum w (y-r)^2 ;  phase 2: f = sum w (y-r)^2
-__device__ __forceinline__ double socp_merit(const SocpProblem& P, const double* x, bool phase1, double tau, double eps1) {
-  double t[kSK], z[kSK][kSP], D[kSK];
-  if (!socp_cones(P, x, phase1 ? x[P.nv] : 0.0, t, z, D)) return __longlong_as_double(0x7ff0000000000000LL);
+template <class PT>
+__device__ __forceinline__ double socp_merit(const PT& P, const double* x, bool phase1, double tau, double eps1) {
+  double t[PT::MK], z[PT::MK][PT::MP], D[PT::MK];
+  if (!socp_cones(P, x, phase1 ? x[P.nv()] : 0.0, t, z, D)) return __longlong_as_double(0x7ff0000000000000LL);
   double f = 0.0;
-  for (int i = 0; i < P.nv; ++i) f = fma(P.w[i] * (x[i] - P.r[i]), (x[i] - P.r[i]), f);
-  double val = phase1 ? tau * (x[P.nv] + eps1 * f) : tau * f;
-  for (int k = 0; k < P.K; ++k) val -= log(D[k]);
+  for (int i = 0; i < P.nv(); ++i) f = fma(P.w[i] * (x[i] - P.r[i]), (x[i] - P.r[i]), f);
+  double val = phase1 ? tau * (x[P.nv()] + eps1 * f) : tau * f;
+  for (int k = 0; k < P.K(); ++k) val -= log(D[k]);
   return val;
 }
 
-__device__ __forceinline__ void socp_grad_hess(const SocpProblem& P, const double* x, bool phase1, double tau,
-                                               double eps1, double* g, double H[][kSN]) {
-  const int nv = P.nv, n = nv + (phase1 ? 1 : 0);
-  double t[kSK], z[kSK][kSP], D[kSK];
+template <class PT>
+__device__ __forceinline__ void socp_grad_hess(const PT& P, const double* x, bool phase1, double tau, double eps1,
+                                               double* g, double H[][PT::MN]) {
+  const int nv = P.nv(), n = nv + (phase1 ? 1 : 0);
+  double t[PT::MK], z[PT::MK][PT::MP], D[PT::MK];
   socp_cones(P, x, phase1 ? x[nv] : 0.0, t, z, D);
   for (int i = 0; i < n; ++i) {
     g[i] = 0.0;
@@ -101,15 +112,15 @@ __device__ __forceinline__ void socp_grad_hess(const SocpProblem& P, const doubl
     H[i][i] = 2.0 * fs * P.w[i];
   }
   if (phase1) g[nv] = tau;
-  for (int k = 0; k < P.K; ++k) {
+  for (int k = 0; k < P.K(); ++k) {
     // u = (t, z),  q = t * dt/dx - sum_q z_q dz_q/dx ;  grad -= 2 q / D ;  Hess += 4 q q^T / D^2 - 2 (dt dt^T - dz^T dz) / D
-    double dt[kSN], q[kSN];
+    double dt[PT::MN], q[PT::MN];
     for (int i = 0; i < nv; ++i) dt[i] = P.c[k][i];
     if (phase1) dt[nv] = 1.0;
     for (int i = 0; i < n; ++i) {
       double v = t[k] * dt[i];
       if (i < nv)
-        for (int e = 0; e < P.pc; ++e) v -= z[k][e] * P.rho * P.A[k][e][i];
+        for (int e = 0; e < P.pc(); ++e) v -= z[k][e] * P.rho * P.A[k][e][i];
       q[i] = v;
     }
     const double iD = 1.0 / D[k];
@@ -118,7 +129,7 @@ __device__ __forceinline__ void socp_grad_hess(const SocpProblem& P, const doubl
       for (int j = 0; j <= i; ++j) {
         double zz = 0.0;
         if (i < nv && j < nv)
-          for (int e = 0; e < P.pc; ++e) zz = fma(P.A[k][e][i], P.A[k][e][j], zz);
+          for (int e = 0; e < P.pc(); ++e) zz = fma(P.A[k][e][i], P.A[k][e][j], zz);
         H[i][j] += 4.0 * q[i] * q[j] * iD * iD - 2.0 * (dt[i] * dt[j] - P.rho * P.rho * zz) * iD;
       }
     }
@@ -127,24 +138,25 @@ __device__ __forceinline__ void socp_grad_hess(const SocpProblem& P, const doubl
 
 // One centering problem: damped Newton.  Returns the number of Newton steps taken; stops early in phase 1 as soon as the
 // slack is negative (a strictly feasible y has been found).
-__device__ __forceinline__ int socp_center(const SocpProblem& P, double* x, bool phase1, double tau, double eps1,
-                                           int max_newton) {
-  const int n = P.nv + (phase1 ? 1 : 0);
+template <class PT>
+__device__ __forceinline__ int socp_center(const PT& P, double* x, bool phase1, double tau, double eps1, int max_newton,
+                                           double center_tol) {
+  const int n = P.nv() + (phase1 ? 1 : 0);
   int it = 0;
   for (; it < max_newton; ++it) {
-    if (phase1 && x[P.nv] < 0.0) break;
-    double g[kSN], H[kSN][kSN], dx[kSN];
+    if (phase1 && x[P.nv()] < 0.0) break;
+    double g[PT::MN], H[PT::MN][PT::MN], dx[PT::MN];
     socp_grad_hess(P, x, phase1, tau, eps1, g, H);
     for (int i = 0; i < n; ++i) dx[i] = -g[i];
     // tiny ridge keeps the factorisation safe when a direction is (numerically) unconstrained
     for (int i = 0; i < n; ++i) H[i][i] += 1e-14 * (1.0 + fabs(H[i][i]));
-    if (!socp_solve(H, dx, n)) break;
+    if (!socp_solve<PT::MN>(H, dx, n)) break;
     double dec = 0.0;  // Newton decrement squared = -g^T dx
     for (int i = 0; i < n; ++i) dec -= g[i] * dx[i];
     if (!(dec > 1e-22)) break;   // also stops on NaN
     const double f0 = socp_merit(P, x, phase1, tau, eps1);
     double step = 1.0;
-    double xn[kSN];
+    double xn[PT::MN];
     bool moved = false;
     for (int ls = 0; ls < 60; ++ls) {
       for (int i = 0; i < n; ++i) xn[i] = fma(step, dx[i], x[i]);
@@ -154,56 +166,62 @@ __device__ __forceinline__ int socp_center(const SocpProblem& P, double* x, bool
     }
     if (!moved) break;
     for (int i = 0; i < n; ++i) x[i] = xn[i];
-    if (dec * 0.5 < 1e-12) { ++it; break; }
+    if (dec * 0.5 < center_tol) { ++it; break; }
   }
   return it;
 }
 
-__global__ void socp_solve_kernel(int Q, int nv, int K, int pc, double rho, const double* __restrict__ w, int w_stride,
-                                  const double* __restrict__ r, const double* __restrict__ c,
-                                  const double* __restrict__ d, const double* __restrict__ A,
-                                  const double* __restrict__ b, double tol, double* __restrict__ y_out,
-                                  int* __restrict__ status, int* __restrict__ iters) {
+template <int NV, int KC, int PC>
+__global__ void __launch_bounds__(32) socp_solve_kernel(int Q, int nv, int K, int pc, double rho,
+                                                        const double* __restrict__ w, int w_stride,
+                                                        const double* __restrict__ r, const double* __restrict__ c,
+                                                        const double* __restrict__ d, const double* __restrict__ A,
+                                                        const double* __restrict__ b, double tol,
+                                                        double* __restrict__ y_out, int* __restrict__ status,
+                                                        int* __restrict__ iters) {
+  using PT = SocpProblem<NV, KC, PC>;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Q) return;
-  SocpProblem P;
-  P.nv = nv; P.K = K; P.pc = pc; P.rho = rho;
-  for (int i = 0; i < nv; ++i) {
+  PT P;
+  P.nv_ = nv; P.K_ = K; P.pc_ = pc; P.rho = rho;
+  for (int i = 0; i < P.nv(); ++i) {
     P.w[i] = w[(long long)p * w_stride + i];
     P.r[i] = r ? r[(long long)p * nv + i] : 0.0;
   }
-  for (int k = 0; k < K; ++k) {
+  for (int k = 0; k < P.K(); ++k) {
     P.d[k] = d[(long long)p * K + k];
-    for (int i = 0; i < nv; ++i) P.c[k][i] = c[((long long)p * K + k) * nv + i];
-    for (int e = 0; e < pc; ++e) {
+    for (int i = 0; i < P.nv(); ++i) P.c[k][i] = c[((long long)p * K + k) * nv + i];
+    for (int e = 0; e < P.pc(); ++e) {
       P.b[k][e] = b[((long long)p * K + k) * pc + e];
-      for (int i = 0; i < nv; ++i) P.A[k][e][i] = A[(((long long)p * K + k) * pc + e) * nv + i];
+      for (int i = 0; i < P.nv(); ++i) P.A[k][e][i] = A[(((long long)p * K + k) * pc + e) * nv + i];
     }
   }
-  double x[kSN];
-  for (int i = 0; i < nv; ++i) x[i] = P.r[i];
+  double x[PT::MN];
+  for (int i = 0; i < P.nv(); ++i) x[i] = P.r[i];
   int total = 0, st = 0;
+  constexpr double kMu = 10.0;          // barrier parameter growth per outer iteration
+  constexpr double kCenterTol = 1e-5;   // Newton decrement^2 / 2 at which an intermediate centering stops
   // ---- phase I: is y = r strictly feasible?  otherwise minimise the slack ----------------------------------------
   {
-    double t[kSK], z[kSK][kSP], D[kSK];
+    double t[PT::MK], z[PT::MK][PT::MP], D[PT::MK];
     if (!socp_cones(P, x, 0.0, t, z, D)) {
       double s0 = 0.0, scale = 1.0;
-      for (int k = 0; k < K; ++k) {
+      for (int k = 0; k < P.K(); ++k) {
         double zz = 0.0;
-        for (int e = 0; e < pc; ++e) zz = fma(z[k][e], z[k][e], zz);
+        for (int e = 0; e < P.pc(); ++e) zz = fma(z[k][e], z[k][e], zz);
         const double need = sqrt(zz) - (t[k]);   // t_k + s > |z_k|
         s0 = fmax(s0, need);
         scale = fmax(scale, fmax(fabs(t[k]), sqrt(zz)));
       }
-      x[nv] = s0 + 0.1 * scale + 1e-3;
+      x[P.nv()] = s0 + 0.1 * scale + 1e-3;
       const double eps1 = 1e-6;
       double tau = 1.0 / scale;
       bool found = false;
       for (int outer = 0; outer < 60; ++outer) {
-        total += socp_center(P, x, true, tau, eps1, 40);
-        if (x[nv] < 0.0) { found = true; break; }
-        if (2.0 * K / tau < tol * scale) break;   // gap closed with s >= 0: no strictly feasible point
-        tau *= 8.0;
+        total += socp_center(P, x, true, tau, eps1, 40, kCenterTol);
+        if (x[P.nv()] < 0.0) { found = true; break; }
+        if (2.0 * P.K() / tau < tol * scale) break;   // gap closed with s >= 0: no strictly feasible point
+        tau *= kMu;
       }
       if (!found) st = 1;
     }
@@ -211,15 +229,17 @@ __global__ void socp_solve_kernel(int Q, int nv, int K, int pc, double rho, cons
   // ---- phase II ------------------------------------------------------------------------------------------------------
   if (st == 0) {
     double fscale = 1.0;
-    for (int i = 0; i < nv; ++i) fscale = fmax(fscale, P.w[i]);
+    for (int i = 0; i < P.nv(); ++i) fscale = fmax(fscale, P.w[i]);
     double tau = 1.0 / fscale;
     for (int outer = 0; outer < 80; ++outer) {
-      total += socp_center(P, x, false, tau, 0.0, 40);
-      if (2.0 * K / tau < tol) break;
-      tau *= 8.0;
+      const bool last = 2.0 * P.K() / tau < tol;
+      total += socp_center(P, x, false, tau, 0.0, 40, last ? 1e-12 : kCenterTol);
+      if (last) break;
+      tau *= kMu;
     }
   }
-  for (int i = 0; i < nv; ++i) y_out[(long long)p * nv + i] = (st == 0) ? x[i] : __longlong_as_double(0x7ff8000000000000LL);
+  for (int i = 0; i < P.nv(); ++i)
+    y_out[(long long)p * nv + i] = (st == 0) ? x[i] : __longlong_as_double(0x7ff8000000000000LL);
   status[p] = st;
   if (iters) iters[p] = total;
 }
@@ -235,8 +255,17 @@ extern "C" int bcbf_socp_solve(int Q, int nv, int K, int pc, double rho, const d
   BCBF_REQUIRE(w && c && d && A && b && y && status, "bcbf_socp_solve: null pointer");
   BCBF_REQUIRE(Q >= 1 && nv >= 1 && nv <= kSV && K >= 1 && K <= kSK && pc >= 1 && pc <= kSP && rho >= 0.0 && tol > 0.0,
                "bcbf_socp_solve: Q=%d nv=%d (<=%d) K=%d (<=%d) pc=%d (<=%d)", Q, nv, kSV, K, kSK, pc, kSP);
-  socp_solve_kernel<<<ceil_div(Q, 64), 64, 0, stream>>>(Q, nv, K, pc, rho, w, w_per_problem ? nv : 0, r, c, d, A, b, tol, y,
-                                                        status, iters);
+  // one thread per problem, 32-thread CTAs so that a few hundred problems still spread over the SMs
+  const int ws = w_per_problem ? nv : 0;
+  const dim3 grid(ceil_div(Q, 32)), block(32);
+#define BCBF_SOCP_LAUNCH(NV, KC, PC) \
+  socp_solve_kernel<NV, KC, PC><<<grid, block, 0, stream>>>(Q, nv, K, pc, rho, w, ws, r, c, d, A, b, tol, y, status, iters)
+  if (nv == 3 && K == 3 && pc == 3) BCBF_SOCP_LAUNCH(3, 3, 3);        // unicycle: [relax, v, omega], CLC + 2 CBCs
+  else if (nv == 3 && K == 2 && pc == 3) BCBF_SOCP_LAUNCH(3, 2, 3);   // unicycle, one obstacle
+  else if (nv == 3 && K == 1 && pc == 3) BCBF_SOCP_LAUNCH(3, 1, 3);   // unicycle, CLC only
+  else if (nv == 2 && K == 2 && pc == 2) BCBF_SOCP_LAUNCH(2, 2, 2);   // pendulum: [relax, u], CLC + CBC
+  else BCBF_SOCP_LAUNCH(0, 0, 0);                                     // any other shape: run-time sizes
+#undef BCBF_SOCP_LAUNCH
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }

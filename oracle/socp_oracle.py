@@ -11,6 +11,10 @@ import math
 import numpy as np
 
 
+MU = 10.0            # barrier parameter growth per outer iteration (socp.cu kMu)
+CENTER_TOL = 1e-5    # intermediate centering tolerance on decrement^2 / 2 (socp.cu kCenterTol)
+
+
 def _cones(c, d, A, b, rho, y, s):
     t = c @ y + d + s                      # (K,)
     z = rho * (A @ y + b)                  # (K, pc)
@@ -56,7 +60,7 @@ def _grad_hess(w, r, c, d, A, b, rho, x, phase1, tau, eps1):
     return g, H
 
 
-def _center(w, r, c, d, A, b, rho, x, phase1, tau, eps1, max_newton):
+def _center(w, r, c, d, A, b, rho, x, phase1, tau, eps1, max_newton, center_tol):
     nv = len(w)
     n = nv + (1 if phase1 else 0)
     it = 0
@@ -84,7 +88,7 @@ def _center(w, r, c, d, A, b, rho, x, phase1, tau, eps1, max_newton):
         if not moved:
             break
         x[:] = xn
-        if dec * 0.5 < 1e-12:
+        if dec * 0.5 < center_tol:
             it += 1
             break
         it += 1
@@ -107,22 +111,23 @@ def solve(w, r, c, d, A, b, rho, tol=1e-9):
         x[nv] = s0 + 0.1 * scale + 1e-3
         tau, found = 1.0 / scale, False
         for _ in range(60):
-            total += _center(w, r, c, d, A, b, rho, x, True, tau, 1e-6, 40)
+            total += _center(w, r, c, d, A, b, rho, x, True, tau, 1e-6, 40, CENTER_TOL)
             if x[nv] < 0.0:
                 found = True
                 break
             if 2.0 * K / tau < tol * scale:
                 break
-            tau *= 8.0
+            tau *= MU
         if not found:
             st = 1
     if st == 0:
         y = x[:nv].copy()
         tau = 1.0 / max(1.0, float(w.max()))
         for _ in range(80):
-            total += _center(w, r, c, d, A, b, rho, y, False, tau, 0.0, 40)
-            if 2.0 * K / tau < tol:
+            last = 2.0 * K / tau < tol
+            total += _center(w, r, c, d, A, b, rho, y, False, tau, 0.0, 40, 1e-12 if last else CENTER_TOL)
+            if last:
                 break
-            tau *= 8.0
+            tau *= MU
         return y, 0, total
     return np.full(nv, np.nan), 1, total

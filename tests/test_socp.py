@@ -90,5 +90,5 @@ def test_cuda_solver_matches_restatement(nv, K, pc):
         else:
             n_inf += 1
             assert np.isnan(y[p]).all()
-    assert 0 < n_inf < Q
+    assert n_inf < Q and (n_inf > 0 or K == 1)     # a single relaxed cone is always feasible
     assert int(iters.max()) < 2000
