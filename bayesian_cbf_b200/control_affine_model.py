@@ -30,7 +30,8 @@ from torch import nn
 from . import autograd_ops, ops
 from ._lib import NotPositiveDefiniteError
 from .gp_algebra import GaussianProcess
-from .gp_modules import (ConstantMean, GammaPrior, IndexKernel, MultivariateNormalResult, RBFKernel, ScaleKernel)
+from .gp_modules import (ConstantMean, GammaPrior, IndexKernel, LinearKernel, MultivariateNormalResult, RBFKernel,
+                         ScaleKernel)
 from .matrix_variate_multitask_kernel import HetergeneousMatrixVariateKernel, MatrixVariateIndexKernel
 from .matrix_variate_multitask_model import HetergeneousMatrixVariateMean
 from .misc import DynamicsModel, torch_kron
@@ -742,3 +743,218 @@ ControlAffineRegressorExactRankOne = partial(
 ControlAffineRegMatrixDiag = partial(
     ControlAffineRegressorExact,
     model_class=partial(ControlAffineExactGP, rank=0))
+
+
+# =====================================================================================================================
+# CoGP comparator: vec F(x) ~ GP(vec M(x), Sigma k(x,x')) with one (p n) x (p n) coregionalisation matrix
+# instead of the Kronecker pair (A, B).  It exists in the reference as the baseline the MVGP is compared against
+# (control_affine_model.py:1106-1331; speed test pendulum.py:1316-1319).  The (N n) x (N n) factorisation and every
+# N-sized product run on the same CUDA kernels; the (u^T (x) I) Sigma (u (x) I) contraction that assembles the Gram
+# entries is small-index glue.  fit() with training_iter > 0 is not provided for this comparator (the fused log
+# marginal of mll.py is specific to the Kronecker model).
+# =====================================================================================================================
+class ControlAffineVectorGP(ControlAffineExactGP):
+    def __init__(self, x_dim, u_dim, likelihood, rank=None, gamma_length_scale_prior=None):
+        nn.Module.__init__(self)
+        self.likelihood = likelihood
+        self.matshape = (1 + u_dim, x_dim)
+        self.decoder = CatEncoder(1, x_dim, 1 + u_dim)
+        self.mean_module = HetergeneousMatrixVariateMean(ConstantMean(), self.decoder, self.matshape)
+        num_tasks = int(np.prod(self.matshape))
+        self.task_covar = IndexKernel(num_tasks=num_tasks, rank=(num_tasks if rank is None else rank))
+        prior = None if gamma_length_scale_prior is None else GammaPrior(*gamma_length_scale_prior)
+        self.input_covar = ScaleKernel(RBFKernel(lengthscale_prior=prior) + LinearKernel())
+        self.covar_module = None     # the lazy HetergeneousCoregionalizationKernel is only needed by gpytorch's fit
+        self.train_inputs = None
+        self.train_targets = None
+
+    def forward(self, mxu):
+        raise NotImplementedError("ControlAffineVectorGP.forward (gpytorch training path) is not provided")
+
+    def state_dict(self, *a, **k):
+        return dict(matshape=self.matshape, decoder=self.decoder.state_dict(),
+                    mean_module=self.mean_module.state_dict(), task_covar=nn.Module.state_dict(self.task_covar),
+                    input_covar=nn.Module.state_dict(self.input_covar), train_inputs=self.train_inputs,
+                    train_targets=self.train_targets)
+
+
+class ControlAffineRegressorVector(ControlAffineRegressor):
+    def __init__(self, *args, model_class=ControlAffineVectorGP, **kwargs):
+        super().__init__(*args, model_class=model_class, **kwargs)
+
+    def _fit_with_warnings(self, Xtrain_in, Utrain_in, XdotTrain_in, training_iter=50, lr=0.1):
+        if Xtrain_in.shape[0] == 0:
+            return self
+        if training_iter > 0:
+            raise NotImplementedError("hyper-parameter fitting of the CoGP comparator is not provided; set its "
+                                      "parameters and call fit(..., training_iter=0)")
+        Xtrain, Utrain, XdotTrain = [self._ensure_device_dtype(X) for X in (Xtrain_in, Utrain_in, XdotTrain_in)]
+        self.clear_cache()
+        self.model.set_train_data(Xtrain, Utrain, XdotTrain)
+        return self
+
+    def set_hyperparameters(self, lengthscale=None, outputscale=None, Sigma=None, C=None, linear_variance=None):
+        """Constrained hyper-parameters of the CoGP model: scalar RBF lengthscale, outputscale, Sigma (pn,pn), C (p,n),
+        LinearKernel variance."""
+        from .gp_modules import inv_softplus
+        mdl, dev, dt = self.model, self.device, self.dtype
+        t = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float64) if not isinstance(v, torch.Tensor) else v,
+                                      dtype=torch.float64)
+        rbf, lin = mdl.input_covar.base_kernel.kernels[0], mdl.input_covar.base_kernel.kernels[1]
+        with torch.no_grad():
+            if lengthscale is not None:
+                rbf.raw_lengthscale.copy_(inv_softplus(t(lengthscale)).reshape(1, 1).to(dev, dt))
+            if linear_variance is not None:
+                lin.raw_variance.copy_(inv_softplus(t(linear_variance)).reshape(1, 1).to(dev, dt))
+            if outputscale is not None:
+                mdl.input_covar.raw_outputscale.copy_(inv_softplus(t(outputscale)).reshape(()).to(dev, dt))
+            if Sigma is not None:
+                M = t(Sigma)
+                d = 0.5 * float(torch.linalg.eigvalsh(M).min())
+                Fm = torch.linalg.cholesky(M - d * torch.eye(M.shape[0], dtype=torch.float64))
+                mdl.task_covar.covar_factor = nn.Parameter(Fm.to(dev, dt))
+                mdl.task_covar.raw_var = nn.Parameter(inv_softplus(torch.full((M.shape[0],), d, dtype=torch.float64)).to(dev, dt))
+            if C is not None:
+                for bm, c in zip(mdl.mean_module.base_means, t(C).reshape(-1)):
+                    bm.constant.fill_(float(c))
+        self.clear_cache()
+        return self
+
+    # ---- pieces -------------------------------------------------------------------------------------------------------
+    def _sigma64(self):
+        return self.model.task_covar.covar_matrix.evaluate().detach().double().contiguous()
+
+    def _k_data(self, a, c):
+        """outputscale * (RBF(a, c) + variance * a c^T) on the GPU (float64)."""
+        ic = self.model.input_covar
+        rbf, lin = ic.base_kernel.kernels[0], ic.base_kernel.kernels[1]
+        s = float(ic.outputscale.detach())
+        ls = rbf.lengthscale.detach().reshape(-1).double().expand(a.shape[1]).contiguous()
+        K = ops.gram_ca(a.contiguous(), c.contiguous(), ls, s)
+        return ops.gemm(a, c, transb=True, alpha=s * float(lin.variance.detach()), beta=1.0, C=K)
+
+    def _u_sigma(self, UH, Sigma):
+        """(u_i^T (x) I_n) Sigma  ->  (k, n, p n)."""
+        p, n = self.model.matshape
+        S4 = Sigma.reshape(p, n, p * n)
+        return torch.einsum('iq,qrc->irc', UH, S4)
+
+    def _perturbed_cholesky_compute(self, k_xx, Sigma, Xtrain, UHtrain, cholesky_tries=10, cholesky_perturb_init=1e-5,
+                                    cholesky_perturb_scale=10):
+        _need_cuda(Xtrain.device)
+        p, n = self.model.matshape
+        X64, UH64 = Xtrain.double().contiguous(), UHtrain.double().contiguous()
+        k = X64.shape[0]
+        KXX = self._k_data(X64, X64)
+        US = self._u_sigma(UH64, Sigma)                                            # (k, n, p n)
+        uSu = torch.einsum('irqs,jq->irjs', US.reshape(k, n, p, n), UH64)            # (k, n, k, n)
+        Kb = (KXX.reshape(k, 1, k, 1) * uSu).reshape(k * n, k * n)
+        Kbp, L = self._make_psd_like_reference(Kb, cholesky_tries, cholesky_perturb_init, cholesky_perturb_scale)
+        return L
+
+    def _make_psd_like_reference(self, M, tries=10, init=1e-5, scale=10, want_inverse=True):
+        nrows = M.shape[0]
+        factor = init
+        for ntry in range(tries):
+            eps = next(self._jitter_source) if self._jitter_source is not None else _draw_jitter(nrows, self.dtype)
+            eps = eps.to(device=M.device, dtype=torch.float64).contiguous()
+            buf = torch.eye(ops.padded(nrows), dtype=torch.float64, device=M.device)
+            buf[:nrows, :nrows] = M
+            try:
+                L, dinv = ops.potrf_(buf, nrows, eps, factor)
+                break
+            except RuntimeError as e:
+                if ntry == tries - 1:
+                    raise
+                LOG.warning("Cholesky failed with perturb={} on error {}".format(factor, str(e)))
+                factor *= scale
+        if want_inverse:
+            self._cache['_Lpad'] = L
+            self._cache['_Linv'] = ops.trtri(L, dinv)
+        return M + factor * torch.diag(eps), L[:nrows, :nrows]
+
+    def _custom_predict_matrix(self, Xtest_in, Xtestp_in=None, compute_cov=True, _out_jitter=True):
+        """M_k (b,n,p) and Sigma_k (b,b',pn,pn)  (reference :1219-1331)."""
+        _need_cuda(self.device)
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        Xtestp = self._ensure_device_dtype(Xtestp_in) if Xtestp_in is not None else Xtest
+        out_dt = self.dtype
+        p, n = self.model.matshape
+        Sigma = self._sigma64()
+        C = self.model.mean_module.constants().detach().double()
+        Xq, Xp = Xtest.double(), Xtestp.double()
+        b, bp_ = Xq.shape[0], Xp.shape[0]
+        M0 = C.t().unsqueeze(0).expand(b, n, p)
+        if self.model.train_inputs is None:
+            return M0.to(out_dt), (Sigma * self._k_data(Xq, Xp).unsqueeze(-1).unsqueeze(-1)).to(out_dt)
+        Xtrain, UHtrain, targets = self._train_data()
+        X64, UH64 = Xtrain.double().contiguous(), UHtrain.double().contiguous()
+        k = X64.shape[0]
+        self._perturbed_cholesky(None, Sigma, Xtrain, UHtrain)
+        Linv = self._cache['_Linv']
+        Npad = Linv.shape[0]
+        Y = (targets.double() - UH64 @ C).reshape(-1, 1)                           # vec, (k n, 1), r fastest
+        if '_alpha_vec' not in self._cache:
+            Ypad = torch.zeros(Npad, 2, dtype=torch.float64, device=Y.device)
+            Ypad[:k * n, :1] = Y
+            z = ops.trmm_lower(Linv, Ypad)
+            self._cache['_alpha_vec'] = ops.trmm_lower(Linv, z.contiguous(), trans=True)[:, :1].contiguous()
+        alpha = self._cache['_alpha_vec']
+        US = self._u_sigma(UH64, Sigma)                                            # (k, n, pn)
+        Kst = self._k_data(Xq, X64)                                                # (b, k)
+        # kb_star as an (Npad, b * pn) matrix: rows (i, r), columns (t, c)
+        kbs = (Kst.t().reshape(k, 1, b, 1) * US.reshape(k, n, 1, p * n)).reshape(k * n, b * p * n)
+        kbs_pad = torch.zeros(Npad, b * p * n, dtype=torch.float64, device=kbs.device)
+        kbs_pad[:k * n] = kbs
+        mean_k = M0 + ops.gemm(kbs_pad, alpha, transa=True).reshape(b, p, n).transpose(-2, -1)
+        if not compute_cov:
+            return mean_k.to(out_dt), Xtest.new_zeros(b, bp_, p * n, p * n)
+        V = ops.trmm_lower(Linv, kbs_pad)
+        KS = torch_kron(self._k_data(Xq, Xp), Sigma, batch_dims=0)
+        KkXX = ops.gemm(V, V, transa=True, alpha=-1.0, beta=1.0, C=KS)
+        if _out_jitter:
+            KkXX, _ = self._make_psd_like_reference(KkXX, want_inverse=False)
+        KkXX = KkXX.reshape(b, p * n, bp_, p * n).transpose(2, 1)
+        return mean_k.to(out_dt), KkXX.to(out_dt)
+
+    def custom_predict(self, Xtest_in, Utest_in=None, UHfill=1, Xtestp_in=None, Utestp_in=None, UHfillp=1,
+                       compute_cov=True):
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        Xtestp = self._ensure_device_dtype(Xtestp_in) if Xtestp_in is not None else Xtest
+        meanFX, KkXX = self._custom_predict_matrix(Xtest_in, Xtestp_in, compute_cov=compute_cov)
+        UHtest = self._uh(Xtest, Utest_in, UHfill)
+        meanFXU = meanFX.bmm(UHtest.unsqueeze(-1)).squeeze(-1)
+        b, n = Xtest.shape
+        if compute_cov:
+            # the reference contracts BOTH sides with UHtest (:1160-1168), also when Utestp is given
+            In = torch.eye(n, dtype=Xtest.dtype, device=Xtest.device)
+            blk = torch_kron(UHtest, In, batch_dims=0).reshape(b, 1, n, -1)
+            blk_T = blk.reshape(1, b, n, -1).transpose(-2, -1)
+            varFXU = torch.matmul(torch.matmul(blk, KkXX), blk_T)
+        else:
+            varFXU = Xtest.new_zeros(b, Xtestp.shape[0], n, n)
+        return meanFXU, varFXU
+
+    def custom_predict_fullmat(self, Xtest_in, Xtestp_in=None):
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        meanFX, varFX = self._custom_predict_matrix(Xtest_in, Xtestp_in, compute_cov=True)
+        b, p, n = Xtest.shape[0], 1 + self.u_dim, self.x_dim
+        return meanFX.transpose(-2, -1).reshape(-1), varFX.transpose(2, 1).reshape(b * p * n, b * p * n)
+
+    def custom_predict_blocks(self, *a, **k):
+        raise NotImplementedError("per-query block fast path exists for the matrix-variate model only")
+
+    def predict(self, Xtest_in, return_cov=True):
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        if isinstance(Xtest_in, np.ndarray):
+            Xtest_in = torch.from_numpy(Xtest_in)
+        meanFX, varFX = self._custom_predict_matrix(Xtest, None, compute_cov=return_cov, _out_jitter=False)
+        b, p, n = Xtest.shape[0], 1 + self.u_dim, self.x_dim
+        mean = meanFX.transpose(-2, -1).to(device=Xtest_in.device, dtype=Xtest_in.dtype)
+        if not return_cov:
+            return mean
+        cov = varFX.transpose(2, 1).reshape(b * p * n, b * p * n)
+        return mean, cov.to(device=Xtest_in.device, dtype=Xtest_in.dtype)
+
+
+ControlAffineRegVectorDiag = partial(ControlAffineRegressorVector, model_class=partial(ControlAffineVectorGP, rank=0))

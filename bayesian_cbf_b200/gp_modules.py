@@ -190,3 +190,42 @@ class MultivariateNormalResult:
     @property
     def lazy_covariance_matrix(self):
         return Evaluated(self._covar)
+
+
+class LinearKernel(Kernel):
+    """variance * x1 x2^T (gpytorch LinearKernel; `raw_variance` (1,1), softplus-positive)."""
+
+    def __init__(self):
+        super().__init__()
+        self.raw_variance = nn.Parameter(torch.zeros(1, 1))
+
+    @property
+    def variance(self):
+        return F.softplus(self.raw_variance)
+
+    def forward(self, x1, x2, diag=False, outputscale=None, **params):
+        _need_cuda(x1, 'LinearKernel')
+        s = 1.0 if outputscale is None else float(outputscale.detach())
+        K = ops.gemm(x1.double(), x2.double(), transb=True, alpha=s * float(self.variance.detach()))
+        K = K.to(x1.dtype)
+        return torch.diagonal(K) if diag else K
+
+
+class AdditiveKernel(Kernel):
+    def __init__(self, *kernels):
+        super().__init__()
+        self.kernels = nn.ModuleList(kernels)
+
+    def forward(self, x1, x2, diag=False, **params):
+        out = None
+        for k in self.kernels:
+            r = k.forward(x1, x2, diag=diag, **params)
+            out = r if out is None else out + r
+        return out
+
+
+def _kernel_add(self, other):
+    return AdditiveKernel(self, other)
+
+
+Kernel.__add__ = _kernel_add

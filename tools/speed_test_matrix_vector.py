@@ -22,7 +22,12 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-PUBLISHED = {256: 0.04359, 320: 0.04527, 384: 0.05029, 512: 0.07753}   # BASELINE.md, matrix/elapsed [s]
+PUBLISHED = {   # BASELINE.md section 1, */elapsed [s] at N = 256, 320, 384, 512
+    'matrix': {256: 0.04359, 320: 0.04527, 384: 0.05029, 512: 0.07753},
+    'vector': {256: 0.06428, 320: 0.08648, 384: 0.11682, 512: 0.19145},
+    'matrixdiag': {256: 0.03314, 320: 0.03629, 384: 0.04174, 512: 0.05108},
+    'vectordiag': {256: 0.05899, 320: 0.08177, 384: 0.11233, 512: 0.17858},
+}
 
 
 def pendulum_trajectory(steps, tau=0.01, x0=(5 * math.pi / 6, -0.01), mass=1.0, gravity=10.0, length=1.0, seed=0):
@@ -56,22 +61,28 @@ def main():
     ap.add_argument('--number', type=int, default=50)
     ap.add_argument('--fit', type=int, default=0, help='Adam iterations before timing (the reference uses 50)')
     ap.add_argument('--dtype', default='float32', choices=['float32', 'float64'])
+    ap.add_argument('--series', nargs='*', default=['matrix', 'vector', 'matrixdiag', 'vectordiag'])
     a = ap.parse_args()
-    from bayesian_cbf_b200.control_affine_model import ControlAffineRegressorExact
+    from bayesian_cbf_b200 import control_affine_model as cam
+    classes = dict(matrix=cam.ControlAffineRegressorExact, vector=cam.ControlAffineRegressorVector,
+                   matrixdiag=cam.ControlAffineRegMatrixDiag, vectordiag=cam.ControlAffineRegVectorDiag)
     dt = torch.float32 if a.dtype == 'float32' else torch.float64
     steps = max(2001, max(a.sizes) + 2)
     dX, X, U = pendulum_trajectory(steps)
     order = np.random.RandomState(0).permutation(X.shape[0])
     out = []
-    for N in a.sizes:
+    for series in a.series:
+      for N in a.sizes:
+        if series.startswith('vector') and N > 2048:
+            continue   # (N n)^2 factor: the reference itself runs out of memory here
         idx = order[:N]
         Xtr, Utr, dXtr = (torch.from_numpy(M[idx]).to(dt) for M in (X, U, dX))
         Xtest = torch.from_numpy(grid_from_Xtrain(X[idx])).to(dt)
         torch.manual_seed(0)
-        dgp = ControlAffineRegressorExact(2, 1, device='cuda')
+        dgp = classes[series](2, 1, device='cuda')
         if dt is torch.float64:
             dgp.model.double()
-        dgp.fit(Xtr, Utr, dXtr, training_iter=a.fit)
+        dgp.fit(Xtr, Utr, dXtr, training_iter=(a.fit if series.startswith('matrix') else 0))
         Xtest_d = Xtest.cuda()
 
         def stmt():
@@ -86,8 +97,9 @@ def main():
             torch.cuda.synchronize()   # the result is consumed on the host in the reference (plots / logs)
         elapsed = min(timeit.repeat(timed, repeat=a.repeat, number=number)) / number
         mean, cov = dgp.custom_predict_fullmat(Xtest_d)
-        rec = dict(N=N, b=int(Xtest.shape[0]), seconds_per_call=elapsed, queries_per_s=Xtest.shape[0] / elapsed,
-                   published_reference_s=PUBLISHED.get(N), speedup_vs_published=(PUBLISHED[N] / elapsed) if N in PUBLISHED else None,
+        rec = dict(series=series, N=N, b=int(Xtest.shape[0]), seconds_per_call=elapsed, queries_per_s=Xtest.shape[0] / elapsed,
+                   published_reference_s=PUBLISHED[series].get(N),
+                   speedup_vs_published=(PUBLISHED[series][N] / elapsed) if N in PUBLISHED[series] else None,
                    cov_shape=list(cov.shape), dtype=a.dtype, fit_iters=a.fit)
         print(json.dumps(rec), flush=True)
         out.append(rec)
