@@ -233,3 +233,46 @@ def test_model_handle_host_pointers():
     assert np.abs(svar - svar_o.numpy()).max() / prior < 1e-8
     assert np.abs(Mk - Mk_o.numpy()).max() < 1e-6 * np.abs(Mk_o.numpy()).max()
     assert np.abs(mean - mean_o.numpy()).max() < 1e-6 * np.abs(mean_o.numpy()).max()
+
+
+def test_model_handle_batches_large_query_sets_and_reports_errors():
+    """bcbf_model_query splits query sets larger than one device batch (148 * 32 * 4 queries at p = 3) and the pieces
+    agree with a single small call; error paths return codes, not crashes."""
+    from bayesian_cbf_b200 import _lib
+    from bayesian_cbf_b200.model import MVGPModel, make_hyper
+    N, n, m = 260, 3, 2
+    X, U, Xdot, hyp, jit, _, _ = _mk(21, N, n, m, 4)
+    model = MVGPModel(0)
+    # querying before fitting is an error, not a crash
+    with pytest.raises(_lib.BcbfError, match="not fitted"):
+        model.hyper = make_hyper(n, m + 1, hyp.lengthscale.numpy(), 1.3, hyp.A.numpy(), hyp.B.numpy(), hyp.C.numpy())
+        model.query(np.zeros((2, n)), np.zeros((2, m)))
+    model.fit(make_hyper(n, m + 1, hyp.lengthscale.numpy(), float(hyp.outputscale), hyp.A.numpy(), hyp.B.numpy(),
+                         hyp.C.numpy()), X.numpy(), U.numpy(), Xdot.numpy(), jit.numpy(), 1e-5)
+    g = torch.Generator().manual_seed(2)
+    Q = 148 * 32 * 4 + 777            # one full device batch plus a ragged tail
+    Xq = (4 * torch.rand(Q, n, generator=g, dtype=torch.float64) - 2).numpy()
+    Uq = (2 * torch.rand(Q, m, generator=g, dtype=torch.float64) - 1).numpy()
+    big = model.query(Xq, Uq)
+    idx = np.array([0, 1, 18943, 18944, 18945, Q - 1])
+    small = model.query(Xq[idx], Uq[idx])
+    for k in ('mean', 'svar', 'Mk', 'Bk'):
+        assert np.array_equal(big[k][idx], small[k]), k     # same kernels, same arithmetic: bit-identical
+    # a non-PD Gram (negative outputscale) reports NOT_PD as a RuntimeError subclass: the caller's jitter-retry loop
+    bad = make_hyper(n, m + 1, hyp.lengthscale.numpy(), -1.0, hyp.A.numpy(), hyp.B.numpy(), hyp.C.numpy())
+    with pytest.raises(RuntimeError, match="not positive-definite"):
+        model.fit(bad, X.numpy(), U.numpy(), Xdot.numpy(), jit.numpy(), 1e-5)
+    model.close()
+
+
+def test_ops_reject_wrong_inputs():
+    from bayesian_cbf_b200 import ops
+    with pytest.raises(RuntimeError, match="float64"):
+        ops.gram_train(torch.zeros(4, 2, device='cuda'), torch.zeros(4, 2, device='cuda'), torch.eye(2, device='cuda'),
+                       torch.ones(2, device='cuda'), 1.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.cross_gram(torch.zeros(4, 2, dtype=torch.float64), torch.zeros(3, 2, dtype=torch.float64),
+                       torch.ones(2, dtype=torch.float64), 1.0)
+    with pytest.raises(RuntimeError, match="even"):     # bcbf_potrf: Npad must be a multiple of 128
+        A = torch.eye(100, dtype=torch.float64, device='cuda')
+        ops.potrf_(A, 100, None, 0.0)
