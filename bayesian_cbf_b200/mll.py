@@ -52,12 +52,14 @@ class _MVGPLogMarginal(torch.autograd.Function):
         z = ops.trmm_lower(Linv, Ypad)                              # L^-1 Y
         alpha = ops.trmm_lower(Linv, z.contiguous(), trans=True)    # Kb^-1 Y
         alpha = alpha[:N].contiguous()
-        La = torch.linalg.cholesky(A.detach())                       # n x n glue
-        Ai = torch.cholesky_inverse(La)
+        # n x n glue: factor A on the host (a 2x2 / 3x3 matrix; avoids dragging a dense-solver library into the loop)
+        A_h = A.detach().cpu()
+        La_h = torch.linalg.cholesky(A_h)
+        Ai = torch.cholesky_inverse(La_h).to(dev)
         YtA = z[:N].transpose(0, 1) @ z[:N]                          # Y^T Kb^-1 Y  (n x n)
         quad = torch.trace(Ai @ YtA)
         logdetK = 2.0 * torch.log(torch.diagonal(L)[:N]).sum()
-        logdetA = 2.0 * torch.log(torch.diagonal(La)).sum()
+        logdetA = (2.0 * torch.log(torch.diagonal(La_h)).sum()).to(dev)
         value = -0.5 * (quad + nout * logdetK + N * logdetA + N * nout * math.log(2 * math.pi))
         # ---- gradients (always needed by fit; computed eagerly) -----------------------------------------------
         Pinv = ops.gemm(Linv, Linv, transa=True)                     # Kb^-1 = L^-T L^-1  (Npad, Npad)

@@ -256,8 +256,10 @@ def test_model_handle_batches_large_query_sets_and_reports_errors():
     big = model.query(Xq, Uq)
     idx = np.array([0, 1, 18943, 18944, 18945, Q - 1])
     small = model.query(Xq[idx], Uq[idx])
+    prior = float(hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)) * 3
     for k in ('mean', 'svar', 'Mk', 'Bk'):
-        assert np.array_equal(big[k][idx], small[k]), k     # same kernels, same arithmetic: bit-identical
+        # same kernels; only the split of the row-block reduction differs with the number of query tiles
+        assert np.abs(big[k][idx] - small[k]).max() < 1e-12 * max(prior, np.abs(small[k]).max()), k
     # a non-PD Gram (negative outputscale) reports NOT_PD as a RuntimeError subclass: the caller's jitter-retry loop
     bad = make_hyper(n, m + 1, hyp.lengthscale.numpy(), -1.0, hyp.A.numpy(), hyp.B.numpy(), hyp.C.numpy())
     with pytest.raises(RuntimeError, match="not positive-definite"):
@@ -273,6 +275,6 @@ def test_ops_reject_wrong_inputs():
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.cross_gram(torch.zeros(4, 2, dtype=torch.float64), torch.zeros(3, 2, dtype=torch.float64),
                        torch.ones(2, dtype=torch.float64), 1.0)
-    with pytest.raises(RuntimeError, match="even"):     # bcbf_potrf: Npad must be a multiple of 128
+    with pytest.raises(RuntimeError, match="libbcbf error -1"):     # bcbf_potrf: Npad must be a multiple of 128
         A = torch.eye(100, dtype=torch.float64, device='cuda')
         ops.potrf_(A, 100, None, 0.0)
