@@ -154,19 +154,31 @@ class BayesCBFController:
         self.clf_gamma, self.cost_weights = float(clf_gamma), [float(w) for w in cost_weights]
         self.rho = cbc1_safety_factor(max_risk)
         self.posterior = posterior
+        self._const = {}
 
-    def constraint_terms(self, X, t):
+    def _constants(self, dev):
+        """Device-resident constants, created once per device (also keeps host->device copies out of CUDA graphs)."""
+        key = str(dev)
+        if key not in self._const:
+            f64 = dict(dtype=torch.float64, device=dev)
+            self._const[key] = dict(
+                A_prior=torch.diag(torch.tensor(self.kdA, **f64)), eye=torch.eye(3, **f64),
+                w=torch.tensor([self.cost_weights[2], self.cost_weights[0], self.cost_weights[1]], **f64))
+        return self._const[key]
+
+    def constraint_terms(self, X, t, goal=None, dplan=None):
         """Cone terms of the CLC (k = 0) and the CBCs (k >= 1): c (R,K,3), d (R,K), A (R,K,3,3), b (R,K,3) in the
-        variables y = [relax, u1, u2]."""
+        variables y = [relax, u1, u2].  goal / dplan: optional (3,) device tensors holding planner.plan(t) /
+        planner.dot_plan(t) (the CUDA-graph path keeps them in static buffers); default: computed from t."""
         R, dev = X.shape[0], X.device
         f64 = dict(dtype=torch.float64, device=dev)
-        goal = torch.tensor(self.planner.plan(t), **f64).expand(R, 3)
-        dplan = torch.tensor(self.planner.dot_plan(t), **f64).expand(R, 3)
+        goal = (torch.tensor(self.planner.plan(t), **f64) if goal is None else goal).expand(R, 3)
+        dplan = (torch.tensor(self.planner.dot_plan(t), **f64) if dplan is None else dplan).expand(R, 3)
         Fbar = ackermann_F(X, self.model_L)
         if self.posterior is None:
             Mk = torch.zeros(R, 3, 3, **f64)
-            Bk = torch.eye(3, **f64).expand(R, 3, 3).contiguous()
-            Amat = torch.diag(torch.tensor(self.kdA, **f64))
+            Bk = self._constants(dev)['eye'].expand(R, 3, 3).contiguous()
+            Amat = self._constants(dev)['A_prior']
         else:
             Mk, Bk, Amat = self.posterior(X)
         K = 1 + len(self.cbfs)
@@ -181,7 +193,7 @@ class BayesCBFController:
         for k, (gh, h, gamma) in enumerate(rows):
             if Amat.ndim == 3:   # per-rollout A: fold grad_h^T A grad_h into B_k (the kernel takes one shared A)
                 sA = torch.einsum('rn,rnm,rm->r', gh, Amat, gh) / (gh * gh).sum(1).clamp_min(1e-300)
-                Bk_k, A_k = Bk * sA.reshape(-1, 1, 1), torch.eye(3, **f64)
+                Bk_k, A_k = Bk * sA.reshape(-1, 1, 1), self._constants(dev)['eye']
             else:
                 Bk_k, A_k = Bk, Amat
             bfe, e, _, A_socp, bfb, status = ops.cbc1_terms(Mk.contiguous(), Bk_k.contiguous(), A_k.contiguous(),
@@ -193,11 +205,10 @@ class BayesCBFController:
         c[:, 0, 0] = 1.0   # the relaxation enters the CLC only
         return c, d, A, b
 
-    def control(self, X, t):
+    def control(self, X, t, goal=None, dplan=None):
         """u (R,2), relax (R,), status (R,) [0 optimal, 1 infeasible]."""
-        c, d, A, b = self.constraint_terms(X, t)
-        w = torch.tensor([self.cost_weights[2], self.cost_weights[0], self.cost_weights[1]], dtype=torch.float64,
-                         device=X.device)
+        c, d, A, b = self.constraint_terms(X, t, goal, dplan)
+        w = self._constants(X.device)['w']
         y, status, _ = ops.socp_solve(w, c.contiguous(), d.contiguous(), A.contiguous(), b.contiguous(), self.rho)
         return y[:, 1:], y[:, 0], status
 
@@ -288,3 +299,72 @@ class EnsembleLearner:
             return torch.zeros(self.R, 3, 3, **f64), Bk.contiguous(), self.A
         Mk, Bk = self.ens.posterior(self.shift_invariant(X).contiguous())
         return Mk, Bk, self.A
+
+
+class GraphedRollout:
+    """The control step of `rollout` captured once in a CUDA graph and replayed every step: the per-step work is ~150
+    tiny launches (CLF / CBF algebra, cone assembly) around three kernels of ours (posterior, CBC terms, SOCP), i.e.
+    launch-bound — exactly what a graph removes.  The planner's goal / derivative are scalars that change with t: they
+    live in static device buffers refreshed from pinned host memory before each replay.  Semantics identical to
+    `rollout` (an infeasible rollout stops and keeps its state)."""
+
+    def __init__(self, controller, X0, dt, true_L=12.0):
+        self.ctrl, self.dt, self.true_L = controller, float(dt), float(true_L)
+        dev = X0.device
+        self.R = X0.shape[0]
+        self.X = X0.clone()
+        self.alive = torch.ones(self.R, dtype=torch.bool, device=dev)
+        self.goal = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.dplan = torch.zeros(3, dtype=torch.float64, device=dev)
+        self._host = torch.zeros(2, 3, dtype=torch.float64).pin_memory()
+        self.graph = None
+        self.u = self.xdot = self.ok = None
+
+    def _set_plan(self, t):
+        self._host[0] = torch.tensor(self.ctrl.planner.plan(t), dtype=torch.float64)
+        self._host[1] = torch.tensor(self.ctrl.planner.dot_plan(t), dtype=torch.float64)
+        self.goal.copy_(self._host[0], non_blocking=True)
+        self.dplan.copy_(self._host[1], non_blocking=True)
+
+    def _step_body(self):
+        u, relax, status = self.ctrl.control(self.X, 0, self.goal, self.dplan)
+        ok = (status == 0) & self.alive
+        u = torch.where(ok.unsqueeze(1), u, torch.zeros_like(u))
+        UH = torch.cat([torch.ones(self.R, 1, dtype=torch.float64, device=self.X.device), u], dim=1)
+        xdot = torch.einsum('rnp,rp->rn', ackermann_F(self.X, self.true_L), UH)
+        return u, xdot, ok
+
+    def capture(self):
+        self._set_plan(0)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):          # warm-up outside the capture (lazy initialisations, allocator)
+            for _ in range(2):
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.u, self.xdot, self.ok = self._step_body()
+        return self
+
+    def step(self, t, on_step=None):
+        self._set_plan(t)
+        self.graph.replay()
+        if on_step is not None:
+            on_step(t, self.X, self.u, self.xdot, self.ok)
+        # state update outside the graph: the learner may refit between steps, the graph reads self.X in place
+        self.X.copy_(torch.where(self.ok.unsqueeze(1), self.X + self.xdot * self.dt, self.X))
+        self.alive.copy_(self.ok)
+
+    def run(self, steps, on_step=None, record=True):
+        Xs, Us, Fs = [self.X.clone()], [], []
+        for t in range(steps):
+            self.step(t, on_step)
+            if record:
+                Xs.append(self.X.clone())
+                Us.append(self.u.clone())
+                Fs.append(self.ok.clone())
+        out = dict(alive=self.alive.clone())
+        if record:
+            out.update(X=torch.stack(Xs), U=torch.stack(Us), feasible=torch.stack(Fs))
+        return out

@@ -87,3 +87,19 @@ def test_rollout_decisions_identical_cuda_vs_restatement(monkeypatch):
     assert torch.equal(got['feasible'].cpu(), want['feasible'])
     assert (got['X'].cpu() - want['X']).abs().max() < 1e-7
     assert (got['U'].cpu() - want['U']).abs().max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_graphed_rollout_equals_eager_rollout():
+    """The CUDA-graph replay of the control step reproduces the eager rollout bit for bit (same kernels, same order)."""
+    d = load('ref_controller_f64')
+    U, planner, cbfs, ctrl = _setup(d, 'cuda')
+    g = torch.Generator().manual_seed(5)
+    R = 6
+    X0 = (torch.from_numpy(d['x0']).repeat(R, 1) + 0.2 * (torch.rand(R, 3, generator=g, dtype=torch.float64) - 0.5)).cuda()
+    X0[R - 1] = torch.tensor([cbfs[0].center[0], cbfs[0].center[1] + 0.05, -1.5], dtype=torch.float64)
+    eager = U.rollout(ctrl, X0, 40, float(d['dt']), true_L=12.0)
+    graphed = U.GraphedRollout(ctrl, X0, float(d['dt']), true_L=12.0).capture().run(40)
+    assert torch.equal(eager['feasible'], graphed['feasible'])
+    assert torch.equal(eager['X'], graphed['X'])
+    assert torch.equal(eager['U'], graphed['U'])

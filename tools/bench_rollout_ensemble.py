@@ -22,6 +22,7 @@ def main():
     ap.add_argument('--steps', type=int, default=600)
     ap.add_argument('--train-every', type=int, default=200)
     ap.add_argument('--max-train', type=int, default=200)
+    ap.add_argument('--eager', action='store_true', help='no CUDA graph')
     a = ap.parse_args()
     from bayesian_cbf_b200 import unicycle as U
     R, dt, numSteps = a.rollouts, 0.001, 2000
@@ -38,15 +39,31 @@ def main():
           + 0.05 * (torch.rand(R, 3, generator=g, dtype=torch.float64) - 0.5)).cuda()
     U.rollout(ctrl, X0, 5, dt, true_L=1.0)          # warm-up launches
     learner.Xs, learner.Us = [], []
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = U.rollout(ctrl, X0, a.steps, dt, true_L=1.0, on_step=learner.record)
+    if a.eager:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = U.rollout(ctrl, X0, a.steps, dt, true_L=1.0, on_step=learner.record)
+    else:
+        # the graph is captured with the prior-only posterior and RE-captured after every refit (the posterior switches
+        # from the analytic prior to the ensemble kernel, and the factor buffers are re-allocated)
+        gr = U.GraphedRollout(ctrl, X0, dt, true_L=1.0).capture()
+        state = dict(refits=0)
+
+        def on_step(t, X, u, xdot, ok):
+            learner.record(t, X, u, xdot, ok)
+            if learner.refits != state['refits']:
+                state['refits'] = learner.refits
+                gr.capture()
+                gr._set_plan(t)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = gr.run(a.steps, on_step=on_step, record=False)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     alive = int(out['alive'].sum())
     print(json.dumps(dict(metric='controlled rollout steps/sec (posterior + CBC terms + SOCP per step)',
                           value=R * a.steps / wall, unit='rollout-steps/s', rollouts=R, steps=a.steps,
-                          ms_per_step=1e3 * wall / a.steps, refits=learner.refits, alive_at_end=alive,
+                          ms_per_step=1e3 * wall / a.steps, refits=learner.refits, cuda_graph=not a.eager, alive_at_end=alive,
                           n_train_last=getattr(learner.ens, 'N', 0),
                           config=dict(workload='ensemble of %d unicycle learning rollouts (BASELINE configs[4] shape), '
                                                'refit every %d steps, max_train %d' % (R, a.train_every, a.max_train)),
