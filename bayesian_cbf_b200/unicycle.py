@@ -316,15 +316,23 @@ class GraphedRollout:
         self.alive = torch.ones(self.R, dtype=torch.bool, device=dev)
         self.goal = torch.zeros(3, dtype=torch.float64, device=dev)
         self.dplan = torch.zeros(3, dtype=torch.float64, device=dev)
-        self._host = torch.zeros(2, 3, dtype=torch.float64).pin_memory()
+        self._plans = None      # (T, 2, 3) device table of planner.plan / dot_plan, filled by `run`
         self.graph = None
         self.u = self.xdot = self.ok = None
 
+    def _plan_table(self, steps):
+        """planner.plan(t), planner.dot_plan(t) for t < steps as one device table: the per-step refresh of the static
+        goal buffers is then a stream-ordered device copy (a re-used pinned staging buffer would race with the host
+        running ahead of the GPU)."""
+        if self._plans is None or self._plans.shape[0] < steps:
+            tab = torch.tensor([[self.ctrl.planner.plan(t), self.ctrl.planner.dot_plan(t)] for t in range(steps)],
+                               dtype=torch.float64)
+            self._plans = tab.to(self.X.device)
+
     def _set_plan(self, t):
-        self._host[0] = torch.tensor(self.ctrl.planner.plan(t), dtype=torch.float64)
-        self._host[1] = torch.tensor(self.ctrl.planner.dot_plan(t), dtype=torch.float64)
-        self.goal.copy_(self._host[0], non_blocking=True)
-        self.dplan.copy_(self._host[1], non_blocking=True)
+        self._plan_table(t + 1)
+        self.goal.copy_(self._plans[t, 0])
+        self.dplan.copy_(self._plans[t, 1])
 
     def _step_body(self):
         u, relax, status = self.ctrl.control(self.X, 0, self.goal, self.dplan)
@@ -350,20 +358,23 @@ class GraphedRollout:
     def step(self, t, on_step=None):
         self._set_plan(t)
         self.graph.replay()
+        u, xdot, ok = self.u, self.xdot, self.ok      # this replay's outputs (on_step may re-capture the graph)
         if on_step is not None:
-            on_step(t, self.X, self.u, self.xdot, self.ok)
+            on_step(t, self.X, u, xdot, ok)
         # state update outside the graph: the learner may refit between steps, the graph reads self.X in place
-        self.X.copy_(torch.where(self.ok.unsqueeze(1), self.X + self.xdot * self.dt, self.X))
-        self.alive.copy_(self.ok)
+        self.X.copy_(torch.where(ok.unsqueeze(1), self.X + xdot * self.dt, self.X))
+        self.alive.copy_(ok)
+        return u, ok
 
     def run(self, steps, on_step=None, record=True):
+        self._plan_table(steps)
         Xs, Us, Fs = [self.X.clone()], [], []
         for t in range(steps):
-            self.step(t, on_step)
+            u, ok = self.step(t, on_step)
             if record:
                 Xs.append(self.X.clone())
-                Us.append(self.u.clone())
-                Fs.append(self.ok.clone())
+                Us.append(u.clone())
+                Fs.append(ok.clone())
         out = dict(alive=self.alive.clone())
         if record:
             out.update(X=torch.stack(Xs), U=torch.stack(Us), feasible=torch.stack(Fs))
