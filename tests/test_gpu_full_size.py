@@ -1,0 +1,85 @@
+"""Parity at BASELINE.json's full size (N = 16384, the bench workload) through size-independent properties — the oracle
+cannot finish this size in test time, so the CUDA path is checked against identities the exact result must satisfy:
+
+  * factor:   L (L^T z) = (Kb + jitter) z  and  L^-1 (L z) = z  for random probe vectors (a checksum of the N^2 entries);
+  * posterior at the training inputs: the variance of F(x_i)[1;u_i] collapses to the jitter level and the mean
+    reproduces the targets to the same level;
+  * B_k is symmetric positive semi-definite and bounded by the prior; the fold-in form (one column per query,
+    bcbf_posterior_fu) equals the [1;u] contraction of the matrix form (bcbf_posterior_blocks);
+  * query batching: a permuted query set gives the permuted answers.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def fitted():
+    import bench
+    from bayesian_cbf_b200.model import MVGPModel, make_hyper
+    N = 16384
+    X, U, Xdot, hyp, jitter = bench.make_workload(N)
+    model = MVGPModel(0)
+    model.fit(make_hyper(3, 3, hyp['lengthscale'].numpy(), float(hyp['outputscale']), hyp['A'].numpy(), hyp['B'].numpy(),
+                         hyp['C'].numpy()), X.numpy(), U.numpy(), Xdot.numpy(), jitter.numpy(), 1e-5)
+    yield model, X, U, Xdot, hyp, jitter
+    model.close()
+
+
+def test_factor_identities_at_full_size(fitted):
+    from bayesian_cbf_b200 import ops
+    model, X, U, Xdot, hyp, jitter = fitted
+    st = model.state_tensors()
+    L, Linv = st['L'], st['Linv']
+    N = X.shape[0]
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(N, 4, generator=g, dtype=torch.float64).cuda()
+    Ltz = ops.trmm_lower(L, z, trans=True)
+    LLtz = ops.trmm_lower(L, Ltz.contiguous())
+    UH = torch.cat([torch.ones(N, 1, dtype=torch.float64), U], dim=1).cuda()
+    Kb = ops.gram_train(X.cuda(), UH, hyp['B'].cuda(), hyp['lengthscale'].cuda(), float(hyp['outputscale']))
+    Kz = ops.gemm(Kb, z) + 1e-5 * jitter.cuda().unsqueeze(1) * z
+    assert ((LLtz - Kz).abs().max() / Kz.abs().max()).item() < 1e-12        # backward error of the factorisation
+    back = ops.trmm_lower(Linv, ops.trmm_lower(L, z).contiguous())
+    # forward error of the explicit inverse is conditioning-limited: eps * cond(L) ~ 1e-16 * 1e5
+    assert ((back - z).abs().max() / z.abs().max()).item() < 1e-8
+    del Kb
+
+
+def test_posterior_properties_at_full_size(fitted):
+    model, X, U, Xdot, hyp, jitter = fitted
+    prior = float(hyp['outputscale'] * torch.linalg.matrix_norm(hyp['B'], 2))
+    # (1) at training inputs
+    idx = torch.arange(0, X.shape[0], 37)[:400]
+    out = model.query(X[idx].numpy(), U[idx].numpy())
+    UHi = torch.cat([torch.ones(len(idx), 1, dtype=torch.float64), U[idx]], dim=1)
+    ubu = torch.einsum('qa,ab,qb->q', UHi, hyp['B'], UHi).numpy() * float(hyp['outputscale'])
+    assert (out['svar'] > -1e-9 * prior).all()
+    assert (out['svar'] < 1e-4 * ubu + 1e-9 * prior).all()                   # collapsed to the 1e-5 jitter level
+    assert np.abs(out['mean'] - Xdot[idx].numpy()).max() < 5e-2               # targets carry 0.01 noise; jitter-level fit
+    # (2) random queries: symmetry, PSD, bounded by the prior, fold-in == contraction
+    g = torch.Generator().manual_seed(3)
+    Q = 2000
+    Xq = (4 * torch.rand(Q, 3, generator=g, dtype=torch.float64) - 2)
+    Uq = (2 * torch.rand(Q, 2, generator=g, dtype=torch.float64) - 1)
+    out = model.query(Xq.numpy(), Uq.numpy())
+    Bk = torch.from_numpy(out['Bk'])
+    assert (Bk - Bk.transpose(1, 2)).abs().max().item() == 0.0
+    ev = torch.linalg.eigvalsh(Bk)
+    assert ev.min().item() > -1e-9 * prior
+    assert ev.max().item() < prior * (1 + 1e-9)
+    UHq = torch.cat([torch.ones(Q, 1, dtype=torch.float64), Uq], dim=1)
+    svar_c = torch.einsum('qa,qab,qb->q', UHq, Bk, UHq).numpy()
+    assert np.abs(out['svar'] - svar_c).max() < 1e-12 * prior * 9
+    from bayesian_cbf_b200 import ops
+    st = model.state_tensors()
+    Ks = ops.cross_gram(st['X'], Xq.cuda(), hyp['lengthscale'].cuda(), float(hyp['outputscale']), Npad=st['Linv'].shape[0])
+    sv_fold = ops.posterior_fu_var(st['Linv'], Ks, st['G'], hyp['B'].cuda(), UHq.cuda(), float(hyp['outputscale']), 3, 3)
+    assert np.abs(sv_fold.cpu().numpy() - out['svar']).max() < 1e-10 * prior
+    # (3) permutation equivariance through the batching loop
+    perm = torch.randperm(Q, generator=g)
+    outp = model.query(Xq[perm].numpy(), Uq[perm].numpy(), want=('mean', 'svar'))
+    assert np.abs(outp['svar'] - out['svar'][perm.numpy()]).max() < 1e-12 * prior
+    assert np.abs(outp['mean'] - out['mean'][perm.numpy()]).max() < 1e-11 * max(1.0, np.abs(out['mean']).max())
