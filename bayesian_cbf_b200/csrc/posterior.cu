@@ -21,9 +21,8 @@
 
 namespace bcbf {
 
-constexpr int kPBK = 32;                        // k extent of one pipeline stage
-constexpr int kPA_Stride = kPBK + 4;            // A tile row stride in doubles (== 4 mod 16: conflict-free fragments)
-constexpr int kPA_Elems = 128 * kPA_Stride;     // 4608
+// k extent of one pipeline stage is PostCfg::BK (32 or 64); A tile row stride BK + 4 doubles (== 4 mod 16: conflict-free
+// fragment loads)
 constexpr int kPMmaWarps = 8;                   // consumer warps: 2 (rows) x 4 (query groups), 64 x (P*H*8) each
 constexpr int kPProdWarps = 4;                  // producer warps, one per SM sub-partition (warp id % 4): each streams a
                                                 // quarter of the L^-1 / K* tiles with cp.async so that no sub-partition's
@@ -40,12 +39,16 @@ struct PostCfg {
   static constexpr int QW = 8 * H;                   // queries per warp column
   static constexpr int TQ = 4 * QW;                  // queries per CTA
   static constexpr int NF = P * H;                   // n-fragments per warp
+  // 32-query tiles (p = 3, 4) can afford 64-deep stages (2 x 88 KB): half as many stage hand-overs per flop
+  static constexpr int BK = (TQ <= 32) ? 64 : 32;
+  static constexpr int AStride = BK + 4;
+  static constexpr int AElems = 128 * AStride;
   static constexpr int KStride = TQ + 4;             // == 4 (mod 16): conflict-free fragment reads
-  static constexpr int KElems = kPBK * KStride;
-  static constexpr int GElems = kPBK * 4;            // packed G rows of the stage (32 * p doubles, p <= 4)
+  static constexpr int KElems = BK * KStride;
+  static constexpr int GElems = BK * 4;              // packed G rows of the stage (BK * p doubles, p <= 4)
   static constexpr int NPair = P * (P + 1) / 2;
-  static constexpr int StageElems = kPA_Elems + KElems + GElems;
-  static constexpr int Stages = (TQ <= 32) ? 4 : 3;
+  static constexpr int StageElems = AElems + KElems + GElems;
+  static constexpr int Stages = (TQ <= 32) ? 2 : 3;
   static constexpr int SmemBytes = (Stages * StageElems + 2 * TQ * NPair) * (int)sizeof(double) + 64;
   static_assert(TQ % 16 == 0, "tile width must keep the padded stride at 4 mod 16");
   static_assert(SmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -90,7 +93,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 template <class Cfg>
 __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
   constexpr int P = Cfg::P, QW = Cfg::QW, TQ = Cfg::TQ, H = Cfg::H, NF = Cfg::NF, KS = Cfg::KStride;
-  constexpr int NPair = Cfg::NPair, S = Cfg::Stages;
+  constexpr int NPair = Cfg::NPair, S = Cfg::Stages, BK = Cfg::BK, AS = Cfg::AStride;
   extern __shared__ __align__(16) double smem[];
   double* Ssm = smem + S * Cfg::StageElems;  // [2][TQ][NPair]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(Ssm + 2 * TQ * NPair);
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
   const int q0 = blockIdx.x * TQ;
   const int nb = a.Npad / kBlk;
   const int split = blockIdx.y, nsplit = a.nsplit;
-  constexpr int kStagesPerBlk = kBlk / kPBK;  // 4
+  constexpr int kStagesPerBlk = kBlk / BK;
 
   const long long tk0 = a.dbg ? clock64() : 0;
   for (int i = tid; i < 2 * TQ * NPair; i += kPThreads) Ssm[i] = 0.0;
@@ -114,11 +117,11 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
 
   // iteration space: row blocks I = split, split+nsplit, ... ; stages kt in [0, (I+1)*4)
   auto stA = [&](int s) { return smem + s * Cfg::StageElems; };
-  auto stK = [&](int s) { return smem + s * Cfg::StageElems + kPA_Elems; };
-  auto stG = [&](int s) { return smem + s * Cfg::StageElems + kPA_Elems + Cfg::KElems; };
+  auto stK = [&](int s) { return smem + s * Cfg::StageElems + Cfg::AElems; };
+  auto stG = [&](int s) { return smem + s * Cfg::StageElems + Cfg::AElems + Cfg::KElems; };
 
   if (warp >= kPMmaWarps) {
-    // ================= producers: L^-1[I rows, k..k+32) -> As[128][36]; K*[k..k+32, q0..q0+TQ) -> Ks[32][TQ+4];
+    // ================= producers: L^-1[I rows, k..k+BK) -> As[128][BK+4]; K*[k..k+BK, q0..q0+TQ) -> Ks[BK][TQ+4];
     //                   G[k..k+32, :] -> Gs (packed).  16-byte cp.async (LDGSTS) only; completion of a lane's copies
     //                   arrives on full[s] (cp.async.mbarrier.arrive).  Measured alternative: one 256-byte
     //                   cp.async.bulk (TMA unit, UBLKCP) per tile row — 161 small bulk copies per stage made the producer
@@ -140,20 +143,22 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
           tp0 = clock64();
         }
         {
-          // this warp's quarter of the A tile: rows [pw*32, pw*32+32) x 16 chunks of 16 B; lane -> (row = it*2 + lane/16)
-          double* s = stA(slot) + (pw * (kBlk / kPProdWarps)) * kPA_Stride;
-          const double* g = gI + kt * kPBK + (long long)(pw * (kBlk / kPProdWarps) + (lane >> 4)) * a.ld + (lane & 15) * 2;
-          double* sd = s + (lane >> 4) * kPA_Stride + (lane & 15) * 2;
+          // this warp's quarter of the A tile: rows [pw*32, pw*32+32) x BK/2 chunks of 16 B;
+          // lane -> (row = it * RPI + lane / CPRA, chunk = lane % CPRA)
+          constexpr int CPRA = BK / 2, RPI = 32 / CPRA, RW = kBlk / kPProdWarps;
+          double* s = stA(slot) + (pw * RW) * AS;
+          const double* g = gI + kt * BK + (long long)(pw * RW + (lane / CPRA)) * a.ld + (lane % CPRA) * 2;
+          double* sd = s + (lane / CPRA) * AS + (lane % CPRA) * 2;
 #pragma unroll 8
-          for (int it = 0; it < kBlk / kPProdWarps / 2; ++it)
-            cp_async16(sd + it * 2 * kPA_Stride, g + (long long)it * 2 * a.ld, true);
+          for (int it = 0; it < RW / RPI; ++it)
+            cp_async16(sd + it * RPI * AS, g + (long long)it * RPI * a.ld, true);
         }
         {
           // this warp's quarter of the K* tile: k rows [pw*8, pw*8+8)
-          constexpr int KR = kPBK / kPProdWarps;  // 8
+          constexpr int KR = BK / kPProdWarps;
           constexpr int CPR = TQ / 2;             // 16-byte chunks per k row
           double* s = stK(slot) + pw * KR * KS;
-          const double* g = gK0 + (long long)(kt * kPBK + pw * KR) * a.ldks;
+          const double* g = gK0 + (long long)(kt * BK + pw * KR) * a.ldks;
 #pragma unroll 4
           for (int it = 0; it < KR * CPR / 32; ++it) {
             const int ch = it * 32 + lane, k = ch / CPR, c2 = (ch % CPR) * 2;
@@ -162,8 +167,8 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
         }
         if (Cfg::GMUL && pw == kPProdWarps - 1) {
           double* s = stG(slot);
-          const double* g = a.G + (long long)kt * kPBK * P;
-          for (int ch = lane; ch < kPBK * P / 2; ch += 32) cp_async16(s + ch * 2, g + ch * 2, true);
+          const double* g = a.G + (long long)kt * BK * P;
+          for (int ch = lane; ch < BK * P / 2; ch += 32) cp_async16(s + ch * 2, g + ch * 2, true);
         }
         mbar_arrive_cp_async(full + slot);
         if (a.dbg && lane == 0 && pw == 0) atomicAdd(a.dbg + 5, (unsigned long long)(clock64() - tp0));  // cycles to issue a stage
@@ -198,14 +203,14 @@ __global__ void __launch_bounds__(kPThreads, 1) post_var_kernel(PostArgs a) {
         } else {
           mbar_wait(full + slot, phase);
         }
-        const double* As = stA(slot) + (wm * 64 + lr) * kPA_Stride + lk;
+        const double* As = stA(slot) + (wm * 64 + lr) * AS + lk;
         const double* Ks = stK(slot) + lk * KS + wn * QW + lr;
         const double* Gs = stG(slot) + lk * P;
 #pragma unroll
-        for (int k4 = 0; k4 < kPBK / 4; ++k4) {
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
           double af[8], kq[H], bf[NF];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) af[i] = As[i * 8 * kPA_Stride + k4 * 4];
+          for (int i = 0; i < 8; ++i) af[i] = As[i * 8 * AS + k4 * 4];
 #pragma unroll
           for (int h = 0; h < H; ++h) kq[h] = Ks[k4 * 4 * KS + h * 8];
           if (Cfg::GMUL) {
