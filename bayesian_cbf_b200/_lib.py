@@ -72,6 +72,10 @@ _SIGNATURES = {
                                         _P]),
     'bcbf_ens_prep': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     'bcbf_ens_w': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    'bcbf_ens_gram_backward': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,
+                                       c_longlong, _P, _P]),
+    'bcbf_gemm_batched': (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _P, c_int, c_longlong, _P, c_int, c_longlong,
+                                  c_double, _P, c_int, c_longlong, c_int, _P]),
     'bcbf_ens_transpose': (c_int, [_P, _P, c_int, c_int, _P]),
     'bcbf_ens_posterior': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     'bcbf_socp_solve': (c_int, [c_int, c_int, c_int, c_int, c_double, _P, c_int, _P, _P, _P, _P, _P, c_double, _P, _P, _P, _P]),

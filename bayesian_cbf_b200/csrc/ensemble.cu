@@ -235,6 +235,109 @@ ens_posterior_kernel(const double* __restrict__ LinvT, const double* __restrict_
   }
 }
 
+
+// Batched twin of gram_backward_kernel (gram.cu): per rollout r, sum_ij Gbar_ij dKb_ij/dtheta with
+// Gbar = 1/2 (alphaAi alpha^T - nout Kb^-1); per-tile partials, then a fixed-order sum per rollout (deterministic).
+// Output layout per rollout: [d/d outputscale, d/d lengthscale (kEN), d/dB (kEP x kEP)].
+constexpr int kEGrad = 1 + kEN + kEP * kEP;
+
+__global__ void __launch_bounds__(256)
+ens_gram_backward_kernel(const double* __restrict__ X, const double* __restrict__ UH, const double* __restrict__ ls,
+                         const double* __restrict__ scale, const double* __restrict__ Bm,
+                         const double* __restrict__ Pinv, const double* __restrict__ alphaAi,
+                         const double* __restrict__ alpha, int N, int Npad, int n, int p, int nd,
+                         double* __restrict__ partial) {
+  constexpr int T = 64;
+  __shared__ double xr[T][kEN + 1], xc[T][kEN + 1], ur[T][kEP], uc[T][kEP], gr[T][kEP], ar[T][kEN], ac[T][kEN];
+  __shared__ double il[kEN], Bs[kEP * kEP], red[8][kEGrad];
+  const int r = blockIdx.z, tid = threadIdx.x;
+  const int r0 = blockIdx.y * T, c0 = blockIdx.x * T;
+  X += (long long)r * N * n;
+  UH += (long long)r * N * p;
+  Pinv += (long long)r * Npad * Npad;
+  alphaAi += (long long)r * N * nd;
+  alpha += (long long)r * N * nd;
+  if (tid < n) il[tid] = 1.0 / ls[(long long)r * n + tid];
+  if (tid < p * p) Bs[tid] = Bm[(long long)r * p * p + tid];
+  __syncthreads();
+  for (int idx = tid; idx < T * n; idx += 256) {
+    int i = idx / n, d = idx % n;
+    xr[i][d] = (r0 + i < N) ? X[(long long)(r0 + i) * n + d] * il[d] : 0.0;
+    xc[i][d] = (c0 + i < N) ? X[(long long)(c0 + i) * n + d] * il[d] : 0.0;
+  }
+  for (int idx = tid; idx < T * nd; idx += 256) {
+    int i = idx / nd, d = idx % nd;
+    ar[i][d] = (r0 + i < N) ? alphaAi[(long long)(r0 + i) * nd + d] : 0.0;
+    ac[i][d] = (c0 + i < N) ? alpha[(long long)(c0 + i) * nd + d] : 0.0;
+  }
+  for (int idx = tid; idx < T * p; idx += 256) {
+    int i = idx / p, q = idx % p;
+    double g = 0.0, u = 0.0;
+    if (r0 + i < N) {
+      u = UH[(long long)(r0 + i) * p + q];
+      for (int t = 0; t < p; ++t) g += UH[(long long)(r0 + i) * p + t] * Bs[t * p + q];
+    }
+    ur[i][q] = u;
+    gr[i][q] = g;
+    uc[i][q] = (c0 + i < N) ? UH[(long long)(c0 + i) * p + q] : 0.0;
+  }
+  __syncthreads();
+  const double s = scale[r];
+  double acc[kEGrad];
+#pragma unroll
+  for (int t = 0; t < kEGrad; ++t) acc[t] = 0.0;
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int i = 0; i < 4; ++i) {
+    const int rl = ty * 4 + i, row = r0 + rl;
+    if (row >= N) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int cl = tx * 4 + j, col = c0 + cl;
+      if (col >= N) continue;
+      double d2 = 0.0, dd[kEN];
+      for (int d = 0; d < n; ++d) {
+        double df = xr[rl][d] - xc[cl][d];
+        dd[d] = df * df;
+        d2 += dd[d];
+      }
+      const double e = exp(-0.5 * d2);
+      double S = 0.0;
+      for (int q = 0; q < p; ++q) S = fma(gr[rl][q], uc[cl][q], S);
+      double aa = 0.0;
+      for (int d = 0; d < nd; ++d) aa = fma(ar[rl][d], ac[cl][d], aa);
+      const double gbar = 0.5 * (aa - (double)nd * Pinv[(long long)row * Npad + col]);
+      const double ge = gbar * e;
+      acc[0] += ge * S;
+      const double gk = ge * S * s;
+      for (int d = 0; d < n; ++d) acc[1 + d] += gk * dd[d] * il[d];
+      const double gs = ge * s;
+      for (int a = 0; a < p; ++a)
+        for (int b = 0; b < p; ++b) acc[1 + kEN + a * kEP + b] += gs * ur[rl][a] * uc[cl][b];
+    }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int t = 0; t < kEGrad; ++t) {
+    double v = warp_sum(acc[t]);
+    if (lane == 0) red[warp][t] = v;
+  }
+  __syncthreads();
+  if (tid < kEGrad) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w][tid];
+    const long long blk = ((long long)r * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    partial[blk * kEGrad + tid] = v;
+  }
+}
+
+__global__ void ens_gram_backward_finalize_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+  // grid (kEGrad, R), one warp each
+  const int t = blockIdx.x, r = blockIdx.y, lane = threadIdx.x;
+  double v = 0.0;
+  for (int b = lane; b < nblocks; b += 32) v += partial[((long long)r * nblocks + b) * kEGrad + t];
+  v = warp_sum(v);
+  if (lane == 0) out[(long long)r * kEGrad + t] = v;
+}
+
 // LinvT[r][k][i] = Linv[r][i][k]  (32x32 smem tiles)
 __global__ void ens_transpose_kernel(const double* __restrict__ A, double* __restrict__ At, int Npad) {
   __shared__ double t[32][33];
@@ -304,6 +407,26 @@ extern "C" int bcbf_ens_posterior(const double* Linv, const double* X, const dou
   BCBF_CUDA(cudaFuncSetAttribute(ens_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   ens_posterior_kernel<<<R, kEnsThreads, smem, stream>>>(Linv, X, G, W, lengthscale, outputscale, Bmat, C, xq, N, Npad, n, p,
                                                  Mk, Bk);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_ens_gram_backward(const double* X, const double* UH, const double* lengthscale,
+                                      const double* outputscale, const double* Bmat, const double* Pinv,
+                                      const double* alphaAi, const double* alpha, int R, int N, int Npad, int n, int p,
+                                      int nout, double* partial, long long partial_elems, double* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(X && UH && lengthscale && outputscale && Bmat && Pinv && alphaAi && alpha && partial && out,
+               "bcbf_ens_gram_backward: null pointer");
+  BCBF_REQUIRE(R >= 1 && N >= 1 && Npad >= N && n >= 1 && n <= kEN && p >= 1 && p <= kEP && nout >= 1 && nout <= kEN,
+               "bcbf_ens_gram_backward: R=%d N=%d Npad=%d n=%d p=%d nout=%d", R, N, Npad, n, p, nout);
+  dim3 grid(ceil_div(N, 64), ceil_div(N, 64), R);
+  const long long nblocks = (long long)grid.x * grid.y;
+  BCBF_REQUIRE(partial_elems >= nblocks * R * kEGrad, "bcbf_ens_gram_backward: partial buffer too small");
+  ens_gram_backward_kernel<<<grid, 256, 0, stream>>>(X, UH, lengthscale, outputscale, Bmat, Pinv, alphaAi, alpha, N, Npad,
+                                                     n, p, nout, partial);
+  BCBF_LAUNCH_CHECK();
+  ens_gram_backward_finalize_kernel<<<dim3(kEGrad, R), 32, 0, stream>>>(partial, (int)nblocks, out);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }

@@ -571,9 +571,28 @@ static int trmm_impl(const double* A, int lda, int Npad, int trans, const double
 // General row-major C(M,N) = alpha * op(A) op(B) + beta * C on the DMMA GEMM (host glue for the small-batch API
 // paths: v^T v', kb*^T alpha, Linv^T Linv).  op(A) is M x K: transa = 0 -> A stored (M,K); 1 -> stored (K,M).
 // op(B) is K x N: transb = 0 -> B stored (K,N); 1 -> stored (N,K).
+static int gemm_impl(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda, long long sA,
+                     const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int R,
+                     cudaStream_t stream);
+
 extern "C" int bcbf_gemm(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda,
                          const double* B, int ldb, double beta, double* C, int ldc, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return gemm_impl(transa, transb, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, 1,
+                   static_cast<cudaStream_t>(stream_));
+}
+
+// R independent products with element strides sA / sB / sC between consecutive operands (ensembles).
+extern "C" int bcbf_gemm_batched(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda,
+                                 long long sA, const double* B, int ldb, long long sB, double beta, double* C, int ldc,
+                                 long long sC, int R, void* stream_) {
+  BCBF_REQUIRE(R >= 1 && sA % 2 == 0 && sB % 2 == 0 && sC % 2 == 0, "bcbf_gemm_batched: R=%d / odd batch stride", R);
+  return gemm_impl(transa, transb, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, R,
+                   static_cast<cudaStream_t>(stream_));
+}
+
+static int gemm_impl(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda, long long sA,
+                     const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int R,
+                     cudaStream_t stream) {
   BCBF_REQUIRE(A && B && C, "bcbf_gemm: null pointer");
   BCBF_REQUIRE(M > 0 && N > 0 && K > 0 && M % 2 == 0 && N % 2 == 0 && K % 2 == 0,
                "bcbf_gemm: M=%d N=%d K=%d must be positive and even (pad with zeros)", M, N, K);
@@ -583,9 +602,10 @@ extern "C" int bcbf_gemm(int transa, int transb, int M, int N, int K, double alp
   GemmArgs g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.tri = kTriNone;
-  if (!transa && !transb) BCBF_CUDA((launch_gemm<true, false>(g, 1, stream)));
-  else if (!transa && transb) BCBF_CUDA((launch_gemm<true, true>(g, 1, stream)));
-  else if (transa && !transb) BCBF_CUDA((launch_gemm<false, false>(g, 1, stream)));
-  else BCBF_CUDA((launch_gemm<false, true>(g, 1, stream)));
+  g.sA = sA; g.sB = sB; g.sC = sC;
+  if (!transa && !transb) BCBF_CUDA((launch_gemm<true, false>(g, R, stream)));
+  else if (!transa && transb) BCBF_CUDA((launch_gemm<true, true>(g, R, stream)));
+  else if (transa && !transb) BCBF_CUDA((launch_gemm<false, false>(g, R, stream)));
+  else BCBF_CUDA((launch_gemm<false, true>(g, R, stream)));
   return BCBF_OK;
 }

@@ -135,3 +135,140 @@ class MVGPEnsemble:
         Bs = Bk * (sA / gn).reshape(-1, 1, 1)
         return ops.cbc1_terms(Mk.contiguous(), Bs.contiguous(), eye, grad_h.contiguous(), h.contiguous(), gamma,
                               None if Fbar is None else Fbar.contiguous())
+
+
+# =====================================================================================================================
+# Per-rollout hyper-parameter fits: R log marginal likelihoods + gradients in the same launches
+# =====================================================================================================================
+class _EnsembleLogMarginal(torch.autograd.Function):
+    """log N(vec Xdot_r; vec(UH_r C_r), Kb_r (x) A_r) for r < R (values (R,)) with the closed-form adjoints of mll.py,
+    batched: ens Gram -> batched Cholesky (psd-safe escalation per call) -> batched inverse -> batched Kb^-1 = L^-T L^-1
+    -> batched fused adjoint reduction (bcbf_ens_gram_backward)."""
+
+    @staticmethod
+    def forward(ctx, ls, s, A, B, C, X, UH, Xdot):
+        import math
+        lib = _lib.load()
+        R, N, n = X.shape
+        p = UH.shape[2]
+        dev = X.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        Npad = ops.padded(N)
+        st = torch.cuda.current_stream().cuda_stream
+        ls_d, s_d, B_d = ls.detach().contiguous(), s.detach().contiguous(), B.detach().contiguous()
+        Y = (Xdot - UH @ C.detach()).contiguous()                       # (R,N,n)
+        ones = torch.ones(R, N, **f64)
+        dinv = torch.empty(R, lib.bcbf_dinv_elems(Npad), **f64)
+        info = torch.zeros(R, dtype=torch.int32, device=dev)
+        jitter = 0.0
+        for attempt in range(7):
+            L = torch.empty(R, Npad, Npad, **f64)
+            check(lib.bcbf_ens_gram(_ptr(X), _ptr(UH), _ptr(ls_d), _ptr(s_d), _ptr(B_d), R, N, n, p, _ptr(L), Npad, st))
+            check(lib.bcbf_potrf_batched(_ptr(L), Npad, Npad, N, _ptr(ones) if jitter > 0 else None, jitter, _ptr(dinv),
+                                         _ptr(info), R, st))
+            if int(info.abs().max()) == 0:
+                break
+            if attempt == 6:
+                raise _lib.NotPositiveDefiniteError(-3, "linalg.cholesky: ensemble log marginal: a Gram matrix is not "
+                                                    "positive-definite even with jitter %g" % jitter)
+            jitter = 1e-8 if jitter == 0.0 else jitter * 10
+        Linv = torch.empty_like(L)
+        scratch = torch.empty_like(L)
+        check(lib.bcbf_trtri_batched(_ptr(L), _ptr(dinv), _ptr(Linv), _ptr(scratch), Npad, Npad, R, st))
+        ldy = (n + 1) // 2 * 2
+        Ypad = torch.zeros(R, Npad, ldy, **f64)
+        Ypad[:, :N, :n] = Y
+        z = torch.empty_like(Ypad)
+        al = torch.empty_like(Ypad)
+        check(lib.bcbf_trmm_lower_batched(_ptr(Linv), Npad, Npad, 0, _ptr(Ypad), ldy, ldy, 1.0, 0.0, _ptr(z), ldy, R, st))
+        check(lib.bcbf_trmm_lower_batched(_ptr(Linv), Npad, Npad, 1, _ptr(z), ldy, ldy, 1.0, 0.0, _ptr(al), ldy, R, st))
+        alpha = al[:, :N, :n].contiguous()                               # Kb^-1 Y
+        zz = z[:, :N, :n]
+        YtA = zz.transpose(1, 2) @ zz                                    # Y^T Kb^-1 Y   (R,n,n)
+        A_h = A.detach().cpu()
+        La_h = torch.linalg.cholesky(A_h)                                # n x n glue, on the host
+        Ai = torch.cholesky_inverse(La_h).to(dev)
+        quad = torch.einsum('rij,rji->r', Ai, YtA)
+        logdetK = 2.0 * torch.log(torch.diagonal(L, dim1=1, dim2=2)[:, :N]).sum(1)
+        logdetA = (2.0 * torch.log(torch.diagonal(La_h, dim1=1, dim2=2)).sum(1)).to(dev)
+        value = -0.5 * (quad + n * logdetK + N * logdetA + N * n * math.log(2 * math.pi))
+        # Kb^-1 = L^-T L^-1 for every rollout, then the fused adjoint reduction
+        Pinv = scratch                                                   # reuse
+        sL = Npad * Npad
+        check(lib.bcbf_gemm_batched(1, 0, Npad, Npad, Npad, 1.0, _ptr(Linv), Npad, sL, _ptr(Linv), Npad, sL, 0.0,
+                                    _ptr(Pinv), Npad, sL, R, st))
+        alphaAi = (alpha @ Ai).contiguous()
+        nblk = ((N + 63) // 64) ** 2
+        egrad = 1 + _lib.MAX_N_DIM + _lib.MAX_P_DIM ** 2
+        partial = torch.empty(R * nblk * egrad, **f64)
+        out = torch.empty(R, egrad, **f64)
+        check(lib.bcbf_ens_gram_backward(_ptr(X), _ptr(UH), _ptr(ls_d), _ptr(s_d), _ptr(B_d), _ptr(Pinv), _ptr(alphaAi),
+                                         _ptr(alpha), R, N, Npad, n, p, n, _ptr(partial), partial.numel(), _ptr(out), st))
+        g_s = out[:, 0].clone()
+        g_ls = out[:, 1:1 + n].clone()
+        g_B = out[:, 1 + _lib.MAX_N_DIM:].reshape(R, _lib.MAX_P_DIM, _lib.MAX_P_DIM)[:, :p, :p].clone()
+        g_A = 0.5 * (Ai @ YtA @ Ai - N * Ai)
+        g_C = UH.transpose(1, 2) @ alphaAi
+        ctx.save_for_backward(g_ls, g_s, g_A, g_B, g_C)
+        return value
+
+    @staticmethod
+    def backward(ctx, g):
+        g_ls, g_s, g_A, g_B, g_C = ctx.saved_tensors
+        return (g.unsqueeze(1) * g_ls, g * g_s, g.reshape(-1, 1, 1) * g_A, g.reshape(-1, 1, 1) * g_B,
+                g.reshape(-1, 1, 1) * g_C, None, None, None)
+
+
+def ensemble_log_marginal(lengthscale, outputscale, A, B, C, X, UH, Xdot):
+    """(R,) log marginal likelihoods of R independent MVGPs; differentiable w.r.t. the five hyper-parameter batches."""
+    for t in (lengthscale, outputscale, A, B, C, X, UH, Xdot):
+        if not t.is_cuda:
+            raise RuntimeError("ensemble_log_marginal runs on a CUDA device only (no CPU fallback)")
+    return _EnsembleLogMarginal.apply(lengthscale, outputscale, A, B, C, X.contiguous(), UH.contiguous(), Xdot.contiguous())
+
+
+class EnsembleHyperParameters(torch.nn.Module):
+    """The reference's parameterisation (gpytorch names / constraints), one set per rollout: raw_lengthscale (R,n),
+    raw_outputscale (R,), U/V covar_factor (R,n,rank) / (R,p,rank) and raw_var, mean constants (R,p,n).
+    rank=1 is `ControlAffineRegressorExactRankOne`, the learned-dynamics class of the rollout recipes
+    (unicycle_move_to_pose.py:301)."""
+
+    def __init__(self, R, n, p, rank=1, device='cuda', seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64).to(device)
+        P = torch.nn.Parameter
+        self.raw_lengthscale = P(torch.zeros(R, n, dtype=torch.float64, device=device))
+        self.raw_outputscale = P(torch.zeros(R, dtype=torch.float64, device=device))
+        self.U_factor, self.U_raw_var = P(rn(R, n, rank)), P(rn(R, n))
+        self.V_factor, self.V_raw_var = P(rn(R, p, rank)), P(rn(R, p))
+        self.C = P(torch.zeros(R, p, n, dtype=torch.float64, device=device))
+
+    def constrained(self):
+        sp = torch.nn.functional.softplus
+        A = self.U_factor @ self.U_factor.transpose(1, 2) + torch.diag_embed(sp(self.U_raw_var))
+        B = self.V_factor @ self.V_factor.transpose(1, 2) + torch.diag_embed(sp(self.V_raw_var))
+        return sp(self.raw_lengthscale), sp(self.raw_outputscale), A, B, self.C
+
+
+def fit_ensemble_hyperparameters(hp, X, U, Xdot, training_iter=100, lr=0.1, generator=None):
+    """ControlAffineRegressor._fit_with_warnings (control_affine_model.py:274-335) for R rollouts at once: Adam +
+    MultiStepLR on -(log marginal)/(N n) summed over rollouts (the rollouts share no parameter, so the sum optimises
+    each one exactly as a separate fit would), fresh 1e-6 multiplicative target noise every iteration.  Returns the
+    (R,) final losses."""
+    R, N, n = X.shape
+    UH = torch.cat([torch.ones(R, N, 1, dtype=torch.float64, device=X.device), U], dim=2).contiguous()
+    opt = torch.optim.Adam(hp.parameters(), lr=lr)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=(torch.tensor([0.3, 0.6, 0.8, 0.90]) * training_iter).tolist())
+    loss_r = None
+    for _ in range(training_iter):
+        opt.zero_grad()
+        noise = torch.rand(Xdot.shape, dtype=torch.float64, generator=generator).to(X.device)
+        ls, s, A, B, C = hp.constrained()
+        logp = ensemble_log_marginal(ls, s, A, B, C, X, UH, Xdot * (1 + 1e-6 * noise))
+        loss_r = -logp / (N * n)
+        assert not torch.isnan(loss_r).any()
+        loss_r.sum().backward()
+        opt.step()
+        sched.step()
+    return loss_r.detach()

@@ -128,6 +128,11 @@ int bcbf_trmm_lower(const double* A, int lda, int Npad, int trans, const double*
 int bcbf_gemm(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
               int ldb, double beta, double* C, int ldc, void* stream);
 
+/* R independent products, element strides sA / sB / sC between consecutive operands (even). */
+int bcbf_gemm_batched(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda, long long sA,
+                      const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int R,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) Batched posterior of F(x) over many query states (matrix form).
  * Replaces ControlAffineRegressorExact._custom_predict_matrix, per-query diagonal blocks
@@ -194,6 +199,14 @@ int bcbf_ens_prep(const double* UH, const double* Xdot, const double* Bmat, cons
                   int n, int p, int ldy, double* G, double* Y, void* stream);
 /* W[r,i,c*p+j] = alpha[r,i,c] * G[r,i,j]   (R,Npad,n*p) */
 int bcbf_ens_w(const double* alpha, int ldy, const double* G, int R, int Npad, int n, int p, double* W, void* stream);
+/* Batched twin of bcbf_gram_train_backward: out (R, 1 + BCBF_MAX_N_DIM + BCBF_MAX_P_DIM^2) per rollout
+ * [d/d outputscale | d/d lengthscale | d/dB]; Pinv (R,Npad,Npad), alphaAi / alpha (R,N,nout) contiguous;
+ * partial: >= R * ceil(N/64)^2 * (1 + BCBF_MAX_N_DIM + BCBF_MAX_P_DIM^2) doubles.  (Per-rollout hyper-parameter
+ * refits of the learning rollouts, unicycle_move_to_pose.py:359-386.)                                              */
+int bcbf_ens_gram_backward(const double* X, const double* UH, const double* lengthscale, const double* outputscale,
+                           const double* Bmat, const double* Pinv, const double* alphaAi, const double* alpha, int R,
+                           int N, int Npad, int n, int p, int nout, double* partial, long long partial_elems,
+                           double* out, void* stream);
 /* At[r] = A[r]^T for R square (Npad,Npad) matrices (Npad multiple of 32; out of place).                          */
 int bcbf_ens_transpose(const double* A, double* At, int Npad, int R, void* stream);
 /* xq (R,n): one query state per rollout -> Mk (R,n,p), Bk (R,p,p) (no output jitter).  LinvT is the TRANSPOSED

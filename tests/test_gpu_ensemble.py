@@ -62,3 +62,43 @@ def test_ensemble_cbc_terms_match_single_model_path():
         assert abs(e[r].item() - e_o.item()) < 1e-12
         assert (A_socp[r].cpu() - A_o).abs().max() < 1e-10
         assert (bfb[r].cpu() - bfb_o).abs().max() < 1e-10
+
+
+def test_ensemble_log_marginal_matches_single_model_path():
+    """Batched value + gradients of R log marginals == R calls of the single-model fused op (mll.py), which is itself
+    checked against torch autograd of the dense density (tests/test_fit_mll.py)."""
+    from bayesian_cbf_b200.ensemble import ensemble_log_marginal
+    from bayesian_cbf_b200.mll import mvgp_log_marginal
+    R, N, n, m = 4, 70, 3, 2
+    X, U, Xdot, ls, s, A, B, C, _, _ = _ensemble(31, R, N, n, m)
+    ls = 0.5 * ls            # short lengthscales keep the jitter-free Gram matrices well conditioned
+    UH = torch.cat([torch.ones(R, N, 1, dtype=torch.float64), U], dim=2)
+    leaves = [t.clone().cuda().requires_grad_(True) for t in (ls, s, A, B, C)]
+    val = ensemble_log_marginal(*leaves, X.cuda(), UH.cuda(), Xdot.cuda())
+    w = torch.linspace(0.5, 1.5, R, dtype=torch.float64).cuda()
+    grads = torch.autograd.grad((w * val).sum(), leaves)
+    for r in range(R):
+        lv = [t[r].clone().cuda().requires_grad_(True) for t in (ls, s, A, B, C)]
+        v1 = mvgp_log_marginal(*lv, X[r].cuda(), UH[r].cuda(), Xdot[r].cuda())
+        g1 = torch.autograd.grad(v1, lv)
+        assert abs(val[r].item() - v1.item()) < 1e-10 * abs(v1.item())
+        for gb, gs in zip(grads, g1):
+            ref = w[r] * gs
+            assert (gb[r] - ref).abs().max() < 1e-9 * max(1.0, ref.abs().max().item())
+
+
+def test_ensemble_hyperparameter_fit_lowers_every_loss():
+    from bayesian_cbf_b200.ensemble import EnsembleHyperParameters, fit_ensemble_hyperparameters
+    R, N, n, m = 6, 60, 3, 2
+    X, U, _, _, _, _, _, _, _, _ = _ensemble(37, R, N, n, m)
+    UH = torch.cat([torch.ones(R, N, 1, dtype=torch.float64), U], dim=2)
+    Ftrue = torch.zeros(R, N, 3, 3, dtype=torch.float64)
+    Ftrue[..., 0, 1] = X[..., 2].cos()
+    Ftrue[..., 1, 1] = X[..., 2].sin()
+    Ftrue[..., 2, 2] = 0.5
+    Xdot = torch.einsum('rinp,rip->rin', Ftrue, UH)
+    hp = EnsembleHyperParameters(R, n, m + 1, rank=1, seed=1)
+    g = torch.Generator().manual_seed(2)
+    first = fit_ensemble_hyperparameters(hp, X.cuda(), U.cuda(), Xdot.cuda(), training_iter=1, lr=1e-9, generator=g)
+    last = fit_ensemble_hyperparameters(hp, X.cuda(), U.cuda(), Xdot.cuda(), training_iter=40, lr=0.05, generator=g)
+    assert (last < first - 0.05).all(), (first, last)
