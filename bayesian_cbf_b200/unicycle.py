@@ -241,11 +241,13 @@ class EnsembleLearner:
     """LearnedShiftInvariantDynamics (reference :295-428) for R rollouts: every rollout records its own (x, u) pairs,
     and every `train_every_n_steps` steps all R per-rollout MVGPs are re-fitted in one batch on the residual
     xdot - F_prior(x)[1;u] over shift-invariant states [0, 0, theta] (at most `max_train` most recent... the reference
-    subsamples at random, :374-384; here a seeded random subset).  Hyper-parameters are held fixed (the reference runs
-    100 Adam steps per refit, :386; batching that across rollouts is future work)."""
+    subsamples at random, :374-384; here a seeded random subset).  With `adam_iters > 0` every refit first runs that
+    many Adam steps on each rollout's own log marginal likelihood (the reference: 100, :386), all rollouts in the
+    same launches (ensemble.fit_ensemble_hyperparameters, rank-one task covariances as in
+    ControlAffineRegressorExactRankOne :301); with 0 the given hyper-parameters are held fixed."""
 
     def __init__(self, R, dt, model_L=12.0, max_train=200, train_every_n_steps=400, lengthscale=(1.0, 1.0, 1.0),
-                 outputscale=1.0, A=None, B=None, seed=0, device='cuda'):
+                 outputscale=1.0, A=None, B=None, seed=0, device='cuda', adam_iters=0, lr=0.1):
         from .ensemble import MVGPEnsemble
         self.R, self.dt, self.model_L = R, float(dt), float(model_L)
         self.max_train, self.every = int(max_train), int(train_every_n_steps)
@@ -261,6 +263,8 @@ class EnsembleLearner:
         self.Xs, self.Us = [], []
         self.gen = torch.Generator().manual_seed(seed)
         self.refits = 0
+        self.adam_iters, self.lr = int(adam_iters), float(lr)
+        self.hp = None
 
     @staticmethod
     def shift_invariant(X):
@@ -287,6 +291,15 @@ class EnsembleLearner:
         if T > self.max_train:
             idx = torch.randperm(T, generator=self.gen)[:self.max_train].to(self.device)
             Xtr, Utr, err = Xtr[:, idx], Utr[:, idx], err[:, idx]
+        if self.adam_iters > 0:
+            from .ensemble import EnsembleHyperParameters, fit_ensemble_hyperparameters
+            if self.hp is None:      # parameters persist across refits, like the reference's learned_dynamics object
+                self.hp = EnsembleHyperParameters(self.R, 3, 3, rank=1, device=self.device)
+            fit_ensemble_hyperparameters(self.hp, Xtr.contiguous(), Utr.contiguous(), err.contiguous(),
+                                         training_iter=self.adam_iters, lr=self.lr, generator=self.gen)
+            with torch.no_grad():
+                ls, s, A, B, C = [t.detach().contiguous() for t in self.hp.constrained()]
+            self.ls, self.s, self.A, self.B, self.C = ls, s, A, B, C
         self.ens.fit(Xtr.contiguous(), Utr.contiguous(), err.contiguous(), self.ls, self.s, self.A, self.B, self.C,
                      jitter=lambda t: torch.rand(self.R, Xtr.shape[1], dtype=torch.float64, generator=self.gen))
         self.fitted = True

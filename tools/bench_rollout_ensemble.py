@@ -3,7 +3,7 @@
 (reference unicycle_move_to_pose.py:1948-1969: true Ackermann L=1, prior L=12 with kernel_diag_A=[1,1,1], learning on,
 2 obstacles, PiecewiseLinearPlanner, dt=0.001), each with its own MVGP refitted every `--train-every` steps on at most
 200 of its own samples.  Per control step and rollout: ensemble posterior (HBM-bound kernel) -> CBC/CLC cone terms ->
-batched SOCP.  Hyper-parameters are fixed.  Reports rollout-steps/s; one JSON line."""
+batched SOCP.  --adam-iters K runs K Adam steps on every rollout's log marginal at each refit (reference: 100).  Reports rollout-steps/s; one JSON line."""
 import argparse
 import json
 import math
@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--train-every', type=int, default=200)
     ap.add_argument('--max-train', type=int, default=200)
     ap.add_argument('--eager', action='store_true', help='no CUDA graph')
+    ap.add_argument('--adam-iters', type=int, default=0, help='Adam steps per refit on every rollout (reference: 100)')
     a = ap.parse_args()
     from bayesian_cbf_b200 import unicycle as U
     R, dt, numSteps = a.rollouts, 0.001, 2000
@@ -31,7 +32,7 @@ def main():
     planner = U.PiecewiseLinearPlanner(x0, xg, numSteps, dt, frac_time_to_reach_goal=0.95)
     cbfs = U.obstacles_at_mid_from_start_and_goal(x0, xg, term_weights=(0.7, 0.3))
     learner = U.EnsembleLearner(R, dt, model_L=12.0, max_train=a.max_train, train_every_n_steps=a.train_every,
-                                lengthscale=(1.0, 1.0, 0.7), outputscale=1.0)
+                                lengthscale=(1.0, 1.0, 0.7), outputscale=1.0, adam_iters=a.adam_iters)
     ctrl = U.BayesCBFController(planner, U.CLFCartesian(Kp=(0.9, 1.5, 0.0)), cbfs, [5.0, 5.0], model_L=12.0,
                                 clf_gamma=10.0, max_risk=0.01, posterior=learner.posterior)
     g = torch.Generator().manual_seed(0)
@@ -63,7 +64,7 @@ def main():
     alive = int(out['alive'].sum())
     print(json.dumps(dict(metric='controlled rollout steps/sec (posterior + CBC terms + SOCP per step)',
                           value=R * a.steps / wall, unit='rollout-steps/s', rollouts=R, steps=a.steps,
-                          ms_per_step=1e3 * wall / a.steps, refits=learner.refits, cuda_graph=not a.eager, alive_at_end=alive,
+                          ms_per_step=1e3 * wall / a.steps, refits=learner.refits, cuda_graph=not a.eager, adam_iters_per_refit=a.adam_iters, alive_at_end=alive,
                           n_train_last=getattr(learner.ens, 'N', 0),
                           config=dict(workload='ensemble of %d unicycle learning rollouts (BASELINE configs[4] shape), '
                                                'refit every %d steps, max_train %d' % (R, a.train_every, a.max_train)),
