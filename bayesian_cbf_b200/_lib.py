@@ -87,6 +87,15 @@ _SIGNATURES = {
     'bcbf_model_state': (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)] + [POINTER(c_void_p)] * 6),
     'bcbf_model_alloc_state': (c_int, [c_void_p, POINTER(Hyper), c_int]),
     'bcbf_model_fit_timing': (c_int, [c_void_p, POINTER(c_double * 5)]),
+    'bcbf_oz_factor_bytes': (c_longlong, [c_int]),
+    'bcbf_oz_max_npad': (c_int, []),
+    'bcbf_oz_split_factor': (c_int, [_P, c_int, c_int, _P, _P, _P]),
+    'bcbf_posterior_var_i8': (c_int, [_P, _P, c_int, _P, c_int, _P, _P, c_double, c_int, c_int, _P, _P]),
+    'bcbf_oz_profile_enable': (c_int, [c_int]),
+    'bcbf_oz_profile_read': (c_int, [POINTER(c_double), POINTER(c_int)]),
+    'bcbf_model_set_var_path': (c_int, [c_void_p, c_int]),
+    'bcbf_model_get_var_path': (c_int, [c_void_p]),
+    'bcbf_model_oz_split_ms': (c_double, [c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

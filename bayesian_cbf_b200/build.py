@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'lib', 'libbcbf.so')
-SOURCES = ['api.cu', 'factor.cu', 'gram.cu', 'posterior.cu', 'ensemble.cu', 'socp.cu']
+SOURCES = ['api.cu', 'factor.cu', 'gram.cu', 'posterior.cu', 'ensemble.cu', 'socp.cu', 'ozaki.cu']
 FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
          '-std=c++17', '-diag-suppress', '177']
 

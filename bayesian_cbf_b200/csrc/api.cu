@@ -217,6 +217,13 @@ struct bcbf_model {
          *svar = nullptr;
   size_t cap_Q = 0, cap_K = 0;
   double fit_ms[5] = {0, 0, 0, 0, 0};
+  // int8 tensor-core covariance path (csrc/ozaki.cu): digits of L^-1, built by fit or lazily by the first query
+  int var_path = 0;
+  void* oz_digits = nullptr;
+  double* oz_rowscale = nullptr;
+  size_t cap_oz = 0;
+  bool oz_ready = false;
+  double oz_split_ms = 0.0;
 };
 
 namespace {
@@ -232,12 +239,57 @@ int dev_alloc(T** p, size_t count) {
   return BCBF_OK;
 }
 
-int query_batch(int p) {
-  // queries per device batch: 4 waves of one CTA per SM (148 SMs) with the posterior kernel's TQ
+int query_batch(int p, int var_path) {
+  // queries per device batch: 4 waves of one CTA per SM (148 SMs) with the posterior kernel's TQ; the int8 path
+  // tiles 64 frakB columns (64 / p queries) per CTA and balances best with a multiple of 148 column tiles
+  if (var_path == 1) return 148 * (64 / p) * 6;
   const int tq = (p == 1) ? 96 : (p == 2 ? 64 : 32);
   return 148 * tq * 4;
 }
 }  // namespace
+
+// digits of L^-1 for the int8 path (allocates on first use; `timed` records the device time in oz_split_ms)
+static int ensure_oz_digits(bcbf_model* m, cudaStream_t s, bool timed) {
+  if (m->oz_ready) return BCBF_OK;
+  BCBF_REQUIRE(m->Npad <= bcbf_oz_max_npad(), "int8 covariance path supports Npad <= %d (got %d): use var_path 0",
+               bcbf_oz_max_npad(), m->Npad);
+  const size_t bytes = (size_t)bcbf_oz_factor_bytes(m->Npad);
+  if (bytes > m->cap_oz) {
+    if (m->oz_digits) { BCBF_CUDA(cudaFree(m->oz_digits)); m->oz_digits = nullptr; }
+    if (m->oz_rowscale) { BCBF_CUDA(cudaFree(m->oz_rowscale)); m->oz_rowscale = nullptr; }
+    m->cap_oz = 0;
+    BCBF_CUDA(cudaMalloc(&m->oz_digits, bytes));
+    BCBF_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->oz_rowscale), sizeof(double) * (size_t)m->Npad));
+    m->cap_oz = bytes;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed) {
+    BCBF_CUDA(cudaEventCreate(&e0));
+    BCBF_CUDA(cudaEventCreate(&e1));
+    BCBF_CUDA(cudaEventRecord(e0, s));
+  }
+  int rc = bcbf_oz_split_factor(m->Linv, m->Npad, m->Npad, m->oz_digits, m->oz_rowscale, s);
+  if (rc) return rc;
+  if (timed) {
+    BCBF_CUDA(cudaEventRecord(e1, s));
+    BCBF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    BCBF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    m->oz_split_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  m->oz_ready = true;
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_model_set_var_path(bcbf_model* m, int path) {
+  BCBF_REQUIRE(m && (path == 0 || path == 1), "bcbf_model_set_var_path: path must be 0 (DMMA) or 1 (int8)");
+  m->var_path = path;
+  return BCBF_OK;
+}
+extern "C" int bcbf_model_get_var_path(bcbf_model* m) { return m ? m->var_path : -1; }
+extern "C" double bcbf_model_oz_split_ms(bcbf_model* m) { return m ? m->oz_split_ms : 0.0; }
 
 extern "C" int bcbf_model_create(bcbf_model** out, int device) {
   BCBF_REQUIRE(out, "bcbf_model_create: null out");
@@ -259,6 +311,8 @@ extern "C" void bcbf_model_destroy(bcbf_model* m) {
   for (double** b : bufs)
     if (*b) cudaFree(*b);
   if (m->info) cudaFree(m->info);
+  if (m->oz_digits) cudaFree(m->oz_digits);
+  if (m->oz_rowscale) cudaFree(m->oz_rowscale);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -318,6 +372,7 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
                               int N, const double* jitter, double jitter_scale) {
   BCBF_REQUIRE(m && hyp && X && U && Xdot, "bcbf_model_fit: null pointer");
   m->fitted = false;
+  m->oz_ready = false;
   int rc = bcbf_model_alloc_state(m, hyp, N);
   if (rc) return rc;
   const int n = hyp->n, p = hyp->p, mm = p - 1, Npad = m->Npad, ldy = ld_y(n);
@@ -357,6 +412,8 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
   BCBF_CUDA(cudaEventRecord(ev[3], s));
   rc = finish_fit_from_factor(m);
   if (rc) return rc;
+  m->oz_split_ms = 0.0;
+  if (m->var_path == 1 && (rc = ensure_oz_digits(m, s, true))) return rc;
   BCBF_CUDA(cudaEventRecord(ev[4], s));
   BCBF_CUDA(cudaStreamSynchronize(s));
   float ms;
@@ -388,8 +445,10 @@ extern "C" int bcbf_model_state(bcbf_model* m, int* N, int* Npad, double** L, do
   if (G) *G = m->G;
   if (W) *W = m->W;
   if (Xtrain) *Xtrain = m->X;
-  // a rank that received the state by broadcast marks itself fitted by asking for it
+  // a rank that received the state by broadcast marks itself fitted by asking for it (its digits of L^-1 are
+  // rebuilt by the next query)
   m->fitted = true;
+  m->oz_ready = false;
   return BCBF_OK;
 }
 
@@ -425,9 +484,16 @@ static int query_batch_device(bcbf_model* m, const double* dXq, const double* dU
   double* Bk = dBk ? dBk : m->Bk;
   const bool need_var = dBk || dsvar;
   const bool need_mean = dMk || dmean;
+  const bool i8 = m->var_path == 1;
   rc = bcbf_posterior_blocks(m->Linv, Npad, Npad, m->Kstar, ldks, m->G, m->W, m->hyp_dev + 8, m->hyp_dev + 56,
-                             m->hyp.outputscale, n, p, Qb, need_mean ? Mk : nullptr, need_var ? Bk : nullptr, s);
+                             m->hyp.outputscale, n, p, Qb, need_mean ? Mk : nullptr, (need_var && !i8) ? Bk : nullptr, s);
   if (rc) return rc;
+  if (need_var && i8) {
+    if ((rc = ensure_oz_digits(m, s, false))) return rc;
+    rc = bcbf_posterior_var_i8(m->oz_digits, m->oz_rowscale, Npad, m->Kstar, ldks, m->G, m->hyp_dev + 8,
+                               m->hyp.outputscale, p, Qb, Bk, s);
+    if (rc) return rc;
+  }
   if (dmean || dsvar) {
     build_uh_kernel<<<ceil_div(Qb, 128), 128, 0, s>>>(dUq, Qb, p, m->UHq);
     BCBF_LAUNCH_CHECK();
@@ -444,7 +510,7 @@ extern "C" int bcbf_model_query_device(bcbf_model* m, const double* Xq, const do
   BCBF_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream_);  // exactly the caller's stream (NULL = the default stream)
   const int n = m->hyp.n, p = m->hyp.p, mm = p - 1;
-  const int QB = query_batch(p);
+  const int QB = query_batch(p, m->var_path);
   int rc = ensure_query_capacity(m, Q < QB ? Q : QB);
   if (rc) return rc;
   for (int q0 = 0; q0 < Q; q0 += QB) {
@@ -464,7 +530,7 @@ extern "C" int bcbf_model_query(bcbf_model* m, const double* Xq, const double* U
   BCBF_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = m->stream;
   const int n = m->hyp.n, p = m->hyp.p, mm = p - 1;
-  const int QB = query_batch(p);
+  const int QB = query_batch(p, m->var_path);
   int rc = ensure_query_capacity(m, Q < QB ? Q : QB);
   if (rc) return rc;
   for (int q0 = 0; q0 < Q; q0 += QB) {

@@ -1,0 +1,509 @@
+// FP64-accurate posterior covariance contraction on the int8 tensor cores (tcgen05, sm_100a).
+//
+//   S(x) = frakB(x)^T Kb^-1 frakB(x) = V^T V,   V = L^-1 frakB(x),   frakB[i,(q,t)] = K*[i,q] G[i,t]
+//   (control_affine_model.py:1051-1088 of the reference; the N^2 p flops per query of SURVEY 8d)
+//
+// The FP64 tensor pipe (DMMA) tops out at 37 TFLOP/s, the int8 pipe at 4.5 POP/s.  Both FP64 operands are therefore split
+// error-free into S = 7 signed 8-bit digits in base 256 (an Ozaki-type splitting):
+//     L^-1[i,k]  = 2^ea_i * sum_j a_j[i,k] 256^-(j+1),      frakB[k,c] = 2^eb_c * sum_j b_j[k,c] 256^-(j+1),
+// with one power-of-two scale per ROW of L^-1 and per COLUMN of frakB, so every digit product a_j b_l is an exact integer
+// and every int32 accumulation over k is exact (|sum| <= 7 * 16384 * 2^14 < 2^31).  Products with j + l = d carry the same
+// weight 256^-(d+2) and share one accumulator; the 28 products with d <= 6 are kept (the dropped ones are below 2^-56 of
+// row-scale x column-scale, the same order as the FP64 rounding of a plain DGEMM; tests/test_gpu_ozaki.py).  The FP64
+// value is recombined from the seven int32 accumulators in the epilogue, where the per-query p x p Gram V^T V is formed:
+// V never exists in HBM.
+//
+// Kernel structure (oz_var_kernel): persistent, one CTA per SM, tile = 128 rows of L^-1 x 64 frakB columns (21 queries
+// at p = 3), seven 64-column int32 accumulators = 448 of the 512 TMEM columns.  Warp roles: warp 4 streams the operand
+// digits with bulk asynchronous copies (cp.async.bulk, one 28 KB + one 14 KB copy per 32-deep K step, 5 stages, the
+// digit arrays are stored in HBM exactly in the shared-memory image the MMA wants: un-swizzled K-major core matrices);
+// one thread of warp 5 issues the MMAs: digit slice a of L^-1 against slices 0..6-a of frakB CONCATENATED along N (the
+// B slices are adjacent in shared memory and the accumulators of consecutive diagonals are adjacent in TMEM), 10 MMAs per
+// K step instead of 28, which keeps the shared-memory operand reads under the 128 B/clk limit (measured: 920 cycles per
+// K step against a tensor-pipe floor of 896, tools/microbench/umma_i8_probe.cu); warps 0-3 drain TMEM, recombine in
+// FP64, apply the scales and reduce the Gram over the 128 rows.
+#include "../../include/bcbf.h"
+#include "common.cuh"
+#include "tc5.cuh"
+
+namespace bcbf {
+namespace oz {
+
+using namespace tc5;
+
+constexpr int S = 7;               // digits per operand
+constexpr int TM = 128, TN = 64;   // tile rows (L^-1) x columns (frakB)
+constexpr int KSTEP = 32;          // K extent of one int8 MMA
+constexpr int A_STEP = S * TM * KSTEP;  // 28672 bytes of L^-1 digits per K step
+constexpr int B_STEP = S * TN * KSTEP;  // 14336 bytes of frakB digits per K step
+constexpr int STAGE = A_STEP + B_STEP;
+constexpr int NSTAGE = 5;
+constexpr int kMaxNpad = 18432;    // 7 * Npad * 2^14 < 2^31
+constexpr int kEpiThreads = 128;
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = NSTAGE * STAGE + 128 + TN * 8 + 4 * 160 * 8;
+
+// power-of-two scale 2^e with |x| / 2^e <= 0.498 for all |x| <= mx (balanced base-256 digits span (-0.502, 0.498))
+__device__ __forceinline__ double scale_of(double mx) {
+  if (!(mx > 0.0)) return 1.0;
+  int ex;
+  const double f = frexp(mx, &ex);  // mx = f 2^ex, f in [0.5, 1)
+  int e = ex + 1;
+  if (f * 0.5 >= 0.498) e += 1;
+  return ldexp(1.0, e);
+}
+
+// x (|x| <= 0.498) -> seven signed digits, x ~= sum_j d[j] 256^-(j+1)
+__device__ __forceinline__ void digits_of(double x, int (&d)[S]) {
+  long long I = __double2ll_rn(x * 72057594037927936.0);  // x 2^56
+#pragma unroll
+  for (int j = S - 1; j >= 1; --j) {
+    const int b = static_cast<int>(static_cast<signed char>(I & 0xFF));
+    d[j] = b;
+    I = (I - b) >> 8;
+  }
+  d[0] = static_cast<int>(I < -128 ? -128 : (I > 127 ? 127 : I));
+}
+
+// ---- L^-1 -> digit blobs (once per fit) -------------------------------------------------------------------------
+__global__ void rowscale_kernel(const double* __restrict__ Linv, int ld, int Npad, double* __restrict__ rowscale) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= Npad) return;
+  double mx = 0.0;
+  for (int k = lane; k <= row; k += 32) mx = fmax(mx, fabs(Linv[(long long)row * ld + k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) rowscale[row] = scale_of(mx);
+}
+
+// blob of row block I, K step ks (ks < 4 (I+1)):  [slice 7][row group 16][k chunk 2][row 8][16 bytes]
+__global__ void __launch_bounds__(256) split_factor_kernel(const double* __restrict__ Linv, int ld,
+                                                           const double* __restrict__ rowscale,
+                                                           int8_t* __restrict__ blob) {
+  const int kc = blockIdx.x, I = blockIdx.y;
+  if (kc > I) return;
+  const int r = threadIdx.x % TM, half = threadIdx.x / TM;
+  const long long row = (long long)I * TM + r;
+  const double inv = 1.0 / rowscale[row];
+  int8_t* base = blob + (2LL * I * (I + 1) + 4LL * kc) * A_STEP;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int c16 = half * 4 + c;  // 16-wide k chunk of this 128-wide block column
+    const double* src = Linv + row * ld + (long long)kc * TM + c16 * 16;
+    uint32_t w[S][4];
+#pragma unroll
+    for (int s = 0; s < S; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      int d[S];
+      digits_of(src[k] * inv, d);
+#pragma unroll
+      for (int s = 0; s < S; ++s) w[s][k / 4] |= static_cast<uint32_t>(d[s] & 0xFF) << (8 * (k % 4));
+    }
+    int8_t* dst = base + (long long)(c16 / 2) * A_STEP + (r / 8) * 256 + (c16 % 2) * 128 + (r % 8) * 16;
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      *reinterpret_cast<uint4*>(dst + s * (TM * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+  }
+}
+
+// ---- frakB -> digit blobs (per query batch) -----------------------------------------------------------------------
+// colmax[q*p + t] = max_i |K*[i,q] G[i,t]|  (as the bit pattern of a non-negative double: unsigned order = value order)
+__global__ void colmax_kernel(const double* __restrict__ Kstar, int ldks, const double* __restrict__ G, int Npad, int p,
+                              int Q, int rows_per_block, unsigned long long* __restrict__ colmax) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int i0 = blockIdx.y * rows_per_block;
+  const int i1 = min(Npad, i0 + rows_per_block);
+  double mx[BCBF_MAX_P_DIM] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = i0; i < i1; ++i) {
+    const double k = fabs(Kstar[(long long)i * ldks + q]);
+    for (int t = 0; t < p; ++t) mx[t] = fmax(mx[t], k * fabs(__ldg(G + (long long)i * p + t)));
+  }
+  for (int t = 0; t < p; ++t)
+    atomicMax(colmax + (long long)q * p + t, static_cast<unsigned long long>(__double_as_longlong(mx[t])));
+}
+
+// blob of column tile J, K step ks:  [slice 7][column group 8][k chunk 2][column 8][16 bytes]; column = P (q % QT) + t
+template <int P>
+__global__ void __launch_bounds__(128) split_frakb_kernel(const double* __restrict__ Kstar, int ldks,
+                                                          const double* __restrict__ G, int Npad, int Q, int Qpad,
+                                                          const unsigned long long* __restrict__ colmax,
+                                                          int8_t* __restrict__ blob, double* __restrict__ colscale) {
+  constexpr int QT = TN / P;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Qpad) return;
+  const int i0 = blockIdx.y * 16;
+  const int J = q / QT, qq = q % QT;
+  const bool live = q < Q;
+  double kv[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) kv[k] = live ? Kstar[(long long)(i0 + k) * ldks + q] : 0.0;
+  int8_t* base = blob + ((long long)J * (Npad / KSTEP) + i0 / KSTEP) * B_STEP + ((i0 / 16) % 2) * 128;
+#pragma unroll
+  for (int t = 0; t < P; ++t) {
+    const double sc = live ? scale_of(__longlong_as_double(static_cast<long long>(colmax[(long long)q * P + t]))) : 0.0;
+    const double inv = live ? 1.0 / sc : 0.0;
+    const int c = P * qq + t;
+    if (blockIdx.y == 0) colscale[(long long)J * TN + c] = sc;
+    uint32_t w[S][4];
+#pragma unroll
+    for (int s = 0; s < S; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      int d[S];
+      digits_of(kv[k] * __ldg(G + (long long)(i0 + k) * P + t) * inv, d);
+#pragma unroll
+      for (int s = 0; s < S; ++s) w[s][k / 4] |= static_cast<uint32_t>(d[s] & 0xFF) << (8 * (k % 4));
+    }
+    int8_t* dst = base + (c / 8) * 256 + (c % 8) * 16;
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      *reinterpret_cast<uint4*>(dst + s * (TN * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+  }
+  if (qq == QT - 1) {  // unused trailing columns of the tile (64 - P QT): zero digits, zero scale
+    for (int c = P * QT; c < TN; ++c) {
+      if (blockIdx.y == 0) colscale[(long long)J * TN + c] = 0.0;
+      int8_t* dst = base + (c / 8) * 256 + (c % 8) * 16;
+      for (int s = 0; s < S; ++s) *reinterpret_cast<uint4*>(dst + s * (TN * KSTEP)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// ---- the contraction --------------------------------------------------------------------------------------------------
+struct VarArgs {
+  const int8_t* Ablob;
+  const int8_t* Bblob;
+  const double* rowscale;
+  const double* colscale;
+  double* Spart;  // [nb][Qpad][NP]
+  int nb;         // row blocks of L^-1 (Npad / 128)
+  int nJ;         // column tiles (Qpad / QT)
+  int Qpad;
+  long long total_tiles;
+  unsigned long long* dbg;
+};
+
+// tile order: groups of 4 row blocks (longest K extent first) x all column tiles; 148 consecutive tiles = 4 row blocks x
+// 37 column tiles, so CTAs running side by side share L^-1 digits 37-fold and frakB digits 4-fold through L2.
+__device__ __forceinline__ bool tile_of(const VarArgs& a, long long t, int& I, int& J) {
+  const int per_group = 4 * a.nJ;
+  const int g = static_cast<int>(t / per_group), r = static_cast<int>(t % per_group);
+  J = r >> 2;
+  const int ii = ((r & 3) + static_cast<int>((t >> 2) & 3)) & 3;
+  I = a.nb - 1 - (4 * g + ii);
+  return I >= 0;
+}
+
+__device__ __forceinline__ void issue_kstep(uint32_t tmem, uint32_t a_base, uint32_t b_base, bool first) {
+#pragma unroll
+  for (int a = 0; a < S; ++a) {
+    const uint64_t ad = smem_desc_kmajor(a_base + a * (TM * KSTEP), 128, 256);
+    int b = 0;
+    while (b <= S - 1 - a) {
+      int nb = S - a - b;
+      if (nb > 4) nb = 4;
+      const uint64_t bd = smem_desc_kmajor(b_base + b * (TN * KSTEP), 128, 256);
+      mma_s8(tmem + (a + b) * TN, ad, bd, idesc_s8(TM, TN * nb), (first && a == 0) ? 0u : 1u);
+      b += nb;
+    }
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
+  constexpr int QT = TN / P, NP = P * (P + 1) / 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* tmem_full = empty + NSTAGE;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  double* cs = reinterpret_cast<double*>(smem + NSTAGE * STAGE + 128);
+  double* red = cs + TN;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kEpiThreads);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {  // ===== producer: bulk copies of the digit blobs =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int I, J;
+        if (!tile_of(a, t, I, J)) continue;
+        const int nks = 4 * (I + 1);
+        const int8_t* ap = a.Ablob + 2LL * I * (I + 1) * A_STEP;
+        const int8_t* bp = a.Bblob + (long long)J * (a.nb * 4) * B_STEP;
+        for (int ks = 0; ks < nks; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* dst = smem + stage * STAGE;
+          mbar_arrive_expect_tx(&full[stage], STAGE);
+          bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
+          bulk_g2s(dst + A_STEP, bp + (long long)ks * B_STEP, B_STEP, &full[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      int stage = 0;
+      uint32_t phase = 0, tile_iter = 0;
+      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int I, J;
+        if (!tile_of(a, t, I, J)) continue;
+        const int nks = 4 * (I + 1);
+        mbar_wait(tmem_empty, (tile_iter & 1u) ^ 1u);  // epilogue has drained the accumulators of the previous tile
+        tc_fence_after();
+        for (int ks = 0; ks < nks; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE);
+          issue_kstep(tmem, sa, sa + A_STEP, ks == 0);
+          mma_commit(&empty[stage]);  // frees the stage when these MMAs have read it
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(tmem_full);
+        ++tile_iter;
+      }
+    }
+  } else {  // ===== epilogue warps 0..3: TMEM lanes 32 warp .. 32 warp + 31 =====
+    const int tid = threadIdx.x;
+    uint32_t tile_iter = 0;
+    for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int I, J;
+      if (!tile_of(a, t, I, J)) continue;
+      if (tid < TN) cs[tid] = a.colscale[(long long)J * TN + tid];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tmem_full, tile_iter & 1u);
+      tc_fence_after();
+      double V[TN];
+#pragma unroll
+      for (int c = 0; c < TN; ++c) V[c] = 0.0;
+      const uint32_t tbase = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+      for (int d = S - 1; d >= 0; --d) {
+        const double w = __longlong_as_double((1023LL - 8 * (d + 2)) << 52);  // 256^-(d+2)
+#pragma unroll
+        for (int c4 = 0; c4 < TN / 16; ++c4) {
+          uint32_t r[16];
+          tmem_ld16(tbase + d * TN + c4 * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) V[c4 * 16 + j] = fma(static_cast<double>(static_cast<int>(r[j])), w, V[c4 * 16 + j]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty);  // accumulators are in registers: the next tile's MMAs may start
+      const double rs = a.rowscale[(long long)I * TM + warp * 32 + lane];
+#pragma unroll
+      for (int c = 0; c < TN; ++c) V[c] *= rs * cs[c];
+#pragma unroll
+      for (int q = 0; q < QT; ++q) {
+        int e = 0;
+#pragma unroll
+        for (int x = 0; x < P; ++x)
+#pragma unroll
+          for (int y = x; y < P; ++y) {
+            const double s = warp_sum(V[P * q + x] * V[P * q + y]);
+            if (lane == 0) red[warp * (QT * NP) + q * NP + e] = s;
+            ++e;
+          }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int x = tid; x < QT * NP; x += kEpiThreads) {
+        const double s = (red[x] + red[QT * NP + x]) + (red[2 * QT * NP + x] + red[3 * QT * NP + x]);
+        const int q = x / NP, e = x % NP;
+        a.Spart[((long long)I * a.Qpad + (long long)J * QT + q) * NP + e] = s;
+      }
+      ++tile_iter;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+// Bk[q] = kss B - sum over row blocks of Spart
+__global__ void finalize_kernel(const double* __restrict__ Spart, int Qpad, int nb, int Q, int p,
+                                const double* __restrict__ Bmat, double kss, double* __restrict__ Bk) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int npair = p * (p + 1) / 2;
+  int e = 0;
+  for (int i = 0; i < p; ++i)
+    for (int j = i; j < p; ++j) {
+      double s = 0.0;
+      for (int sp = 0; sp < nb; ++sp) s += Spart[((long long)sp * Qpad + q) * npair + e];
+      const double v = kss * Bmat[i * p + j] - s;
+      Bk[((long long)q * p + i) * p + j] = v;
+      Bk[((long long)q * p + j) * p + i] = v;
+      ++e;
+    }
+}
+
+struct Ws {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+static Ws g_ws[4][64];  // 0: frakB digits, 1: colmax, 2: colscale, 3: Spart
+
+static int workspace(int slot, size_t bytes, void** out) {
+  int dev = 0;
+  BCBF_CUDA(cudaGetDevice(&dev));
+  Ws& w = g_ws[slot][dev & 63];
+  if (w.bytes < bytes) {
+    if (w.ptr) BCBF_CUDA(cudaFree(w.ptr));
+    w.ptr = nullptr;
+    w.bytes = 0;
+    BCBF_CUDA(cudaMalloc(&w.ptr, bytes));
+    w.bytes = bytes;
+  }
+  *out = w.ptr;
+  return BCBF_OK;
+}
+
+struct Prof {
+  bool on = false;
+  cudaEvent_t e0[256], e1[256];
+  int n = 0;
+};
+static Prof g_prof;
+
+template <int P>
+static int run_var(const int8_t* Ablob, const double* rowscale, int Npad, const double* Kstar, int ldks,
+                   const double* G, const double* Bmat, double kss, int Q, double* Bk, cudaStream_t stream) {
+  constexpr int QT = TN / P, NP = P * (P + 1) / 2;
+  const int nb = Npad / TM, nJ = ceil_div(Q, QT), Qpad = nJ * QT;
+  void *bblob, *colmax, *colscale, *spart;
+  int rc;
+  if ((rc = workspace(0, (size_t)nJ * (Npad / KSTEP) * B_STEP, &bblob))) return rc;
+  if ((rc = workspace(1, sizeof(unsigned long long) * (size_t)Qpad * P, &colmax))) return rc;
+  if ((rc = workspace(2, sizeof(double) * (size_t)nJ * TN, &colscale))) return rc;
+  if ((rc = workspace(3, sizeof(double) * (size_t)nb * Qpad * NP, &spart))) return rc;
+  BCBF_CUDA(cudaMemsetAsync(colmax, 0, sizeof(unsigned long long) * (size_t)Qpad * P, stream));
+  const int rows_per_block = 256;
+  colmax_kernel<<<dim3(ceil_div(Q, 128), ceil_div(Npad, rows_per_block)), 128, 0, stream>>>(
+      Kstar, ldks, G, Npad, P, Q, rows_per_block, static_cast<unsigned long long*>(colmax));
+  BCBF_LAUNCH_CHECK();
+  split_frakb_kernel<P><<<dim3(ceil_div(Qpad, 128), Npad / 16), 128, 0, stream>>>(
+      Kstar, ldks, G, Npad, Q, Qpad, static_cast<const unsigned long long*>(colmax), static_cast<int8_t*>(bblob),
+      static_cast<double*>(colscale));
+  BCBF_LAUNCH_CHECK();
+  VarArgs a{};
+  a.Ablob = Ablob;
+  a.Bblob = static_cast<const int8_t*>(bblob);
+  a.rowscale = rowscale;
+  a.colscale = static_cast<const double*>(colscale);
+  a.Spart = static_cast<double*>(spart);
+  a.nb = nb;
+  a.nJ = nJ;
+  a.Qpad = Qpad;
+  a.total_tiles = (long long)ceil_div(nb, 4) * 4 * nJ;
+  int dev = 0, sms = 148;
+  BCBF_CUDA(cudaGetDevice(&dev));
+  BCBF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sms -= sms % 4;  // the tile order rotates row blocks in groups of 4
+  BCBF_CUDA(cudaFuncSetAttribute(oz_var_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const int grid = a.total_tiles < sms ? static_cast<int>(a.total_tiles) : sms;
+  const bool prof = g_prof.on && g_prof.n < 256;
+  if (prof) {
+    BCBF_CUDA(cudaEventCreate(&g_prof.e0[g_prof.n]));
+    BCBF_CUDA(cudaEventCreate(&g_prof.e1[g_prof.n]));
+    BCBF_CUDA(cudaEventRecord(g_prof.e0[g_prof.n], stream));
+  }
+  oz_var_kernel<P><<<grid, kThreads, kSmemBytes, stream>>>(a);
+  BCBF_LAUNCH_CHECK();
+  if (prof) {
+    BCBF_CUDA(cudaEventRecord(g_prof.e1[g_prof.n], stream));
+    ++g_prof.n;
+  }
+  finalize_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(a.Spart, Qpad, nb, Q, P, Bmat, kss, Bk);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+}  // namespace oz
+}  // namespace bcbf
+
+using namespace bcbf;
+
+extern "C" long long bcbf_oz_factor_bytes(int Npad) {
+  if (Npad <= 0 || Npad % oz::TM != 0) return 0;
+  const long long nb = Npad / oz::TM;
+  return 2LL * nb * (nb + 1) * oz::A_STEP;
+}
+
+extern "C" int bcbf_oz_max_npad(void) { return oz::kMaxNpad; }
+
+extern "C" int bcbf_oz_split_factor(const double* Linv, int ld, int Npad, void* digits, double* rowscale,
+                                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(Linv && digits && rowscale, "bcbf_oz_split_factor: null pointer");
+  BCBF_REQUIRE(Npad > 0 && Npad % oz::TM == 0 && ld >= Npad && Npad <= oz::kMaxNpad,
+               "bcbf_oz_split_factor: Npad=%d ld=%d (Npad must be a multiple of 128 and <= %d)", Npad, ld, oz::kMaxNpad);
+  oz::rowscale_kernel<<<ceil_div(Npad, 8), 256, 0, stream>>>(Linv, ld, Npad, rowscale);
+  BCBF_LAUNCH_CHECK();
+  const int nb = Npad / oz::TM;
+  oz::split_factor_kernel<<<dim3(nb, nb), 256, 0, stream>>>(Linv, ld, rowscale, static_cast<int8_t*>(digits));
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_posterior_var_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar,
+                                     int ldks, const double* G, const double* Bmat, double kss, int p, int Q, double* Bk,
+                                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(digits && rowscale && Kstar && G && Bmat && Bk, "bcbf_posterior_var_i8: null pointer");
+  BCBF_REQUIRE(Npad > 0 && Npad % oz::TM == 0 && Npad <= oz::kMaxNpad && Q >= 1 && ldks >= Q,
+               "bcbf_posterior_var_i8: Npad=%d Q=%d ldks=%d", Npad, Q, ldks);
+  const int8_t* A = static_cast<const int8_t*>(digits);
+  switch (p) {
+    case 1: return oz::run_var<1>(A, rowscale, Npad, Kstar, ldks, G, Bmat, kss, Q, Bk, stream);
+    case 2: return oz::run_var<2>(A, rowscale, Npad, Kstar, ldks, G, Bmat, kss, Q, Bk, stream);
+    case 3: return oz::run_var<3>(A, rowscale, Npad, Kstar, ldks, G, Bmat, kss, Q, Bk, stream);
+    case 4: return oz::run_var<4>(A, rowscale, Npad, Kstar, ldks, G, Bmat, kss, Q, Bk, stream);
+    default: break;
+  }
+  set_last_error("bcbf_posterior_var_i8: p=%d unsupported", p);
+  return BCBF_ERR_INVALID;
+}
+
+extern "C" int bcbf_oz_profile_enable(int on) {
+  for (int i = 0; i < oz::g_prof.n; ++i) {
+    cudaEventDestroy(oz::g_prof.e0[i]);
+    cudaEventDestroy(oz::g_prof.e1[i]);
+  }
+  oz::g_prof.n = 0;
+  oz::g_prof.on = on != 0;
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_oz_profile_read(double* total_ms, int* launches) {
+  double tot = 0.0;
+  for (int i = 0; i < oz::g_prof.n; ++i) {
+    BCBF_CUDA(cudaEventSynchronize(oz::g_prof.e1[i]));
+    float ms = 0.f;
+    BCBF_CUDA(cudaEventElapsedTime(&ms, oz::g_prof.e0[i], oz::g_prof.e1[i]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = oz::g_prof.n;
+  return BCBF_OK;
+}

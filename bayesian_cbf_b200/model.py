@@ -79,7 +79,21 @@ class MVGPModel:
     def fit_timing_ms(self):
         ms = (ctypes.c_double * 5)()
         check(self._lib.bcbf_model_fit_timing(self._h, ctypes.byref(ms)))
-        return dict(gram=ms[0], potrf=ms[1], trtri=ms[2], alpha=ms[3], total=ms[4])
+        return dict(gram=ms[0], potrf=ms[1], trtri=ms[2], alpha=ms[3], total=ms[4],
+                    oz_split=self._lib.bcbf_model_oz_split_ms(self._h))
+
+    # ------------------------------------------------------------------ which kernel computes B_k
+    VAR_PATHS = {'dmma': 0, 'int8': 1}
+
+    def set_var_path(self, path):
+        """'dmma': FP64 tensor pipe (post_var_kernel);  'int8': tcgen05 int8 tensor cores with error-free digit
+        splitting (oz_var_kernel), FP64-accurate, Npad <= 18432."""
+        check(self._lib.bcbf_model_set_var_path(self._h, self.VAR_PATHS[path] if isinstance(path, str) else int(path)))
+        return self
+
+    @property
+    def var_path(self):
+        return {v: k for k, v in self.VAR_PATHS.items()}[self._lib.bcbf_model_get_var_path(self._h)]
 
     # ------------------------------------------------------------------ state (multi-GPU broadcast)
     def alloc_state(self, hyper, N):

@@ -171,6 +171,27 @@ def posterior_blocks(Linv, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, 
     return Mk, Bk
 
 
+def oz_split_factor(Linv):
+    """Digits of L^-1 for the int8 tensor-core covariance path (csrc/ozaki.cu): (digits uint8 blob, rowscale (Npad))."""
+    _req(Linv)
+    Npad = Linv.shape[0]
+    lib = _lib.load()
+    digits = torch.empty(lib.bcbf_oz_factor_bytes(Npad), dtype=torch.int8, device=Linv.device)
+    rowscale = torch.empty(Npad, dtype=torch.float64, device=Linv.device)
+    check(lib.bcbf_oz_split_factor(_ptr(Linv), Linv.stride(0), Npad, _ptr(digits), _ptr(rowscale), _stream()))
+    return digits, rowscale
+
+
+def posterior_var_i8(digits, rowscale, Kstar, G, Bmat, kss, p, Q):
+    """B_k (Q,p,p) with the N^2 p contraction on the int8 tensor cores; same result as posterior_blocks' B_k."""
+    _req(rowscale, Kstar, G, Bmat)
+    Npad = rowscale.shape[0]
+    Bk = torch.empty(Q, p, p, dtype=torch.float64, device=Kstar.device)
+    check(_lib.load().bcbf_posterior_var_i8(_ptr(digits), _ptr(rowscale), Npad, _ptr(Kstar), Kstar.stride(0), _ptr(G),
+                                            _ptr(Bmat), float(kss), p, Q, _ptr(Bk), _stream()))
+    return Bk
+
+
 def posterior_fu_var(Linv, Kstar, G, Bmat, UHq, kss, n, p):
     _req(Linv, Kstar, G, Bmat, UHq)
     Npad = Linv.shape[0]

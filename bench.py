@@ -218,7 +218,10 @@ def run_ours(args):
     X, U, Xdot, hyp, jitter = make_workload(N)
     hyper = make_hyper(N_DIM, P_DIM, hyp['lengthscale'].numpy(), float(hyp['outputscale']), hyp['A'].numpy(),
                        hyp['B'].numpy(), hyp['C'].numpy())
-    model = MVGPModel(local_rank)
+    model = MVGPModel(local_rank).set_var_path(args.var_path)
+    i8 = args.var_path == 'int8'
+    prof_enable = lib.bcbf_oz_profile_enable if i8 else lib.bcbf_profile_enable
+    prof_read = lib.bcbf_oz_profile_read if i8 else lib.bcbf_profile_read
 
     # ---- fit (Gram + jittered Cholesky + L^-1 + alpha): rank 0 factorises, NCCL broadcasts the state ----------
     fit = dict()
@@ -260,7 +263,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    lib.bcbf_profile_enable(1)
+    prof_enable(1)
     launches0 = lib.bcbf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -275,8 +278,8 @@ def run_ours(args):
     launches = lib.bcbf_launch_count() - launches0
     import ctypes
     kms, kn = ctypes.c_double(), ctypes.c_int()
-    lib.bcbf_profile_read(ctypes.byref(kms), ctypes.byref(kn))
-    lib.bcbf_profile_enable(0)
+    prof_read(ctypes.byref(kms), ctypes.byref(kn))
+    prof_enable(0)
     clocks = sampler.stop() if rank == 0 else {}
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -376,13 +379,19 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n-train', type=int, default=16384)
-    ap.add_argument('--queries-per-step', type=int, default=18944)
+    ap.add_argument('--queries-per-step', type=int, default=None,
+                    help='default: 18944 (dmma: 148 SMs x 32 x 4) / 18648 (int8: 148 SMs x 21 x 6)')
+    ap.add_argument('--var-path', default='dmma', choices=['dmma', 'int8'],
+                    help='kernel of the N^2 p covariance contraction: FP64 tensor pipe, or int8 tensor cores (tcgen05) with '
+                         'error-free digit splitting')
     ap.add_argument('--e2e-steps', type=int, default=8)
     ap.add_argument('--cpu-sample-queries', type=int, default=2048)
     ap.add_argument('--ref-queries-per-step', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.queries_per_step is None:
+        args.queries_per_step = 18648 if args.var_path == 'int8' else 18944
     if args.impl == 'reference':
         run_reference_arm(args)
     else:

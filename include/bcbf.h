@@ -159,6 +159,23 @@ int bcbf_posterior_fu(const double* Linv, int ld, int Npad, const double* Kstar,
                       const double* alpha, const double* Bmat, const double* C, const double* UHq, double kss,
                       int n, int p, int Q, double* mean, double* svar, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (3b) The same B_k(x) with the N^2 p contraction on the int8 tensor cores (tcgen05), FP64-accurate: both operands are
+ * split error-free into seven signed 8-bit digits (Ozaki-type splitting, csrc/ozaki.cu), all integer arithmetic is exact,
+ * the FP64 value is recombined in the kernel epilogue.  Same inputs and outputs as the B_k half of
+ * bcbf_posterior_blocks (control_affine_model.py:1051-1091); results agree with the DMMA path to FP64 rounding level.
+ *   bcbf_oz_factor_bytes(Npad): size of the digit array of L^-1;  bcbf_oz_max_npad(): largest supported Npad (exact int32
+ *   accumulation);  bcbf_oz_split_factor: Linv (Npad,Npad; ld) -> digits (bcbf_oz_factor_bytes bytes), rowscale (Npad);
+ *   once per fit.  bcbf_posterior_var_i8: Kstar from bcbf_cross_gram (ldks >= Q), G (Npad,p) -> Bk (Q,p,p).           */
+long long bcbf_oz_factor_bytes(int Npad);
+int bcbf_oz_max_npad(void);
+int bcbf_oz_split_factor(const double* Linv, int ld, int Npad, void* digits, double* rowscale, void* stream);
+int bcbf_posterior_var_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar, int ldks,
+                          const double* G, const double* Bmat, double kss, int p, int Q, double* Bk, void* stream);
+/* CUDA-event timing of oz_var_kernel launches (bench.py's roofline leg), like bcbf_profile_enable/read. */
+int bcbf_oz_profile_enable(int on);
+int bcbf_oz_profile_read(double* total_ms, int* launches);
+
 /* Relative-degree-1 control-barrier-condition terms in closed form, replacing the autograd
  * extraction of cbc2_quadratic_terms (cbc2.py:7-23) + convert_cbc_terms_to_socp_terms
  * (unicycle_move_to_pose.py:837-878), batched over Q constraints:
@@ -264,6 +281,12 @@ int bcbf_model_state(bcbf_model* m, int* N, int* Npad, double** L, double** Linv
 int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int N);
 /* Milliseconds spent in the stages of the last bcbf_model_fit (gram, potrf, trtri, alpha, total). */
 int bcbf_model_fit_timing(bcbf_model* m, double out_ms[5]);
+/* Which kernel computes B_k in bcbf_model_query*: 0 = FP64 tensor pipe (DMMA, post_var_kernel), 1 = int8 tensor cores
+ * with error-free digit splitting (oz_var_kernel; needs Npad <= bcbf_oz_max_npad()).  With path 1 the fit also splits
+ * L^-1 into digits (bcbf_model_oz_split_ms: device time of that step in the last fit; it is part of fit "total").  */
+int bcbf_model_set_var_path(bcbf_model* m, int path);
+int bcbf_model_get_var_path(bcbf_model* m);
+double bcbf_model_oz_split_ms(bcbf_model* m);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,88 @@
+"""GPU parity of the int8 tensor-core covariance path (csrc/ozaki.cu: tcgen05 kind::i8, error-free digit splitting) against
+the CPU oracle and against the FP64 DMMA path, through the C ABI.  Integer arithmetic is exact, so the digit arrays are
+checked bit-for-bit against a host reconstruction and B_k to FP64 rounding level (tolerances written at each check)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvgp_oracle as O
+from tests.test_gpu_kernels import _d, _fit_on_gpu, _mk
+
+pytestmark = pytest.mark.gpu
+
+S, TM, TN, KSTEP = 7, 128, 64, 32
+A_STEP = S * TM * KSTEP
+
+
+def _decode_factor_digits(blob, rowscale, Npad):
+    """Host reconstruction of L^-1 from the digit blob: [row block I][K step][slice][row group][k chunk][row][16]."""
+    nb = Npad // TM
+    blob = blob.cpu().numpy().astype(np.int64)
+    out = np.zeros((Npad, Npad))
+    w = 256.0 ** -(np.arange(S) + 1.0)
+    for I in range(nb):
+        for ks in range(4 * (I + 1)):
+            off = (2 * I * (I + 1) + ks) * A_STEP
+            t = blob[off:off + A_STEP].reshape(S, TM // 8, 2, 8, 16)          # slice, row group, k chunk, row, k
+            t = t.transpose(0, 1, 3, 2, 4).reshape(S, TM, KSTEP)
+            out[I * TM:(I + 1) * TM, ks * KSTEP:(ks + 1) * KSTEP] = np.tensordot(w, t.astype(np.float64), axes=1)
+    return out * rowscale.cpu().numpy()[:, None]
+
+
+def test_factor_digits_reconstruct_the_factor():
+    from bayesian_cbf_b200 import ops
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(3, 300, 3, 2, 10)
+    L, Linv, G, alpha, W = _fit_on_gpu(X, U, Xdot, hyp, jit)
+    digits, rowscale = ops.oz_split_factor(Linv)
+    Npad = Linv.shape[0]
+    rs = rowscale.cpu().numpy()
+    assert np.all(np.log2(rs) == np.round(np.log2(rs)))                        # powers of two
+    Lh = Linv.cpu().numpy()
+    assert np.all(np.abs(Lh).max(1) / rs <= 0.498) and np.all(np.abs(Lh).max(1) / rs > 0.124)
+    rec = _decode_factor_digits(digits, rowscale, Npad)
+    # 56 bits below the row scale: |error| <= 2^-57 * rowscale (round to nearest of the last digit)
+    assert np.all(np.abs(rec - Lh) <= 2.0 ** -57 * rs[:, None] * (1 + 1e-12))
+    d = digits.cpu().numpy()
+    assert d.min() >= -128 and d.max() <= 127
+
+
+@pytest.mark.parametrize('N,n,m,Q', [(500, 3, 2, 200), (1000, 2, 1, 333), (260, 3, 3, 50), (150, 2, 0, 40), (700, 3, 2, 21)])
+def test_posterior_var_i8(N, n, m, Q):
+    from bayesian_cbf_b200 import ops
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(7, N, n, m, Q, box=3.0)
+    p = m + 1
+    L, Linv, G, alpha, W = _fit_on_gpu(X, U, Xdot, hyp, jit)
+    Ks = ops.cross_gram(_d(X), _d(Xq), _d(hyp.lengthscale), float(hyp.outputscale))
+    _, Bk_dmma = ops.posterior_blocks(Linv, Ks, G, W, _d(hyp.B), _d(hyp.C.t()), float(hyp.outputscale), n, p, Q,
+                                      want_mean=False)
+    digits, rowscale = ops.oz_split_factor(Linv)
+    Bk = ops.posterior_var_i8(digits, rowscale, Ks, G, _d(hyp.B), float(hyp.outputscale), p, Q)
+    torch.cuda.synchronize()
+    prior = (hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)).item()
+    # same inputs (L^-1, K*, G) through two exact-to-rounding contractions: FP64 rounding level apart
+    d_paths = ((Bk - Bk_dmma).abs().max() / prior).item()
+    assert d_paths < 1e-12, d_paths
+    assert (Bk - Bk.transpose(1, 2)).abs().max().item() == 0.0
+    Lref = O.perturbed_cholesky(hyp, X, O.homogeneous(U), [jit], direct=True)
+    Mk_o, Bk_o, mean_o, svar_o = O.posterior_blocks(hyp, X, U, Xdot, Lref, Xq, Uq, direct=True)
+    d_oracle = ((Bk.cpu() - Bk_o).abs().max() / prior).item()
+    assert d_oracle < 1e-9, d_oracle                                            # north-star tolerance (rel. 1e-9, float64)
+
+
+def test_model_handle_int8_path_matches_dmma_path():
+    from bayesian_cbf_b200.model import MVGPModel, make_hyper
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(11, 900, 3, 2, 5000, box=2.0)
+    h = make_hyper(3, 3, hyp.lengthscale.numpy(), float(hyp.outputscale), hyp.A.numpy(), hyp.B.numpy(), hyp.C.numpy())
+    outs = {}
+    for path in ('dmma', 'int8'):
+        model = MVGPModel(0).set_var_path(path)
+        assert model.var_path == path
+        model.fit(h, X.numpy(), U.numpy(), Xdot.numpy(), jit.numpy(), 1e-5)
+        outs[path] = model.query(Xq.numpy(), Uq.numpy())
+        if path == 'int8':
+            assert model.fit_timing_ms()['oz_split'] > 0.0
+        model.close()
+    prior = (hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)).item()
+    assert np.abs(outs['int8']['Bk'] - outs['dmma']['Bk']).max() / prior < 1e-12
+    assert np.abs(outs['int8']['svar'] - outs['dmma']['svar']).max() / prior < 1e-11
+    assert np.array_equal(outs['int8']['Mk'], outs['dmma']['Mk'])              # the mean path is shared
