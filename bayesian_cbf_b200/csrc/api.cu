@@ -485,15 +485,18 @@ static int query_batch_device(bcbf_model* m, const double* dXq, const double* dU
   const bool need_var = dBk || dsvar;
   const bool need_mean = dMk || dmean;
   const bool i8 = m->var_path == 1;
-  rc = bcbf_posterior_blocks(m->Linv, Npad, Npad, m->Kstar, ldks, m->G, m->W, m->hyp_dev + 8, m->hyp_dev + 56,
-                             m->hyp.outputscale, n, p, Qb, need_mean ? Mk : nullptr, (need_var && !i8) ? Bk : nullptr, s);
-  if (rc) return rc;
-  if (need_var && i8) {
-    if ((rc = ensure_oz_digits(m, s, false))) return rc;
-    rc = bcbf_posterior_var_i8(m->oz_digits, m->oz_rowscale, Npad, m->Kstar, ldks, m->G, m->hyp_dev + 8,
-                               m->hyp.outputscale, p, Qb, Bk, s);
-    if (rc) return rc;
+  if (i8) {
+    if (need_var && (rc = ensure_oz_digits(m, s, false))) return rc;
+    rc = need_var ? bcbf_posterior_blocks_i8(m->oz_digits, m->oz_rowscale, Npad, m->Kstar, ldks, m->G, m->W,
+                                             m->hyp_dev + 8, m->hyp_dev + 56, m->hyp.outputscale, n, p, Qb,
+                                             need_mean ? Mk : nullptr, Bk, s)
+                  : bcbf_posterior_blocks(m->Linv, Npad, Npad, m->Kstar, ldks, m->G, m->W, m->hyp_dev + 8,
+                                          m->hyp_dev + 56, m->hyp.outputscale, n, p, Qb, Mk, nullptr, s);
+  } else {
+    rc = bcbf_posterior_blocks(m->Linv, Npad, Npad, m->Kstar, ldks, m->G, m->W, m->hyp_dev + 8, m->hyp_dev + 56,
+                               m->hyp.outputscale, n, p, Qb, need_mean ? Mk : nullptr, need_var ? Bk : nullptr, s);
   }
+  if (rc) return rc;
   if (dmean || dsvar) {
     build_uh_kernel<<<ceil_div(Qb, 128), 128, 0, s>>>(dUq, Qb, p, m->UHq);
     BCBF_LAUNCH_CHECK();

@@ -109,46 +109,100 @@ __global__ void __launch_bounds__(256) split_factor_kernel(const double* __restr
 
 // ---- frakB -> digit blobs (per query batch) -----------------------------------------------------------------------
 // colmax[q*p + t] = max_i |K*[i,q] G[i,t]|  (as the bit pattern of a non-negative double: unsigned order = value order)
-__global__ void colmax_kernel(const double* __restrict__ Kstar, int ldks, const double* __restrict__ G, int Npad, int p,
-                              int Q, int rows_per_block, unsigned long long* __restrict__ colmax) {
+// and, in the same pass over K*, the partial posterior mean  part[split][q][c] = sum_{i in split} K*[i,q] W[i,c]
+// (M_k = C^T + K*^T W, control_affine_model.py:1079-1088); W may be NULL (covariance only).
+constexpr int kCmRows = 256;
+template <int P, int NCMAX>
+__global__ void __launch_bounds__(128) colmax_mean_kernel(const double* __restrict__ Kstar, int ldks,
+                                                          const double* __restrict__ G, const double* __restrict__ W,
+                                                          int nc, int Npad, int Q, int Qpad,
+                                                          unsigned long long* __restrict__ colmax,
+                                                          double* __restrict__ part) {
+  __shared__ double Gs[kCmRows * P];
+  __shared__ double Ws[64 * NCMAX];
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Q) return;
-  const int i0 = blockIdx.y * rows_per_block;
-  const int i1 = min(Npad, i0 + rows_per_block);
-  double mx[BCBF_MAX_P_DIM] = {0.0, 0.0, 0.0, 0.0};
-  for (int i = i0; i < i1; ++i) {
-    const double k = fabs(Kstar[(long long)i * ldks + q]);
-    for (int t = 0; t < p; ++t) mx[t] = fmax(mx[t], k * fabs(__ldg(G + (long long)i * p + t)));
+  const int i0 = blockIdx.y * kCmRows;
+  const int rows = min(Npad - i0, kCmRows);
+  for (int x = threadIdx.x; x < rows * P; x += blockDim.x) Gs[x] = fabs(G[(long long)i0 * P + x]);
+  double mx[P];
+#pragma unroll
+  for (int t = 0; t < P; ++t) mx[t] = 0.0;
+  double acc[NCMAX];
+#pragma unroll
+  for (int c = 0; c < NCMAX; ++c) acc[c] = 0.0;
+  for (int ib = 0; ib < rows; ib += 64) {
+    const int rb = min(64, rows - ib);
+    __syncthreads();
+    if (W)
+      for (int x = threadIdx.x; x < rb * NCMAX; x += blockDim.x) {
+        const int r = x / NCMAX, c = x % NCMAX;
+        Ws[x] = c < nc ? W[(long long)(i0 + ib + r) * nc + c] : 0.0;
+      }
+    __syncthreads();
+    if (q < Q) {
+      for (int r = 0; r < rb; r += 8) {  // rows is a multiple of 128
+        double kv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kv[u] = Kstar[(long long)(i0 + ib + r + u) * ldks + q];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double ka = fabs(kv[u]);
+#pragma unroll
+          for (int t = 0; t < P; ++t) mx[t] = fmax(mx[t], ka * Gs[(ib + r + u) * P + t]);
+          if (W) {
+#pragma unroll
+            for (int c = 0; c < NCMAX; ++c) acc[c] = fma(kv[u], Ws[(r + u) * NCMAX + c], acc[c]);
+          }
+        }
+      }
+    }
   }
-  for (int t = 0; t < p; ++t)
-    atomicMax(colmax + (long long)q * p + t, static_cast<unsigned long long>(__double_as_longlong(mx[t])));
+  if (q >= Q) return;
+#pragma unroll
+  for (int t = 0; t < P; ++t)
+    atomicMax(colmax + (long long)q * P + t, static_cast<unsigned long long>(__double_as_longlong(mx[t])));
+  if (W) {
+#pragma unroll
+    for (int c = 0; c < NCMAX; ++c)
+      if (c < nc) part[((long long)blockIdx.y * Qpad + q) * nc + c] = acc[c];
+  }
 }
 
-// blob of column tile J, K step ks:  [slice 7][column group 8][k chunk 2][column 8][16 bytes]; column = P (q % QT) + t
+__global__ void mean_finalize_kernel(const double* __restrict__ part, int Qpad, int nsplit, int Q, int nc,
+                                     const double* __restrict__ Ct, double* __restrict__ Mk) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Q * nc) return;
+  const int q = static_cast<int>(idx / nc), c = static_cast<int>(idx % nc);
+  double s = Ct[c];
+  for (int sp = 0; sp < nsplit; ++sp) s += part[((long long)sp * Qpad + q) * nc + c];
+  Mk[idx] = s;
+}
+
+// blob of column tile J, K step ks:  [slice 7][column group 8][k chunk 2][column 8][16 bytes]; column = P (q % QT) + t.
+// One thread per frakB COLUMN and 16 consecutive rows i: eight neighbouring threads store 128 contiguous bytes per slice.
 template <int P>
 __global__ void __launch_bounds__(128) split_frakb_kernel(const double* __restrict__ Kstar, int ldks,
-                                                          const double* __restrict__ G, int Npad, int Q, int Qpad,
+                                                          const double* __restrict__ G, int Npad, int Q, int nJ,
                                                           const unsigned long long* __restrict__ colmax,
                                                           int8_t* __restrict__ blob, double* __restrict__ colscale) {
   constexpr int QT = TN / P;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Qpad) return;
+  const int cg = blockIdx.x * blockDim.x + threadIdx.x;  // global column
+  if (cg >= nJ * TN) return;
   const int i0 = blockIdx.y * 16;
-  const int J = q / QT, qq = q % QT;
-  const bool live = q < Q;
-  double kv[16];
+  const int J = cg / TN, c = cg % TN;
+  const int qq = c / P, t = c % P;
+  const int q = J * QT + qq;
+  const bool live = qq < QT && q < Q;  // trailing columns of a tile (64 - P QT) and queries past Q: zero digits, zero scale
+  const double sc = live ? scale_of(__longlong_as_double(static_cast<long long>(colmax[(long long)q * P + t]))) : 0.0;
+  const double inv = live ? 1.0 / sc : 0.0;
+  if (blockIdx.y == 0) colscale[cg] = sc;
+  uint32_t w[S][4];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) kv[k] = live ? Kstar[(long long)(i0 + k) * ldks + q] : 0.0;
-  int8_t* base = blob + ((long long)J * (Npad / KSTEP) + i0 / KSTEP) * B_STEP + ((i0 / 16) % 2) * 128;
+  for (int s = 0; s < S; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+  if (live) {
+    double kv[16];
 #pragma unroll
-  for (int t = 0; t < P; ++t) {
-    const double sc = live ? scale_of(__longlong_as_double(static_cast<long long>(colmax[(long long)q * P + t]))) : 0.0;
-    const double inv = live ? 1.0 / sc : 0.0;
-    const int c = P * qq + t;
-    if (blockIdx.y == 0) colscale[(long long)J * TN + c] = sc;
-    uint32_t w[S][4];
-#pragma unroll
-    for (int s = 0; s < S; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+    for (int k = 0; k < 16; ++k) kv[k] = Kstar[(long long)(i0 + k) * ldks + q];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       int d[S];
@@ -156,18 +210,12 @@ __global__ void __launch_bounds__(128) split_frakb_kernel(const double* __restri
 #pragma unroll
       for (int s = 0; s < S; ++s) w[s][k / 4] |= static_cast<uint32_t>(d[s] & 0xFF) << (8 * (k % 4));
     }
-    int8_t* dst = base + (c / 8) * 256 + (c % 8) * 16;
+  }
+  int8_t* dst = blob + ((long long)J * (Npad / KSTEP) + i0 / KSTEP) * B_STEP + ((i0 / 16) % 2) * 128 + (c / 8) * 256 +
+                (c % 8) * 16;
 #pragma unroll
-    for (int s = 0; s < S; ++s)
-      *reinterpret_cast<uint4*>(dst + s * (TN * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
-  }
-  if (qq == QT - 1) {  // unused trailing columns of the tile (64 - P QT): zero digits, zero scale
-    for (int c = P * QT; c < TN; ++c) {
-      if (blockIdx.y == 0) colscale[(long long)J * TN + c] = 0.0;
-      int8_t* dst = base + (c / 8) * 256 + (c % 8) * 16;
-      for (int s = 0; s < S; ++s) *reinterpret_cast<uint4*>(dst + s * (TN * KSTEP)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-  }
+  for (int s = 0; s < S; ++s)
+    *reinterpret_cast<uint4*>(dst + s * (TN * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
 }
 
 // ---- the contraction --------------------------------------------------------------------------------------------------
@@ -245,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
     if (lane == 0) {  // ===== producer: bulk copies of the digit blobs =====
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
       for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         int I, J;
         if (!tile_of(a, t, I, J)) continue;
@@ -252,7 +301,13 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
         const int8_t* ap = a.Ablob + 2LL * I * (I + 1) * A_STEP;
         const int8_t* bp = a.Bblob + (long long)J * (a.nb * 4) * B_STEP;
         for (int ks = 0; ks < nks; ++ks) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+          if (a.dbg) {
+            const long long c0 = clock64();
+            mbar_wait(&empty[stage], phase ^ 1u);
+            w_empty += clock64() - c0;
+          } else {
+            mbar_wait(&empty[stage], phase ^ 1u);
+          }
           uint8_t* dst = smem + stage * STAGE;
           mbar_arrive_expect_tx(&full[stage], STAGE);
           bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
@@ -260,19 +315,35 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }
+      if (a.dbg) atomicAdd(a.dbg + 3, static_cast<unsigned long long>(w_empty));
     }
   } else if (warp == 5) {
     if (lane == 0) {  // ===== MMA issuer =====
       int stage = 0;
       uint32_t phase = 0, tile_iter = 0;
+      long long w_full = 0, w_tmem = 0, nstep = 0;
+      const long long t_begin = clock64();
       for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         int I, J;
         if (!tile_of(a, t, I, J)) continue;
         const int nks = 4 * (I + 1);
-        mbar_wait(tmem_empty, (tile_iter & 1u) ^ 1u);  // epilogue has drained the accumulators of the previous tile
+        if (a.dbg) {
+          const long long c0 = clock64();
+          mbar_wait(tmem_empty, (tile_iter & 1u) ^ 1u);
+          w_tmem += clock64() - c0;
+          nstep += nks;
+        } else {
+          mbar_wait(tmem_empty, (tile_iter & 1u) ^ 1u);  // epilogue has drained the accumulators of the previous tile
+        }
         tc_fence_after();
         for (int ks = 0; ks < nks; ++ks) {
-          mbar_wait(&full[stage], phase);
+          if (a.dbg) {
+            const long long c0 = clock64();
+            mbar_wait(&full[stage], phase);
+            w_full += clock64() - c0;
+          } else {
+            mbar_wait(&full[stage], phase);
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE);
           issue_kstep(tmem, sa, sa + A_STEP, ks == 0);
@@ -281,6 +352,12 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
         }
         mma_commit(tmem_full);
         ++tile_iter;
+      }
+      if (a.dbg) {  // [0] issue-thread cycles, [1] of which waiting for operands, [2] for the epilogue, [4] K steps
+        atomicAdd(a.dbg + 0, static_cast<unsigned long long>(clock64() - t_begin));
+        atomicAdd(a.dbg + 1, static_cast<unsigned long long>(w_full));
+        atomicAdd(a.dbg + 2, static_cast<unsigned long long>(w_tmem));
+        atomicAdd(a.dbg + 4, static_cast<unsigned long long>(nstep));
       }
     }
   } else {  // ===== epilogue warps 0..3: TMEM lanes 32 warp .. 32 warp + 31 =====
@@ -362,7 +439,7 @@ struct Ws {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-static Ws g_ws[4][64];  // 0: frakB digits, 1: colmax, 2: colscale, 3: Spart
+static Ws g_ws[5][64];  // 0: frakB digits, 1: colmax, 2: colscale, 3: Spart, 4: mean partials
 
 static int workspace(int slot, size_t bytes, void** out) {
   int dev = 0;
@@ -386,24 +463,42 @@ struct Prof {
 };
 static Prof g_prof;
 
+static unsigned long long* g_dbg = nullptr;
+
 template <int P>
-static int run_var(const int8_t* Ablob, const double* rowscale, int Npad, const double* Kstar, int ldks,
-                   const double* G, const double* Bmat, double kss, int Q, double* Bk, cudaStream_t stream) {
+static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, const double* Kstar, int ldks,
+                      const double* G, const double* W, const double* Bmat, const double* Ct, double kss, int n, int Q,
+                      double* Mk, double* Bk, cudaStream_t stream) {
   constexpr int QT = TN / P, NP = P * (P + 1) / 2;
-  const int nb = Npad / TM, nJ = ceil_div(Q, QT), Qpad = nJ * QT;
-  void *bblob, *colmax, *colscale, *spart;
+  const int nb = Npad / TM, nJ = ceil_div(Q, QT), Qpad = nJ * QT, nc = n * P;
+  const int nsplit = ceil_div(Npad, kCmRows);
+  void *bblob, *colmax, *colscale, *spart, *mpart = nullptr;
   int rc;
-  if ((rc = workspace(0, (size_t)nJ * (Npad / KSTEP) * B_STEP, &bblob))) return rc;
   if ((rc = workspace(1, sizeof(unsigned long long) * (size_t)Qpad * P, &colmax))) return rc;
+  if (Mk && (rc = workspace(4, sizeof(double) * (size_t)nsplit * Qpad * nc, &mpart))) return rc;
+  BCBF_CUDA(cudaMemsetAsync(colmax, 0, sizeof(unsigned long long) * (size_t)Qpad * P, stream));
+  {
+    const dim3 grid(ceil_div(Q, 128), nsplit);
+    unsigned long long* cm = static_cast<unsigned long long*>(colmax);
+    double* mp = static_cast<double*>(mpart);
+    const double* Wm = Mk ? W : nullptr;
+    if (nc <= 4) colmax_mean_kernel<P, 4><<<grid, 128, 0, stream>>>(Kstar, ldks, G, Wm, nc, Npad, Q, Qpad, cm, mp);
+    else if (nc <= 9) colmax_mean_kernel<P, 9><<<grid, 128, 0, stream>>>(Kstar, ldks, G, Wm, nc, Npad, Q, Qpad, cm, mp);
+    else if (nc <= 16) colmax_mean_kernel<P, 16><<<grid, 128, 0, stream>>>(Kstar, ldks, G, Wm, nc, Npad, Q, Qpad, cm, mp);
+    else colmax_mean_kernel<P, 32><<<grid, 128, 0, stream>>>(Kstar, ldks, G, Wm, nc, Npad, Q, Qpad, cm, mp);
+  }
+  BCBF_LAUNCH_CHECK();
+  if (Mk) {
+    mean_finalize_kernel<<<ceil_div((long long)Q * nc, 256), 256, 0, stream>>>(static_cast<const double*>(mpart), Qpad,
+                                                                               nsplit, Q, nc, Ct, Mk);
+    BCBF_LAUNCH_CHECK();
+  }
+  if (!Bk) return BCBF_OK;
+  if ((rc = workspace(0, (size_t)nJ * (Npad / KSTEP) * B_STEP, &bblob))) return rc;
   if ((rc = workspace(2, sizeof(double) * (size_t)nJ * TN, &colscale))) return rc;
   if ((rc = workspace(3, sizeof(double) * (size_t)nb * Qpad * NP, &spart))) return rc;
-  BCBF_CUDA(cudaMemsetAsync(colmax, 0, sizeof(unsigned long long) * (size_t)Qpad * P, stream));
-  const int rows_per_block = 256;
-  colmax_kernel<<<dim3(ceil_div(Q, 128), ceil_div(Npad, rows_per_block)), 128, 0, stream>>>(
-      Kstar, ldks, G, Npad, P, Q, rows_per_block, static_cast<unsigned long long*>(colmax));
-  BCBF_LAUNCH_CHECK();
-  split_frakb_kernel<P><<<dim3(ceil_div(Qpad, 128), Npad / 16), 128, 0, stream>>>(
-      Kstar, ldks, G, Npad, Q, Qpad, static_cast<const unsigned long long*>(colmax), static_cast<int8_t*>(bblob),
+  split_frakb_kernel<P><<<dim3(ceil_div(nJ * TN, 128), Npad / 16), 128, 0, stream>>>(
+      Kstar, ldks, G, Npad, Q, nJ, static_cast<const unsigned long long*>(colmax), static_cast<int8_t*>(bblob),
       static_cast<double*>(colscale));
   BCBF_LAUNCH_CHECK();
   VarArgs a{};
@@ -416,6 +511,7 @@ static int run_var(const int8_t* Ablob, const double* rowscale, int Npad, const 
   a.nJ = nJ;
   a.Qpad = Qpad;
   a.total_tiles = (long long)ceil_div(nb, 4) * 4 * nJ;
+  a.dbg = g_dbg;
   int dev = 0, sms = 148;
   BCBF_CUDA(cudaGetDevice(&dev));
   BCBF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -466,23 +562,51 @@ extern "C" int bcbf_oz_split_factor(const double* Linv, int ld, int Npad, void* 
   return BCBF_OK;
 }
 
-extern "C" int bcbf_posterior_var_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar,
-                                     int ldks, const double* G, const double* Bmat, double kss, int p, int Q, double* Bk,
-                                     void* stream_) {
+extern "C" int bcbf_posterior_blocks_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar,
+                                        int ldks, const double* G, const double* W, const double* Bmat,
+                                        const double* Ct, double kss, int n, int p, int Q, double* Mk, double* Bk,
+                                        void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BCBF_REQUIRE(digits && rowscale && Kstar && G && Bmat && Bk, "bcbf_posterior_var_i8: null pointer");
+  BCBF_REQUIRE(digits && rowscale && Kstar && G && Bmat && (Mk || Bk), "bcbf_posterior_blocks_i8: null pointer");
+  BCBF_REQUIRE(!Mk || (W && Ct), "bcbf_posterior_blocks_i8: Mk requested without W / Ct");
+  BCBF_REQUIRE(n >= 1 && n <= BCBF_MAX_N_DIM, "bcbf_posterior_blocks_i8: n=%d", n);
   BCBF_REQUIRE(Npad > 0 && Npad % oz::TM == 0 && Npad <= oz::kMaxNpad && Q >= 1 && ldks >= Q,
-               "bcbf_posterior_var_i8: Npad=%d Q=%d ldks=%d", Npad, Q, ldks);
+               "bcbf_posterior_blocks_i8: Npad=%d Q=%d ldks=%d", Npad, Q, ldks);
   const int8_t* A = static_cast<const int8_t*>(digits);
   switch (p) {
-    case 1: return oz::run_var<1>(A, rowscale, Npad, Kstar, ldks, G, Bmat, kss, Q, Bk, stream);
-    case 2: return oz::run_var<2>(A, rowscale, Npad, Kstar, ldks, G, Bmat, kss, Q, Bk, stream);
-    case 3: return oz::run_var<3>(A, rowscale, Npad, Kstar, ldks, G, Bmat, kss, Q, Bk, stream);
-    case 4: return oz::run_var<4>(A, rowscale, Npad, Kstar, ldks, G, Bmat, kss, Q, Bk, stream);
+    case 1: return oz::run_blocks<1>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream);
+    case 2: return oz::run_blocks<2>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream);
+    case 3: return oz::run_blocks<3>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream);
+    case 4: return oz::run_blocks<4>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream);
     default: break;
   }
-  set_last_error("bcbf_posterior_var_i8: p=%d unsupported", p);
+  set_last_error("bcbf_posterior_blocks_i8: p=%d unsupported", p);
   return BCBF_ERR_INVALID;
+}
+
+extern "C" int bcbf_posterior_var_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar,
+                                     int ldks, const double* G, const double* Bmat, double kss, int p, int Q, double* Bk,
+                                     void* stream) {
+  BCBF_REQUIRE(Bk, "bcbf_posterior_var_i8: null pointer");
+  return bcbf_posterior_blocks_i8(digits, rowscale, Npad, Kstar, ldks, G, nullptr, Bmat, nullptr, kss, 1, p, Q, nullptr,
+                                  Bk, stream);
+}
+
+// Pipeline counters of oz_var_kernel (development aid; adds clock64 reads while enabled): out[0] cycles of the MMA
+// issue thread summed over CTAs, [1] of which waiting for operand stages, [2] waiting for the epilogue to drain TMEM,
+// [3] producer cycles waiting for a free stage, [4] K steps issued.
+extern "C" int bcbf_oz_debug_counters(int enable, unsigned long long out[8]) {
+  if (out != nullptr && oz::g_dbg != nullptr) {
+    BCBF_CUDA(cudaDeviceSynchronize());
+    BCBF_CUDA(cudaMemcpy(out, oz::g_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  if (enable && oz::g_dbg == nullptr) BCBF_CUDA(cudaMalloc(&oz::g_dbg, 8 * sizeof(unsigned long long)));
+  if (oz::g_dbg != nullptr) BCBF_CUDA(cudaMemset(oz::g_dbg, 0, 8 * sizeof(unsigned long long)));
+  if (!enable && oz::g_dbg != nullptr) {
+    BCBF_CUDA(cudaFree(oz::g_dbg));
+    oz::g_dbg = nullptr;
+  }
+  return BCBF_OK;
 }
 
 extern "C" int bcbf_oz_profile_enable(int on) {

@@ -316,24 +316,49 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (post_var_kernel: N^2 p flops per query) ---------------------
-    flops_per_launch = float(N) * N * P_DIM * QS
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
     kernel_ms = kms.value / max(kn.value, 1)
-    achieved = flops_per_launch / (kernel_ms * 1e-3) * 1e-12
-    peak_live = measure_dgemm_peak(dev)
+    fp64_flops_per_launch = float(N) * N * P_DIM * QS          # N^2 p FP64 flops per query
+    peak_dgemm = measure_dgemm_peak(dev)
+    if i8:
+        # oz_var_kernel runs the contraction on the int8 tensor pipe: 7 x 7 digit products with digit sum <= 6 = 28
+        # int8 GEMMs of the same (triangular) shape, N^2/2 MACs per column each -> 28 N^2 p int8 ops per query
+        ops_per_launch = 28.0 * fp64_flops_per_launch
+        achieved = ops_per_launch / (kernel_ms * 1e-3) * 1e-12
+        peak, peak_source = None, None
+        mp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(mp):
+            try:
+                peak = 2.0 * float(json.load(open(mp))['bf16_tflops_sustained'])
+                peak_source = ('2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense = 2 x bf16 dense on B200; the '
+                               'kernel is timed inside a seconds-long step under the power cap), of measured')
+            except Exception:
+                peak = None
+        if peak is None:
+            peak = 2.0 * 1400.0
+            peak_source = '2 x 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md fallback), of fallback'
+        tname, kname = 'oz_var_ncu_summary.json', 'oz_var_kernel'
+        extra = dict(unit_note='int8 tensor ops (TOP/s)', algorithmic_ops_per_launch=ops_per_launch,
+                     fp64_equivalent_tflops=fp64_flops_per_launch / (kernel_ms * 1e-3) * 1e-12,
+                     cublas_dgemm_tflops_live=peak_dgemm,
+                     tcgen05_int8_issue_peak_tops=4572.0)
+    else:
+        achieved = fp64_flops_per_launch / (kernel_ms * 1e-3) * 1e-12
+        peak = peak_dgemm
+        peak_source = ('cuBLAS DGEMM 8192^3 measured live on this GPU (FP64 tensor pipe; MEASURED_PEAKS.json has no FP64 '
+                       'entry; DMMA instruction peak measured 37.1 TFLOP/s, profiles/r01_fp64_peaks.txt)')
+        tname, kname = 'post_var_ncu_summary.json', 'post_var_kernel'
+        extra = dict(algorithmic_flops_per_launch=fp64_flops_per_launch)
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'post_var_ncu_summary.json')
+    tpath = os.path.join(ROOT, 'profiles', tname)
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
         except Exception:
             traffic = None
-    roofline = dict(bound='tensor', achieved=achieved, peak=peak_live, unit='TFLOP/s', frac=achieved / peak_live,
-                    traffic=traffic, kernel='post_var_kernel', kernel_ms=kernel_ms,
-                    kernel_share_of_step=kms.value / ms,
-                    algorithmic_flops_per_launch=flops_per_launch,
-                    peak_source='cuBLAS DGEMM 8192^3 measured live on this GPU (FP64 tensor pipe; MEASURED_PEAKS.json '
-                                'has no FP64 entry; DMMA instruction peak measured 37.1 TFLOP/s, profiles/r01_fp64_peaks.txt)')
+    roofline = dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
+                    traffic=traffic, kernel=kname, kernel_ms=kernel_ms, kernel_share_of_step=kms.value / ms,
+                    peak_source=peak_source, **extra)
 
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 only, N=1 only --------------------------------------
     cpu = None
@@ -360,6 +385,9 @@ def run_ours(args):
                 config=dict(workload='synthetic unicycle MVGP fit N=%d + batched posterior query, %d queries/step/GPU '
                                      '(BASELINE configs[3]; 53 steps = 1.004M queries)' % (N, QS),
                             n_train=N, n=N_DIM, m=M_DIM, queries_per_step=QS, outputs='M_k(3x3), B_k(3x3), mean(3), svar',
+                            covariance_kernel=('oz_var_kernel: tcgen05 int8 tensor cores, 7x7 error-free digit splitting of '
+                                               'both FP64 operands, FP64 recombination' if i8 else
+                                               'post_var_kernel: FP64 tensor pipe (DMMA)'),
                             parallelism='queries sharded, factor broadcast once (NCCL)' if world > 1 else 'single GPU',
                             l2='inputs larger than L2: L^-1 is %.2f GB (lower triangle), streamed every step' % (4.0 * N * (N + 1) / 1e9)),
                 fit_ms=fit.get('total'), fit_breakdown_ms=fit, fit_wall_s=fit_wall_s, factor_broadcast_ms=bcast_ms,
@@ -381,7 +409,7 @@ def main():
     ap.add_argument('--n-train', type=int, default=16384)
     ap.add_argument('--queries-per-step', type=int, default=None,
                     help='default: 18944 (dmma: 148 SMs x 32 x 4) / 18648 (int8: 148 SMs x 21 x 6)')
-    ap.add_argument('--var-path', default='dmma', choices=['dmma', 'int8'],
+    ap.add_argument('--var-path', default='int8', choices=['dmma', 'int8'],
                     help='kernel of the N^2 p covariance contraction: FP64 tensor pipe, or int8 tensor cores (tcgen05) with '
                          'error-free digit splitting')
     ap.add_argument('--e2e-steps', type=int, default=8)

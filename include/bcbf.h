@@ -172,6 +172,13 @@ int bcbf_oz_max_npad(void);
 int bcbf_oz_split_factor(const double* Linv, int ld, int Npad, void* digits, double* rowscale, void* stream);
 int bcbf_posterior_var_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar, int ldks,
                           const double* G, const double* Bmat, double kss, int p, int Q, double* Bk, void* stream);
+/* M_k and B_k together (either may be NULL): the posterior mean partial sums ride on the pass over K* that finds the
+ * column scales of frakB.  Arguments as bcbf_posterior_blocks.                                                    */
+int bcbf_posterior_blocks_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar, int ldks,
+                             const double* G, const double* W, const double* Bmat, const double* Ct, double kss, int n,
+                             int p, int Q, double* Mk, double* Bk, void* stream);
+/* Development aid: pipeline counters of oz_var_kernel (see csrc/ozaki.cu). */
+int bcbf_oz_debug_counters(int enable, unsigned long long out[8]);
 /* CUDA-event timing of oz_var_kernel launches (bench.py's roofline leg), like bcbf_profile_enable/read. */
 int bcbf_oz_profile_enable(int on);
 int bcbf_oz_profile_read(double* total_ms, int* launches);

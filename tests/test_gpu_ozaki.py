@@ -85,4 +85,6 @@ def test_model_handle_int8_path_matches_dmma_path():
     prior = (hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)).item()
     assert np.abs(outs['int8']['Bk'] - outs['dmma']['Bk']).max() / prior < 1e-12
     assert np.abs(outs['int8']['svar'] - outs['dmma']['svar']).max() / prior < 1e-11
-    assert np.array_equal(outs['int8']['Mk'], outs['dmma']['Mk'])              # the mean path is shared
+    # the mean rides on a different pass over K* (other summation order of a cancelling sum): rounding level of sum |K* W|
+    assert np.abs(outs['int8']['Mk'] - outs['dmma']['Mk']).max() < 1e-8 * np.abs(outs['dmma']['Mk']).max()
+    assert np.abs(outs['int8']['mean'] - outs['dmma']['mean']).max() < 1e-8 * np.abs(outs['dmma']['mean']).max()
