@@ -83,3 +83,36 @@ def test_posterior_properties_at_full_size(fitted):
     outp = model.query(Xq[perm].numpy(), Uq[perm].numpy(), want=('mean', 'svar'))
     assert np.abs(outp['svar'] - out['svar'][perm.numpy()]).max() < 1e-12 * prior
     assert np.abs(outp['mean'] - out['mean'][perm.numpy()]).max() < 1e-11 * max(1.0, np.abs(out['mean']).max())
+
+
+def test_int8_tensor_core_path_at_full_size(fitted):
+    """The int8 (tcgen05, digit-splitting) covariance kernel on the same fitted N=16384 model: it must satisfy the same
+    properties and agree with the FP64 DMMA kernel to rounding level (both contract the same L^-1, K*, G)."""
+    model, X, U, Xdot, hyp, jitter = fitted
+    prior = float(hyp['outputscale'] * torch.linalg.matrix_norm(hyp['B'], 2))
+    g = torch.Generator().manual_seed(5)
+    Q = 2500                                                                   # 120 column tiles, last one partial
+    Xq = (4 * torch.rand(Q, 3, generator=g, dtype=torch.float64) - 2)
+    Uq = (2 * torch.rand(Q, 2, generator=g, dtype=torch.float64) - 1)
+    idx = torch.arange(0, X.shape[0], 41)[:400]
+    Xq[:400], Uq[:400] = X[idx], U[idx]                                        # 400 training inputs among the queries
+    ref = model.query(Xq.numpy(), Uq.numpy())
+    model.set_var_path('int8')
+    try:
+        out = model.query(Xq.numpy(), Uq.numpy())
+        perm = torch.randperm(Q, generator=g)
+        outp = model.query(Xq[perm].numpy(), Uq[perm].numpy(), want=('svar', 'Bk'))
+    finally:
+        model.set_var_path('dmma')
+    assert np.abs(out['Bk'] - ref['Bk']).max() < 1e-11 * prior               # measured 2e-13
+    assert np.abs(out['svar'] - ref['svar']).max() < 1e-11 * prior
+    Bk = torch.from_numpy(out['Bk'])
+    assert (Bk - Bk.transpose(1, 2)).abs().max().item() == 0.0
+    ev = torch.linalg.eigvalsh(Bk)
+    assert ev.min().item() > -1e-9 * prior and ev.max().item() < prior * (1 + 1e-9)
+    UHi = torch.cat([torch.ones(400, 1, dtype=torch.float64), U[idx]], dim=1)
+    ubu = torch.einsum('qa,ab,qb->q', UHi, hyp['B'], UHi).numpy() * float(hyp['outputscale'])
+    assert (out['svar'][:400] < 1e-4 * ubu + 1e-9 * prior).all()              # collapsed to the jitter level
+    # integer arithmetic is exact and the tile a query lands in only changes which other columns share its MMAs:
+    # permuting the queries permutes the answers bit for bit
+    assert np.array_equal(outp['Bk'], out['Bk'][perm.numpy()])
