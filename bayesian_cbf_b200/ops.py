@@ -192,6 +192,24 @@ def posterior_var_i8(digits, rowscale, Kstar, G, Bmat, kss, p, Q):
     return Bk
 
 
+def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, want_cov=True):
+    """posterior_blocks with the covariance contraction on the int8 tensor cores and the mean fused into the pass over
+    K* that finds the column scales (bcbf_posterior_blocks_i8)."""
+    _req(rowscale, Kstar, G, W, Bmat, Ct)
+    Npad = rowscale.shape[0]
+    dev = Kstar.device
+    Mk = torch.empty(Q, n, p, dtype=torch.float64, device=dev) if want_mean else None
+    Bk = torch.empty(Q, p, p, dtype=torch.float64, device=dev) if want_cov else None
+    check(_lib.load().bcbf_posterior_blocks_i8(_ptr(digits), _ptr(rowscale), Npad, _ptr(Kstar), Kstar.stride(0), _ptr(G),
+                                               _ptr(W), _ptr(Bmat), _ptr(Ct), float(kss), n, p, Q, _ptr(Mk), _ptr(Bk),
+                                               _stream()))
+    return Mk, Bk
+
+
+def oz_max_npad():
+    return _lib.load().bcbf_oz_max_npad()
+
+
 def posterior_fu_var(Linv, Kstar, G, Bmat, UHq, kss, n, p):
     _req(Linv, Kstar, G, Bmat, UHq)
     Npad = Linv.shape[0]

@@ -88,3 +88,26 @@ def test_model_handle_int8_path_matches_dmma_path():
     # the mean rides on a different pass over K* (other summation order of a cancelling sum): rounding level of sum |K* W|
     assert np.abs(outs['int8']['Mk'] - outs['dmma']['Mk']).max() < 1e-8 * np.abs(outs['dmma']['Mk']).max()
     assert np.abs(outs['int8']['mean'] - outs['dmma']['mean']).max() < 1e-8 * np.abs(outs['dmma']['mean']).max()
+
+
+def test_host_class_picks_the_int8_kernel_for_large_batches():
+    """ControlAffineRegressorExact.custom_predict_blocks: 'auto' switches to the int8 kernel at N >= 1024, >= 512 queries;
+    both kernels give the same blocks."""
+    from bayesian_cbf_b200.control_affine_model import ControlAffineRegressorExact
+    torch.manual_seed(0)
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(21, 1100, 3, 2, 700, box=2.0)
+    reg = ControlAffineRegressorExact(3, 2, device='cuda')
+    reg.double_()
+    reg.fit(X, U, Xdot, training_iter=0)
+    out = {}
+    for kern in ('dmma', 'int8', 'auto'):
+        reg.covariance_kernel = kern
+        Mk, Bk, mean, svar = reg.custom_predict_blocks(Xq, Uq)
+        out[kern] = (Mk.cpu(), Bk.cpu(), mean.cpu(), svar.cpu())
+        assert ('_oz' in reg._cache) == (kern != 'dmma')
+    scale = out['dmma'][1].abs().max().item()
+    assert (out['int8'][1] - out['dmma'][1]).abs().max().item() < 1e-12 * scale
+    assert torch.equal(out['auto'][1], out['int8'][1]) and torch.equal(out['auto'][0], out['int8'][0])
+    assert (out['int8'][0] - out['dmma'][0]).abs().max().item() < 1e-8 * out['dmma'][0].abs().max().item()
+    reg.clear_cache()
+    assert '_oz' not in reg._cache
