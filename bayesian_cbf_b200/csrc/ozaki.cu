@@ -226,18 +226,19 @@ struct VarArgs {
   const double* colscale;
   double* Spart;  // [nb][Qpad][NP]
   int nb;         // row blocks of L^-1 (Npad / 128)
-  int nJ;         // column tiles (Qpad / QT)
+  int nJg;        // groups of CL column tiles (Qpad / (CL QT))
   int Qpad;
-  long long total_tiles;
+  long long total_tiles;  // work items: 4 ceil(nb / 4) nJg
   unsigned long long* dbg;
 };
 
-// tile order: groups of 4 row blocks (longest K extent first) x all column tiles; 148 consecutive tiles = 4 row blocks x
-// 37 column tiles, so CTAs running side by side share L^-1 digits 37-fold and frakB digits 4-fold through L2.
-__device__ __forceinline__ bool tile_of(const VarArgs& a, long long t, int& I, int& J) {
-  const int per_group = 4 * a.nJ;
+// tile order: groups of 4 row blocks (longest K extent first) x all column-tile groups; consecutive work items = 4 row
+// blocks x consecutive column tiles, so CTAs running side by side share L^-1 digits ~37-fold and frakB digits 4-fold
+// through L2.  A work item is (row block I, group of CL column tiles); CTA `rank` of the cluster takes tile CL Jg + rank.
+__device__ __forceinline__ bool tile_of(const VarArgs& a, long long t, int& I, int& Jg) {
+  const int per_group = 4 * a.nJg;
   const int g = static_cast<int>(t / per_group), r = static_cast<int>(t % per_group);
-  J = r >> 2;
+  Jg = r >> 2;
   const int ii = ((r & 3) + static_cast<int>((t >> 2) & 3)) & 3;
   I = a.nb - 1 - (4 * g + ii);
   return I >= 0;
@@ -258,9 +259,17 @@ __device__ __forceinline__ void issue_kstep(uint32_t tmem, uint32_t a_base, uint
   }
 }
 
-template <int P>
+// CL = 1 (default): every CTA works alone.  CL = 2: clusters of two CTAs work on the same row block and neighbouring
+// column tiles and share the L^-1 digits: each CTA fetches half of the 28 KB blob and multicasts it into both shared
+// memories (L2 -> SM requests per K step 42 KB -> 28 KB per CTA).  Measured: bit-identical results, NO speed-up (1070 vs
+// 1050 cycles per K step with counters on) - the limiter is the shared-memory port, which carries the MMA operand reads
+// (96 KB per K step) AND the incoming copies (42 KB): 138 KB / 128 B/clk = 1080 cycles against the 920-cycle MMA pattern,
+// and multicast does not change what arrives in shared memory.  Kept as an option (bcbf_oz_set_cluster).
+template <int P, int CL>
 __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
   constexpr int QT = TN / P, NP = P * (P + 1) / 2;
+  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const long long worker = blockIdx.x / CL, nworkers = gridDim.x / CL;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
   uint64_t* empty = full + NSTAGE;
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, kEpiThreads);
@@ -286,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -294,9 +304,10 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
-      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      for (long long t = worker; t < a.total_tiles; t += nworkers) {
         int I, J;
         if (!tile_of(a, t, I, J)) continue;
+        J = J * CL + rank;
         const int nks = 4 * (I + 1);
         const int8_t* ap = a.Ablob + 2LL * I * (I + 1) * A_STEP;
         const int8_t* bp = a.Bblob + (long long)J * (a.nb * 4) * B_STEP;
@@ -310,8 +321,19 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
           }
           uint8_t* dst = smem + stage * STAGE;
           mbar_arrive_expect_tx(&full[stage], STAGE);
-          bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
+          if (CL == 1) {
+            bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
+          } else {  // my half of the L^-1 digits goes to both CTAs; the peer sends the other half
+            constexpr int HALF = A_STEP / 2;
+            bulk_g2s_multicast(dst + rank * HALF, ap + (long long)ks * A_STEP + rank * HALF, HALF, &full[stage], 0x3);
+          }
           bulk_g2s(dst + A_STEP, bp + (long long)ks * B_STEP, B_STEP, &full[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (CL > 1) {  // tail: every arrival the peer still owes my barriers has landed before this CTA may exit
+        for (int s = 0; s < NSTAGE; ++s) {
+          mbar_wait(&empty[stage], phase ^ 1u);
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }
@@ -323,9 +345,10 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
       uint32_t phase = 0, tile_iter = 0;
       long long w_full = 0, w_tmem = 0, nstep = 0;
       const long long t_begin = clock64();
-      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      for (long long t = worker; t < a.total_tiles; t += nworkers) {
         int I, J;
         if (!tile_of(a, t, I, J)) continue;
+        J = J * CL + rank;
         const int nks = 4 * (I + 1);
         if (a.dbg) {
           const long long c0 = clock64();
@@ -347,7 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE);
           issue_kstep(tmem, sa, sa + A_STEP, ks == 0);
-          mma_commit(&empty[stage]);  // frees the stage when these MMAs have read it
+          if (CL == 1) mma_commit(&empty[stage]);  // frees the stage when these MMAs have read it
+          else mma_commit_multicast(&empty[stage], 0x3);  // ... in both CTAs: the peer writes half of my stage
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
         mma_commit(tmem_full);
@@ -363,9 +387,10 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
   } else {  // ===== epilogue warps 0..3: TMEM lanes 32 warp .. 32 warp + 31 =====
     const int tid = threadIdx.x;
     uint32_t tile_iter = 0;
-    for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    for (long long t = worker; t < a.total_tiles; t += nworkers) {
       int I, J;
       if (!tile_of(a, t, I, J)) continue;
+      J = J * CL + rank;
       if (tid < TN) cs[tid] = a.colscale[(long long)J * TN + tid];
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(tmem_full, tile_iter & 1u);
@@ -414,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   if (warp == 5) tmem_dealloc(tmem, 512);
 }
 
@@ -465,12 +491,61 @@ static Prof g_prof;
 
 static unsigned long long* g_dbg = nullptr;
 
+static int g_cluster = 1;  // CTAs per cluster of oz_var_kernel (1 or 2); bcbf_oz_set_cluster
+
+template <int P, int CL>
+static int launch_var(VarArgs a, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  BCBF_CUDA(cudaGetDevice(&dev));
+  BCBF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  BCBF_CUDA(cudaFuncSetAttribute(oz_var_kernel<P, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int workers = sms / CL;
+  if (CL > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // a persistent grid must be co-resident: ask how many clusters fit (SM pairs of one TPC)
+    static int max_clusters[64] = {0};
+    if (max_clusters[dev & 63] == 0) {
+      cfg.gridDim = dim3(sms - sms % CL);
+      int n = 0;
+      BCBF_CUDA(cudaOccupancyMaxActiveClusters(&n, oz_var_kernel<P, CL>, &cfg));
+      max_clusters[dev & 63] = n > 0 ? n : 1;
+    }
+    if (workers > max_clusters[dev & 63]) workers = max_clusters[dev & 63];
+  }
+  if (a.total_tiles < workers) workers = static_cast<int>(a.total_tiles);
+  cfg.gridDim = dim3(workers * CL);
+  const bool prof = g_prof.on && g_prof.n < 256;
+  if (prof) {
+    BCBF_CUDA(cudaEventCreate(&g_prof.e0[g_prof.n]));
+    BCBF_CUDA(cudaEventCreate(&g_prof.e1[g_prof.n]));
+    BCBF_CUDA(cudaEventRecord(g_prof.e0[g_prof.n], stream));
+  }
+  BCBF_CUDA(cudaLaunchKernelEx(&cfg, oz_var_kernel<P, CL>, a));
+  BCBF_LAUNCH_CHECK();
+  if (prof) {
+    BCBF_CUDA(cudaEventRecord(g_prof.e1[g_prof.n], stream));
+    ++g_prof.n;
+  }
+  return BCBF_OK;
+}
+
 template <int P>
 static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, const double* Kstar, int ldks,
                       const double* G, const double* W, const double* Bmat, const double* Ct, double kss, int n, int Q,
                       double* Mk, double* Bk, cudaStream_t stream) {
   constexpr int QT = TN / P, NP = P * (P + 1) / 2;
-  const int nb = Npad / TM, nJ = ceil_div(Q, QT), Qpad = nJ * QT, nc = n * P;
+  const int CL = g_cluster;
+  const int nb = Npad / TM, nJg = ceil_div(Q, QT * CL), nJ = nJg * CL, Qpad = nJ * QT, nc = n * P;
   const int nsplit = ceil_div(Npad, kCmRows);
   void *bblob, *colmax, *colscale, *spart, *mpart = nullptr;
   int rc;
@@ -497,6 +572,7 @@ static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, con
   if ((rc = workspace(0, (size_t)nJ * (Npad / KSTEP) * B_STEP, &bblob))) return rc;
   if ((rc = workspace(2, sizeof(double) * (size_t)nJ * TN, &colscale))) return rc;
   if ((rc = workspace(3, sizeof(double) * (size_t)nb * Qpad * NP, &spart))) return rc;
+  // every column of every tile is written (dead columns and queries past Q: zero digits, zero scale)
   split_frakb_kernel<P><<<dim3(ceil_div(nJ * TN, 128), Npad / 16), 128, 0, stream>>>(
       Kstar, ldks, G, Npad, Q, nJ, static_cast<const unsigned long long*>(colmax), static_cast<int8_t*>(bblob),
       static_cast<double*>(colscale));
@@ -508,28 +584,12 @@ static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, con
   a.colscale = static_cast<const double*>(colscale);
   a.Spart = static_cast<double*>(spart);
   a.nb = nb;
-  a.nJ = nJ;
+  a.nJg = nJg;
   a.Qpad = Qpad;
-  a.total_tiles = (long long)ceil_div(nb, 4) * 4 * nJ;
+  a.total_tiles = (long long)ceil_div(nb, 4) * 4 * nJg;
   a.dbg = g_dbg;
-  int dev = 0, sms = 148;
-  BCBF_CUDA(cudaGetDevice(&dev));
-  BCBF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  sms -= sms % 4;  // the tile order rotates row blocks in groups of 4
-  BCBF_CUDA(cudaFuncSetAttribute(oz_var_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  const int grid = a.total_tiles < sms ? static_cast<int>(a.total_tiles) : sms;
-  const bool prof = g_prof.on && g_prof.n < 256;
-  if (prof) {
-    BCBF_CUDA(cudaEventCreate(&g_prof.e0[g_prof.n]));
-    BCBF_CUDA(cudaEventCreate(&g_prof.e1[g_prof.n]));
-    BCBF_CUDA(cudaEventRecord(g_prof.e0[g_prof.n], stream));
-  }
-  oz_var_kernel<P><<<grid, kThreads, kSmemBytes, stream>>>(a);
-  BCBF_LAUNCH_CHECK();
-  if (prof) {
-    BCBF_CUDA(cudaEventRecord(g_prof.e1[g_prof.n], stream));
-    ++g_prof.n;
-  }
+  rc = CL == 2 ? launch_var<P, 2>(a, stream) : launch_var<P, 1>(a, stream);
+  if (rc) return rc;
   finalize_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(a.Spart, Qpad, nb, Q, P, Bmat, kss, Bk);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
@@ -606,6 +666,13 @@ extern "C" int bcbf_oz_debug_counters(int enable, unsigned long long out[8]) {
     BCBF_CUDA(cudaFree(oz::g_dbg));
     oz::g_dbg = nullptr;
   }
+  return BCBF_OK;
+}
+
+// CTAs per cluster of oz_var_kernel: 1 (default) or 2 (the pair multicasts the L^-1 digits to each other).
+extern "C" int bcbf_oz_set_cluster(int ctas) {
+  BCBF_REQUIRE(ctas == 1 || ctas == 2, "bcbf_oz_set_cluster: 1 or 2");
+  oz::g_cluster = ctas;
   return BCBF_OK;
 }
 

@@ -177,6 +177,9 @@ int bcbf_posterior_var_i8(const void* digits, const double* rowscale, int Npad, 
 int bcbf_posterior_blocks_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar, int ldks,
                              const double* G, const double* W, const double* Bmat, const double* Ct, double kss, int n,
                              int p, int Q, double* Mk, double* Bk, void* stream);
+/* oz_var_kernel runs as single CTAs (1, default) or as clusters of 2 CTAs that multicast the L^-1 digits to each other
+ * (bit-identical results; measured no faster: the shared-memory port, not L2, is the limiter). */
+int bcbf_oz_set_cluster(int ctas);
 /* Development aid: pipeline counters of oz_var_kernel (see csrc/ozaki.cu). */
 int bcbf_oz_debug_counters(int enable, unsigned long long out[8]);
 /* CUDA-event timing of oz_var_kernel launches (bench.py's roofline leg), like bcbf_profile_enable/read. */

@@ -111,3 +111,23 @@ def test_host_class_picks_the_int8_kernel_for_large_batches():
     assert (out['int8'][0] - out['dmma'][0]).abs().max().item() < 1e-8 * out['dmma'][0].abs().max().item()
     reg.clear_cache()
     assert '_oz' not in reg._cache
+
+
+def test_cluster_multicast_variant_is_bit_identical():
+    """oz_var_kernel as single CTAs (the default) and as clusters of two CTAs (multicast of the L^-1 digits): the same
+    integers are accumulated, so B_k agrees bit for bit; odd and even numbers of column tiles."""
+    from bayesian_cbf_b200 import _lib, ops
+    lib = _lib.load()
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(9, 640, 3, 2, 21 * 5 + 3, box=2.5)
+    L, Linv, G, alpha, W = _fit_on_gpu(X, U, Xdot, hyp, jit)
+    digits, rowscale = ops.oz_split_factor(Linv)
+    try:
+        for Q in (21 * 5 + 3, 21 * 4, 1):
+            Ks = ops.cross_gram(_d(X), _d(Xq[:Q]), _d(hyp.lengthscale), float(hyp.outputscale))
+            res = []
+            for ctas in (1, 2):
+                assert lib.bcbf_oz_set_cluster(ctas) == 0
+                res.append(ops.posterior_var_i8(digits, rowscale, Ks, G, _d(hyp.B), float(hyp.outputscale), 3, Q).cpu())
+            assert torch.equal(res[0], res[1]), Q
+    finally:
+        lib.bcbf_oz_set_cluster(1)
