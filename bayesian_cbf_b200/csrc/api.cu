@@ -413,7 +413,7 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
   rc = finish_fit_from_factor(m);
   if (rc) return rc;
   m->oz_split_ms = 0.0;
-  if (m->var_path == 1 && (rc = ensure_oz_digits(m, s, true))) return rc;
+  if (m->var_path == 1 && Npad <= bcbf_oz_max_npad() && (rc = ensure_oz_digits(m, s, true))) return rc;
   BCBF_CUDA(cudaEventRecord(ev[4], s));
   BCBF_CUDA(cudaStreamSynchronize(s));
   float ms;
@@ -484,7 +484,8 @@ static int query_batch_device(bcbf_model* m, const double* dXq, const double* dU
   double* Bk = dBk ? dBk : m->Bk;
   const bool need_var = dBk || dsvar;
   const bool need_mean = dMk || dmean;
-  const bool i8 = m->var_path == 1;
+  // factors beyond the exact-int32-accumulation limit of the int8 kernel stay on the FP64 pipe
+  const bool i8 = m->var_path == 1 && Npad <= bcbf_oz_max_npad();
   if (i8) {
     if (need_var && (rc = ensure_oz_digits(m, s, false))) return rc;
     rc = need_var ? bcbf_posterior_blocks_i8(m->oz_digits, m->oz_rowscale, Npad, m->Kstar, ldks, m->G, m->W,

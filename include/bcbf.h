@@ -292,7 +292,8 @@ int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int N);
 /* Milliseconds spent in the stages of the last bcbf_model_fit (gram, potrf, trtri, alpha, total). */
 int bcbf_model_fit_timing(bcbf_model* m, double out_ms[5]);
 /* Which kernel computes B_k in bcbf_model_query*: 0 = FP64 tensor pipe (DMMA, post_var_kernel), 1 = int8 tensor cores
- * with error-free digit splitting (oz_var_kernel; needs Npad <= bcbf_oz_max_npad()).  With path 1 the fit also splits
+ * with error-free digit splitting (oz_var_kernel; larger factors than bcbf_oz_max_npad() silently stay on path 0: same
+ * results).  With path 1 the fit also splits
  * L^-1 into digits (bcbf_model_oz_split_ms: device time of that step in the last fit; it is part of fit "total").  */
 int bcbf_model_set_var_path(bcbf_model* m, int path);
 int bcbf_model_get_var_path(bcbf_model* m);

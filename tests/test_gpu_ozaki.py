@@ -131,3 +131,41 @@ def test_cluster_multicast_variant_is_bit_identical():
             assert torch.equal(res[0], res[1]), Q
     finally:
         lib.bcbf_oz_set_cluster(1)
+
+
+def test_int8_entry_points_reject_bad_arguments():
+    from bayesian_cbf_b200 import _lib
+    lib = _lib.load()
+    big = lib.bcbf_oz_max_npad() + 128
+    assert lib.bcbf_oz_max_npad() == 18432 and lib.bcbf_oz_factor_bytes(256) == 2 * 2 * 3 * 7 * 128 * 32
+    assert lib.bcbf_oz_factor_bytes(100) == 0
+    x = torch.zeros(16, dtype=torch.float64, device='cuda')
+    ptr = x.data_ptr()
+    # factor larger than the exact-int32 limit, Npad not a multiple of 128, ldks < Q, unsupported p, null pointers
+    assert lib.bcbf_oz_split_factor(ptr, big, big, ptr, ptr, None) == _lib.BCBF_ERR_INVALID
+    assert lib.bcbf_posterior_var_i8(ptr, ptr, big, ptr, 64, ptr, ptr, 1.0, 3, 8, ptr, None) == _lib.BCBF_ERR_INVALID
+    assert lib.bcbf_posterior_var_i8(ptr, ptr, 200, ptr, 64, ptr, ptr, 1.0, 3, 8, ptr, None) == _lib.BCBF_ERR_INVALID
+    assert lib.bcbf_posterior_var_i8(ptr, ptr, 256, ptr, 4, ptr, ptr, 1.0, 3, 8, ptr, None) == _lib.BCBF_ERR_INVALID
+    assert lib.bcbf_posterior_var_i8(ptr, ptr, 256, ptr, 64, ptr, ptr, 1.0, 5, 8, ptr, None) == _lib.BCBF_ERR_INVALID
+    assert lib.bcbf_posterior_var_i8(None, ptr, 256, ptr, 64, ptr, ptr, 1.0, 3, 8, ptr, None) == _lib.BCBF_ERR_INVALID
+    assert b'bcbf_posterior' in lib.bcbf_last_error()
+    assert lib.bcbf_oz_set_cluster(3) == _lib.BCBF_ERR_INVALID
+
+
+@pytest.mark.parametrize('n,m', [(2, 0), (2, 1), (3, 3)])
+def test_model_handle_int8_other_control_dimensions(n, m):
+    """p = 1, 2, 4 (64, 32, 16 queries per tile) through the model handle, against the oracle."""
+    from bayesian_cbf_b200.model import MVGPModel, make_hyper
+    p = m + 1
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(31 + p, 400, n, m, 333, box=2.0)
+    h = make_hyper(n, p, hyp.lengthscale.numpy(), float(hyp.outputscale), hyp.A.numpy(), hyp.B.numpy(), hyp.C.numpy())
+    model = MVGPModel(0).set_var_path('int8')
+    model.fit(h, X.numpy(), U.numpy().reshape(400, m), Xdot.numpy(), jit.numpy(), 1e-5)
+    out = model.query(Xq.numpy(), Uq.numpy().reshape(333, m) if m else None)
+    model.close()
+    Lref = O.perturbed_cholesky(hyp, X, O.homogeneous(U), [jit], direct=True)
+    Mk_o, Bk_o, mean_o, svar_o = O.posterior_blocks(hyp, X, U, Xdot, Lref, Xq, Uq, direct=True)
+    prior = (hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)).item()
+    assert np.abs(out['Bk'] - Bk_o.numpy()).max() / prior < 1e-9
+    assert np.abs(out['svar'] - svar_o.numpy()).max() / prior < 1e-8
+    assert np.abs(out['Mk'] - Mk_o.numpy()).max() < 1e-6 * np.abs(Mk_o.numpy()).max()
