@@ -113,6 +113,19 @@ __device__ __forceinline__ void mma_s8(uint32_t tmem_d, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the A operand in tensor memory (128 lanes x 8 columns per 32-byte K step, written by tmem_cp_128x256b)
+__device__ __forceinline__ void mma_s8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared memory (matrix descriptor: 128 rows x 32 bytes) -> tensor memory (128 lanes x 8 columns), issued by one thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
 // all MMAs issued so far by this thread -> one arrival on `bar` when they have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -36,6 +36,24 @@ __device__ __forceinline__ void issue_pattern(uint32_t tmem, uint32_t a_base, ui
   }
 }
 
+// the same products with A in tensor memory: slice a is copied to TMEM columns 448 + 8 a right before its MMAs; copies
+// and MMAs execute in issue order, so the copy of the NEXT K step's slice a may be issued as soon as this step's
+// slice-a MMAs are
+__device__ __forceinline__ void issue_pattern_ts(uint32_t tmem, uint32_t a_base, uint32_t b_base, bool first) {
+#pragma unroll
+  for (int a = 0; a < S; ++a) {
+    tmem_cp_128x256b(tmem + 448 + 8 * a, smem_desc_kmajor(a_base + a * (TM * 32), 128, 256));
+    int b = 0;
+    while (b <= S - 1 - a) {
+      int nb = S - a - b;
+      if (nb > 4) nb = 4;
+      const uint64_t bd = smem_desc_kmajor(b_base + b * (TN * 32), 128, 256);
+      mma_s8_ts(tmem + (a + b) * TN, tmem + 448 + 8 * a, bd, idesc_s8(TM, TN * nb), (first && a == 0) ? 0u : 1u);
+      b += nb;
+    }
+  }
+}
+
 // mode 0: A0 x B0 (N=64);  1: A0 x [B0..B3] (N=256);  2: full pattern over KS K steps
 __global__ void __launch_bounds__(128, 1) probe_kernel(const int8_t* Ablob, const int8_t* Bblob, int KS, int mode,
                                                        uint32_t lbo, uint32_t sbo, int* out) {
@@ -70,9 +88,11 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const int8_t* Ablob, cons
       mma_s8(tmem, smem_desc_kmajor(smem_u32(sA), lbo, sbo), smem_desc_kmajor(smem_u32(sB), lbo, sbo), idesc_s8(TM, 64), 0);
     } else if (mode == 1) {
       mma_s8(tmem, smem_desc_kmajor(smem_u32(sA), lbo, sbo), smem_desc_kmajor(smem_u32(sB), lbo, sbo), idesc_s8(TM, 256), 0);
-    } else {
+    } else if (mode == 2) {
       for (int ks = 0; ks < KS; ++ks)
         issue_pattern(tmem, smem_u32(sA + ks * A_STEP), smem_u32(sB + ks * B_STEP), lbo, sbo, ks == 0);
+    } else {  // mode 3: A slices copied to tensor memory (columns 448..503), MMAs take A from there
+      for (int ks = 0; ks < KS; ++ks) issue_pattern_ts(tmem, smem_u32(sA + ks * A_STEP), smem_u32(sB + ks * B_STEP), ks == 0);
     }
     mma_commit(&bar_mma);
   }
@@ -130,6 +150,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int pattern, int iters, lo
         tc_fence_after();
         issue_pattern(tmem, a_base, b_base, 128, 256, it == 0);
         if (it & 1) mma_commit(&bar_ring[(it >> 1) & 7]);
+      } else if (pattern == 5) {
+        issue_pattern_ts(tmem, a_base, b_base, it == 0);
       } else if (pattern == 1) {
         for (int a = 0; a < S; ++a)
           for (int b = 0; b <= S - 1 - a; ++b)
@@ -186,9 +208,10 @@ int main() {
   std::vector<int> out(128 * 512);
   for (int variant = 0; variant < 2; ++variant) {
     const uint32_t lbo = variant == 0 ? 128 : 256, sbo = variant == 0 ? 256 : 128;
-    for (int mode = 0; mode < 3; ++mode) {
+    for (int mode = 0; mode < 4; ++mode) {
+      if (mode == 3 && variant == 1) continue;
       CK(cudaMemset(dOut, 0xff, 128 * 512 * 4));
-      probe_kernel<<<1, 128, smem_bytes>>>(dA, dB, mode == 2 ? KS : 1, mode, lbo, sbo, dOut);
+      probe_kernel<<<1, 128, smem_bytes>>>(dA, dB, mode >= 2 ? KS : 1, mode, lbo, sbo, dOut);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("variant %d mode %d: kernel failed: %s\n", variant, mode, cudaGetErrorString(e)); return 1; }
       CK(cudaMemcpy(out.data(), dOut, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -232,10 +255,10 @@ int main() {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  const char* names[5] = {"10-MMA concatenated pattern", "28 separate N=64 MMAs", "7 MMAs of N=256",
-                          "10-MMA + fence + commit / step", "10-MMA + commit / 2 steps"};
+  const char* names[6] = {"10-MMA concatenated pattern", "28 separate N=64 MMAs", "7 MMAs of N=256",
+                          "10-MMA + fence + commit / step", "10-MMA + commit / 2 steps", "10-MMA, A via tcgen05.cp -> TMEM"};
   for (int grid : {1, 148}) {
-    for (int pattern = 0; pattern < 5; ++pattern) {
+    for (int pattern = 0; pattern < 6; ++pattern) {
       const int iters = 20000;
       rate_kernel<<<grid, 128, 200 * 1024>>>(pattern, 200, dCyc);   // warm-up
       CK(cudaDeviceSynchronize());
