@@ -94,6 +94,9 @@ _SIGNATURES = {
     'bcbf_posterior_blocks_i8': (c_int, [_P, _P, c_int, _P, c_int, _P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, _P,
                                          _P]),
     'bcbf_oz_debug_counters': (c_int, [c_int, POINTER(ctypes.c_ulonglong * 8)]),
+    'bcbf_oz_gemm': (c_int, [c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
+    'bcbf_oz_gemm_reserve': (c_int, [c_int, c_int, c_int]),
+    'bcbf_set_trtri_i8': (c_int, [c_int]),
     'bcbf_oz_set_cluster': (c_int, [c_int]),
     'bcbf_oz_profile_enable': (c_int, [c_int]),
     'bcbf_oz_profile_read': (c_int, [POINTER(c_double), POINTER(c_int)]),

@@ -159,6 +159,74 @@ __global__ void build_w_kernel(const double* __restrict__ alpha, int lda, const 
     for (int j = 0; j < p; ++j) W[((long long)i * n + r) * p + j] = alpha[(long long)i * lda + r] * G[(long long)i * p + j];
 }
 
+// ---- skinny triangular products: y = beta * y0 + alpha * op(T) x,  T lower triangular (Npad,Npad; ld, strictly upper part
+// stored as zero), x / y / y0 (Npad, nc <= 8 columns, leading dimension ldx).  HBM-bound: T is read once (4 Npad^2 bytes).
+// Used for alpha = Kb^-1 Y and its refinement step (control_affine_model.py:545).
+constexpr int kMvMaxC = 8;
+__global__ void __launch_bounds__(256) tri_mv_n_kernel(const double* __restrict__ T, int ld, int Npad,
+                                                       const double* __restrict__ x, int ldx, int nc, double alpha,
+                                                       double beta, const double* __restrict__ y0,
+                                                       double* __restrict__ y) {
+  const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= Npad) return;
+  double acc[kMvMaxC];
+#pragma unroll
+  for (int c = 0; c < kMvMaxC; ++c) acc[c] = 0.0;
+  const double* t = T + (long long)row * ld;
+  for (int k = lane; k <= row; k += 32) {
+    const double v = t[k];
+#pragma unroll
+    for (int c = 0; c < kMvMaxC; ++c)
+      if (c < nc) acc[c] = fma(v, x[(long long)k * ldx + c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < kMvMaxC; ++c)
+    if (c < nc) {
+      const double s = warp_sum(acc[c]);
+      if (lane == 0) y[(long long)row * ldx + c] = (y0 ? beta * y0[(long long)row * ldx + c] : 0.0) + alpha * s;
+    }
+}
+
+// op(T) = T^T: thread per column j of a 128-column strip, rows split over blockIdx.y; partial[split][j][c]
+constexpr int kMvRows = 1024;
+__global__ void __launch_bounds__(128) tri_mv_t_kernel(const double* __restrict__ T, int ld, int Npad,
+                                                       const double* __restrict__ x, int ldx, int nc,
+                                                       double* __restrict__ partial) {
+  __shared__ double xs[64 * kMvMaxC];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int i0 = max(blockIdx.y * kMvRows, blockIdx.x * 128), i1 = min(Npad, (blockIdx.y + 1) * kMvRows);
+  double acc[kMvMaxC];
+#pragma unroll
+  for (int c = 0; c < kMvMaxC; ++c) acc[c] = 0.0;
+  for (int ib = i0; ib < i1; ib += 64) {   // i0 and i1 are multiples of 128
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * nc; e += 128) xs[(e / nc) * kMvMaxC + e % nc] = x[(long long)(ib + e / nc) * ldx + e % nc];
+    __syncthreads();
+    for (int r = 0; r < 64; r += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (ib + r + u >= j) ? T[(long long)(ib + r + u) * ld + j] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int c = 0; c < kMvMaxC; ++c)
+          if (c < nc) acc[c] = fma(v[u], xs[(r + u) * kMvMaxC + c], acc[c]);
+    }
+  }
+  for (int c = 0; c < nc; ++c) partial[((long long)blockIdx.y * Npad + j) * nc + c] = acc[c];
+}
+
+__global__ void tri_mv_t_finalize_kernel(const double* __restrict__ partial, int Npad, int nc, int nsplit, int ldx,
+                                         double alpha, double beta, const double* __restrict__ y0,
+                                         double* __restrict__ y) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Npad * nc) return;
+  const int j = static_cast<int>(idx / nc), c = static_cast<int>(idx % nc);
+  double s = 0.0;
+  for (int sp = j / kMvRows; sp < nsplit; ++sp) s += partial[((long long)sp * Npad + j) * nc + c];
+  y[(long long)j * ldx + c] = (y0 ? beta * y0[(long long)j * ldx + c] : 0.0) + alpha * s;
+}
+
 __global__ void build_uh_kernel(const double* __restrict__ U, int Q, int p, double* __restrict__ UH) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Q) return;
@@ -333,7 +401,8 @@ extern "C" int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int 
     if ((rc = dev_alloc(&m->UH, (size_t)Npad * BCBF_MAX_P_DIM))) return rc;
     if ((rc = dev_alloc(&m->G, (size_t)Npad * BCBF_MAX_P_DIM))) return rc;
     if ((rc = dev_alloc(&m->alpha, (size_t)Npad * BCBF_MAX_N_DIM))) return rc;
-    if ((rc = dev_alloc(&m->Y, (size_t)Npad * BCBF_MAX_N_DIM * 2))) return rc;
+    // Y, two scratch copies and the split partials of the transposed skinny products (finish_fit_from_factor)
+    if ((rc = dev_alloc(&m->Y, (size_t)Npad * BCBF_MAX_N_DIM * (3 + (size_t)ceil_div(Npad, 1024))))) return rc;
     if ((rc = dev_alloc(&m->W, (size_t)Npad * BCBF_MAX_N_DIM * BCBF_MAX_P_DIM))) return rc;
     if ((rc = dev_alloc(&m->hyp_dev, (size_t)256))) return rc;
     if (!m->info) BCBF_CUDA(cudaMalloc(&m->info, sizeof(int)));
@@ -341,6 +410,12 @@ extern "C" int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int 
   }
   m->N = N;
   m->Npad = Npad;
+  if (Npad >= 4096 && Npad <= bcbf_oz_max_npad()) {  // bcbf_trtri's int8 levels: workspaces sized outside the timed fit
+    int hmax = 2048;
+    while (2 * hmax < Npad) hmax *= 2;
+    int rc = bcbf_oz_gemm_reserve(hmax, hmax, hmax);
+    if (rc) return rc;
+  }
   // hyper-parameter block on the device: [lengthscale(8) | B(16) | C(32) | Ct(32) | A(64)]
   double hbuf[256];
   memset(hbuf, 0, sizeof(hbuf));
@@ -355,15 +430,44 @@ extern "C" int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int 
   return BCBF_OK;
 }
 
-static int finish_fit_from_factor(bcbf_model* m) {
-  // alpha = Linv^T (Linv Y);  W = alpha (.) G
+// y = beta * y0 + alpha * op(T) x  (y0 may be null); `partial` holds ceil(Npad / 1024) * Npad * nc doubles
+static int tri_mv(const double* T, int ld, int Npad, int trans, const double* x, int ldx, int nc, double alpha, double beta,
+                  const double* y0, double* y, double* partial, cudaStream_t s) {
+  if (!trans) {
+    tri_mv_n_kernel<<<ceil_div(Npad, 8), 256, 0, s>>>(T, ld, Npad, x, ldx, nc, alpha, beta, y0, y);
+    BCBF_LAUNCH_CHECK();
+    return BCBF_OK;
+  }
+  const int nsplit = ceil_div(Npad, kMvRows);
+  tri_mv_t_kernel<<<dim3(Npad / 128, nsplit), 128, 0, s>>>(T, ld, Npad, x, ldx, nc, partial);
+  BCBF_LAUNCH_CHECK();
+  tri_mv_t_finalize_kernel<<<ceil_div((long long)Npad * nc, 256), 256, 0, s>>>(partial, Npad, nc, nsplit, ldx, alpha, beta,
+                                                                               y0, y);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+static int finish_fit_from_factor(bcbf_model* m, bool have_factor) {
+  // alpha = Linv^T (Linv Y), then one step of iterative refinement against the factor itself,
+  //   r = Y - L (L^T alpha),  alpha += Linv^T (Linv r):
+  // the explicit inverse carries a forward error ~ eps * cond(L); the residual is formed with L (backward stable), so
+  // the refined alpha predicts like the reference's cholesky_solve (control_affine_model.py:545).  W = alpha (.) G.
+  // A rank that adopted a broadcast state has no L (have_factor = false) and keeps the broadcast alpha.
   const int n = m->hyp.n, p = m->hyp.p, Npad = m->Npad, ldy = ld_y(n);
-  double* tmp = m->Y + (size_t)Npad * ldy;  // second half of the Y buffer
-  int rc = bcbf_trmm_lower(m->Linv, Npad, Npad, 0, m->Y, ldy, ldy, 1.0, 0.0, tmp, ldy, m->stream);
-  if (rc) return rc;
-  rc = bcbf_trmm_lower(m->Linv, Npad, Npad, 1, tmp, ldy, ldy, 1.0, 0.0, m->alpha, ldy, m->stream);
-  if (rc) return rc;
-  build_w_kernel<<<ceil_div(Npad, 128), 128, 0, m->stream>>>(m->alpha, ldy, m->G, Npad, n, p, m->W);
+  cudaStream_t s = m->stream;
+  double* t = m->Y + (size_t)Npad * ldy;          // scratch columns inside the Y buffer (6 x Npad x ldy)
+  double* r = t + (size_t)Npad * ldy;
+  double* part = r + (size_t)Npad * ldy;          // ceil(Npad / 1024) * Npad * ldy
+  int rc;
+  if ((rc = tri_mv(m->Linv, Npad, Npad, 0, m->Y, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;
+  if ((rc = tri_mv(m->Linv, Npad, Npad, 1, t, ldy, ldy, 1.0, 0.0, nullptr, m->alpha, part, s))) return rc;
+  if (have_factor) {
+    if ((rc = tri_mv(m->L, Npad, Npad, 1, m->alpha, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;   // L^T alpha
+    if ((rc = tri_mv(m->L, Npad, Npad, 0, t, ldy, ldy, -1.0, 1.0, m->Y, r, part, s))) return rc;            // Y - L (.)
+    if ((rc = tri_mv(m->Linv, Npad, Npad, 0, r, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;
+    if ((rc = tri_mv(m->Linv, Npad, Npad, 1, t, ldy, ldy, 1.0, 1.0, m->alpha, m->alpha, part, s))) return rc;
+  }
+  build_w_kernel<<<ceil_div(Npad, 128), 128, 0, s>>>(m->alpha, ldy, m->G, Npad, n, p, m->W);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }
@@ -410,7 +514,7 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
   rc = bcbf_trtri(m->L, m->dinv, m->Linv, m->Kstar, Npad, Npad, s);
   if (rc) return rc;
   BCBF_CUDA(cudaEventRecord(ev[3], s));
-  rc = finish_fit_from_factor(m);
+  rc = finish_fit_from_factor(m, true);
   if (rc) return rc;
   m->oz_split_ms = 0.0;
   if (m->var_path == 1 && Npad <= bcbf_oz_max_npad() && (rc = ensure_oz_digits(m, s, true))) return rc;

@@ -464,6 +464,16 @@ extern "C" int bcbf_check_info(const int* info, void* stream_) {
   return BCBF_OK;
 }
 
+// Levels of the divide-and-conquer triangular inverse with half-size h >= kTrtriI8MinH run their two products per pair on
+// the int8 tensor cores (csrc/ozaki.cu); smaller levels and ensembles stay on the DMMA GEMM.  bcbf_set_trtri_i8(0) turns
+// it off (all levels on the FP64 pipe).
+static int g_trtri_i8 = 1;
+constexpr int kTrtriI8MinH = 2048;
+extern "C" int bcbf_set_trtri_i8(int on) {
+  g_trtri_i8 = on ? 1 : 0;
+  return BCBF_OK;
+}
+
 // R independent triangular inverses (stride sL between factor-sized matrices, sD between dinv block sets).
 static int trtri_impl(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad, int R,
                       long long sL, long long sD, cudaStream_t stream) {
@@ -497,6 +507,19 @@ static int trtri_impl(const double* L, const double* dinv, double* Linv, double*
         stride = sL;
       }
       if (batch == 0) continue;
+      if (R == 1 && g_trtri_i8 && h >= kTrtriI8MinH && M2 % kBlk == 0) {
+        // large levels (94 % of the flops): the two products on the int8 tensor cores (bcbf_oz_gemm, FP64-accurate)
+        for (int b = 0; b < batch; ++b) {
+          const long long o = r0 + (long long)b * 2 * h;
+          int rc = bcbf_oz_gemm(M2, h, h, 1.0, L + (o + h) * ld + o, ld, Linv + o * (ld + 1), ld,
+                                scratch + (o + h) * ld + o, ld, /*B lower triangular*/ 2, stream);
+          if (rc) return rc;
+          rc = bcbf_oz_gemm(M2, h, M2, -1.0, Linv + (o + h) * (ld + 1), ld, scratch + (o + h) * ld + o, ld,
+                            Linv + (o + h) * ld + o, ld, /*A lower triangular*/ 1, stream);
+          if (rc) return rc;
+        }
+        continue;
+      }
       GemmArgs t{};  // T = L21 * X11
       t.A = L + (r0 + h) * ld + r0; t.lda = ld;
       t.B = Linv + r0 * (ld + 1); t.ldb = ld;

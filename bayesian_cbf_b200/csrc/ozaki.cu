@@ -465,7 +465,8 @@ struct Ws {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-static Ws g_ws[5][64];  // 0: frakB digits, 1: colmax, 2: colscale, 3: Spart, 4: mean partials
+static Ws g_ws[9][64];  // 0: frakB digits, 1: colmax, 2: colscale, 3: Spart, 4: mean partials; GEMM: 5: A digits,
+                         // 6: B digits, 7: row scales, 8: column maxima + scales
 
 static int workspace(int slot, size_t bytes, void** out) {
   int dev = 0;
@@ -595,6 +596,341 @@ static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, con
   return BCBF_OK;
 }
 
+// ======================================================================================================================
+// General FP64-accurate GEMM on the int8 tensor cores:  C (M,N) = alpha A (M,K) B (K,N), row-major, with optional
+// triangular structure of one operand.  Same digit arithmetic, MMA pattern and pipeline as oz_var_kernel; the epilogue
+// stores the recombined FP64 tile.  Used by bcbf_trtri for the large levels of the triangular inverse
+// (T = L21 X11, X21 = -X22 T: control_affine_model.py:565's solves become products with L^-1).
+// ======================================================================================================================
+constexpr int kTriGemmNone = 0, kTriGemmALower = 1, kTriGemmBLower = 2;
+
+// Inner-dimension balancing: C = (A D)(D^-1 B) for any diagonal D.  With one scale per row of A and per column of B, an
+// operand whose magnitude falls steeply along k (rows of a Cholesky factor) loses the bits of its small entries even
+// though they meet large entries of the other operand (rows of its inverse).  D_k = 2^round(log2 sqrt(rowmax_k(B) /
+// colmax_k(A))) equalises the two profiles; powers of two, so the products are unchanged.
+__global__ void colmax_of_a_kernel(const double* __restrict__ A, int lda, int M, int K, int tri, int rows_per_block,
+                                   unsigned long long* __restrict__ amax) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  int i0 = blockIdx.y * rows_per_block;
+  const int i1 = min(M, i0 + rows_per_block);
+  if (tri == kTriGemmALower) i0 = max(i0, k);
+  double mx = 0.0;
+  for (int i = i0; i < i1; ++i) mx = fmax(mx, fabs(A[(long long)i * lda + k]));
+  atomicMax(amax + k, static_cast<unsigned long long>(__double_as_longlong(mx)));
+}
+
+__global__ void kscale_kernel(const double* __restrict__ B, int ldb, int K, int N, int tri,
+                              const unsigned long long* __restrict__ amax, double* __restrict__ kscale) {
+  const int k = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (k >= K) return;
+  const int jend = tri == kTriGemmBLower ? min(N, k + 1) : N;
+  double mx = 0.0;
+  for (int j = lane; j < jend; j += 32) mx = fmax(mx, fabs(B[(long long)k * ldb + j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) {
+    const double ca = __longlong_as_double(static_cast<long long>(amax[k]));
+    double d = 1.0;
+    if (mx > 0.0 && ca > 0.0) {
+      int eb, ea;
+      frexp(mx, &eb);
+      frexp(ca, &ea);
+      int e = eb - ea;               // log2(rowmax_B / colmax_A), rounded; D = 2^(e/2)
+      e = (e >= 0 ? e + 1 : e) / 2;
+      d = ldexp(1.0, e);
+    }
+    kscale[k] = d;
+  }
+}
+
+__global__ void rowscale_rect_kernel(const double* __restrict__ A, int lda, int M, int K, int tri,
+                                     const double* __restrict__ kscale, double* __restrict__ rowscale) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= M) return;
+  const int kend = tri == kTriGemmALower ? min(K, row + 1) : K;
+  double mx = 0.0;
+  for (int k = lane; k < kend; k += 32) mx = fmax(mx, fabs(A[(long long)row * lda + k]) * kscale[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) rowscale[row] = scale_of(mx);
+}
+
+// A D (M,K) row-major -> blobs [(I nks + ks)] of [digit][row group 16][k chunk 2][row 8][16 B]; entries with k > row are
+// taken as zero when A is lower triangular (the strictly upper part of the storage is not read)
+__global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ A, int lda, int K, int tri,
+                                                         const double* __restrict__ kscale,
+                                                         const double* __restrict__ rowscale,
+                                                         int8_t* __restrict__ blob) {
+  const int kc = blockIdx.x, I = blockIdx.y;  // 128-wide k block, 128-row block
+  const int nks = K / KSTEP;
+  const int r = threadIdx.x % TM, half = threadIdx.x / TM;
+  const long long row = (long long)I * TM + r;
+  const double inv = 1.0 / rowscale[row];
+  int8_t* base = blob + ((long long)I * nks + 4LL * kc) * A_STEP;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int c16 = half * 4 + c;
+    const int k0 = kc * TM + c16 * 16;
+    if (k0 >= K) break;
+    const double* src = A + row * lda + k0;
+    uint32_t w[S][4];
+#pragma unroll
+    for (int s = 0; s < S; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const double v = (tri == kTriGemmALower && k0 + k > row) ? 0.0 : src[k] * __ldg(kscale + k0 + k);
+      int d[S];
+      digits_of(v * inv, d);
+#pragma unroll
+      for (int s = 0; s < S; ++s) w[s][k / 4] |= static_cast<uint32_t>(d[s] & 0xFF) << (8 * (k % 4));
+    }
+    int8_t* dst = base + (long long)(c16 / 2) * A_STEP + (r / 8) * 256 + (c16 % 2) * 128 + (r % 8) * 16;
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      *reinterpret_cast<uint4*>(dst + s * (TM * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+  }
+}
+
+// column maxima of D^-1 B, B (K,N) row-major (entries with k < j are taken as zero when B is lower triangular)
+__global__ void colmax_rect_kernel(const double* __restrict__ B, int ldb, int K, int N, int tri, int rows_per_block,
+                                   const double* __restrict__ kscale, unsigned long long* __restrict__ colmax) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  int k0 = blockIdx.y * rows_per_block;
+  const int k1 = min(K, k0 + rows_per_block);
+  if (tri == kTriGemmBLower) k0 = max(k0, j);
+  double mx = 0.0;
+  for (int k = k0; k < k1; ++k) mx = fmax(mx, fabs(B[(long long)k * ldb + j]) / __ldg(kscale + k));
+  atomicMax(colmax + j, static_cast<unsigned long long>(__double_as_longlong(mx)));
+}
+
+// D^-1 B (K,N) row-major -> blobs [(J nks + ks)] of [digit][column group 8][k chunk 2][column 8][16 B], one thread per
+// column and 16 consecutive k
+__global__ void __launch_bounds__(128) split_cols_kernel(const double* __restrict__ B, int ldb, int K, int N, int tri,
+                                                         const double* __restrict__ kscale,
+                                                         const unsigned long long* __restrict__ colmax,
+                                                         int8_t* __restrict__ blob, double* __restrict__ colscale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const int k0 = blockIdx.y * 16;
+  const int J = j / TN, c = j % TN;
+  const double sc = scale_of(__longlong_as_double(static_cast<long long>(colmax[j])));
+  const double inv = 1.0 / sc;
+  if (blockIdx.y == 0) colscale[j] = sc;
+  uint32_t w[S][4];
+#pragma unroll
+  for (int s = 0; s < S; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+  if (!(tri == kTriGemmBLower && k0 + 15 < j)) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const double v =
+          (tri == kTriGemmBLower && k0 + k < j) ? 0.0 : B[(long long)(k0 + k) * ldb + j] / __ldg(kscale + k0 + k);
+      int d[S];
+      digits_of(v * inv, d);
+#pragma unroll
+      for (int s = 0; s < S; ++s) w[s][k / 4] |= static_cast<uint32_t>(d[s] & 0xFF) << (8 * (k % 4));
+    }
+  }
+  int8_t* dst = blob + ((long long)J * (K / KSTEP) + k0 / KSTEP) * B_STEP + ((k0 / 16) % 2) * 128 + (c / 8) * 256 +
+                (c % 8) * 16;
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+    *reinterpret_cast<uint4*>(dst + s * (TN * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+}
+
+struct GemmI8Args {
+  const int8_t* Ablob;
+  const int8_t* Bblob;
+  const double* rowscale;
+  const double* colscale;
+  double* C;
+  long long ldc;
+  double alpha;
+  int nI, nJ, nks, tri;
+  long long total_tiles;
+};
+
+// tile t -> (I, J) and its K-step range.  Order: row-block groups of 4 x all column tiles (operand sharing through L2 as
+// in oz_var_kernel); with a lower-triangular A the longest row blocks come first.
+__device__ __forceinline__ bool gemm_tile_of(const GemmI8Args& a, long long t, int& I, int& J, int& ks0, int& ks1) {
+  const int per_group = 4 * a.nJ;
+  const int g = static_cast<int>(t / per_group), r = static_cast<int>(t % per_group);
+  J = r >> 2;
+  const int ii = ((r & 3) + static_cast<int>((t >> 2) & 3)) & 3;
+  I = a.nI - 1 - (4 * g + ii);
+  if (I < 0) return false;
+  ks0 = a.tri == kTriGemmBLower ? (J * TN) / KSTEP : 0;
+  ks1 = a.tri == kTriGemmALower ? min(a.nks, 4 * (I + 1)) : a.nks;
+  return ks1 > ks0;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) oz_gemm_kernel(GemmI8Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* tmem_full = empty + NSTAGE;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  double* cs = reinterpret_cast<double*>(smem + NSTAGE * STAGE + 128);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kEpiThreads);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int I, J, ks0, ks1;
+        if (!gemm_tile_of(a, t, I, J, ks0, ks1)) continue;
+        const int8_t* ap = a.Ablob + (long long)I * a.nks * A_STEP;
+        const int8_t* bp = a.Bblob + (long long)J * a.nks * B_STEP;
+        for (int ks = ks0; ks < ks1; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* dst = smem + stage * STAGE;
+          mbar_arrive_expect_tx(&full[stage], STAGE);
+          bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
+          bulk_g2s(dst + A_STEP, bp + (long long)ks * B_STEP, B_STEP, &full[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, tile_iter = 0;
+      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int I, J, ks0, ks1;
+        if (!gemm_tile_of(a, t, I, J, ks0, ks1)) continue;
+        mbar_wait(tmem_empty, (tile_iter & 1u) ^ 1u);
+        tc_fence_after();
+        for (int ks = ks0; ks < ks1; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE);
+          issue_kstep(tmem, sa, sa + A_STEP, ks == ks0);
+          mma_commit(&empty[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(tmem_full);
+        ++tile_iter;
+      }
+    }
+  } else {
+    const int tid = threadIdx.x;
+    uint32_t tile_iter = 0;
+    for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int I, J, ks0, ks1;
+      if (!gemm_tile_of(a, t, I, J, ks0, ks1)) continue;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous tile's column scales
+      if (tid < TN) cs[tid] = a.colscale[(long long)J * TN + tid];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tmem_full, tile_iter & 1u);
+      tc_fence_after();
+      const uint32_t tbase = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+      const long long row = (long long)I * TM + warp * 32 + lane;
+      const double rs = a.alpha * a.rowscale[row];
+      double* crow = a.C + row * a.ldc + (long long)J * TN;
+#pragma unroll
+      for (int c4 = 0; c4 < TN / 16; ++c4) {
+        double v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0;
+#pragma unroll
+        for (int d = S - 1; d >= 0; --d) {
+          const double w = __longlong_as_double((1023LL - 8 * (d + 2)) << 52);
+          uint32_t r[16];
+          tmem_ld16(tbase + d * TN + c4 * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fma(static_cast<double>(static_cast<int>(r[j])), w, v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 2)
+          *reinterpret_cast<double2*>(crow + c4 * 16 + j) =
+              make_double2(v[j] * (rs * cs[c4 * 16 + j]), v[j + 1] * (rs * cs[c4 * 16 + j + 1]));
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty);
+      ++tile_iter;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+static int run_gemm(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C,
+                    int ldc, int tri, cudaStream_t stream) {
+  const int nI = M / TM, nJ = N / TN, nks = K / KSTEP;
+  void *ablob, *bblob, *rows, *cols;
+  int rc;
+  if ((rc = workspace(5, (size_t)nI * nks * A_STEP, &ablob))) return rc;
+  if ((rc = workspace(6, (size_t)nJ * nks * B_STEP, &bblob))) return rc;
+  if ((rc = workspace(7, sizeof(double) * (size_t)M, &rows))) return rc;
+  if ((rc = workspace(8, 16 * ((size_t)N + (size_t)K), &cols))) return rc;
+  // workspace 8: [colmax N | colscale N | amax K | kscale K]
+  unsigned long long* colmax = static_cast<unsigned long long*>(cols);
+  double* colscale = reinterpret_cast<double*>(colmax + N);
+  unsigned long long* amax = reinterpret_cast<unsigned long long*>(colscale + N);
+  double* kscale = reinterpret_cast<double*>(amax + K);
+  BCBF_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned long long) * (size_t)K, stream));
+  colmax_of_a_kernel<<<dim3(ceil_div(K, 128), ceil_div(M, 256)), 128, 0, stream>>>(A, lda, M, K, tri, 256, amax);
+  BCBF_LAUNCH_CHECK();
+  kscale_kernel<<<ceil_div(K, 8), 256, 0, stream>>>(B, ldb, K, N, tri, amax, kscale);
+  BCBF_LAUNCH_CHECK();
+  rowscale_rect_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(A, lda, M, K, tri, kscale, static_cast<double*>(rows));
+  BCBF_LAUNCH_CHECK();
+  split_rows_kernel<<<dim3(ceil_div(K, TM), nI), 256, 0, stream>>>(A, lda, K, tri, kscale,
+                                                                  static_cast<const double*>(rows),
+                                                                  static_cast<int8_t*>(ablob));
+  BCBF_LAUNCH_CHECK();
+  BCBF_CUDA(cudaMemsetAsync(colmax, 0, sizeof(unsigned long long) * (size_t)N, stream));
+  colmax_rect_kernel<<<dim3(ceil_div(N, 128), ceil_div(K, 256)), 128, 0, stream>>>(B, ldb, K, N, tri, 256, kscale,
+                                                                                   colmax);
+  BCBF_LAUNCH_CHECK();
+  split_cols_kernel<<<dim3(ceil_div(N, 128), K / 16), 128, 0, stream>>>(B, ldb, K, N, tri, kscale, colmax,
+                                                                       static_cast<int8_t*>(bblob), colscale);
+  BCBF_LAUNCH_CHECK();
+  GemmI8Args a{};
+  a.Ablob = static_cast<const int8_t*>(ablob);
+  a.Bblob = static_cast<const int8_t*>(bblob);
+  a.rowscale = static_cast<const double*>(rows);
+  a.colscale = colscale;
+  a.C = C;
+  a.ldc = ldc;
+  a.alpha = alpha;
+  a.nI = nI;
+  a.nJ = nJ;
+  a.nks = nks;
+  a.tri = tri;
+  a.total_tiles = (long long)ceil_div(nI, 4) * 4 * nJ;
+  int dev = 0, sms = 148;
+  BCBF_CUDA(cudaGetDevice(&dev));
+  BCBF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  BCBF_CUDA(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const int grid = a.total_tiles < sms ? static_cast<int>(a.total_tiles) : sms;
+  oz_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
 }  // namespace oz
 }  // namespace bcbf
 
@@ -667,6 +1003,30 @@ extern "C" int bcbf_oz_debug_counters(int enable, unsigned long long out[8]) {
     oz::g_dbg = nullptr;
   }
   return BCBF_OK;
+}
+
+// Pre-size the operand-digit workspaces of bcbf_oz_gemm (so that a timed caller does not pay cudaMalloc).
+extern "C" int bcbf_oz_gemm_reserve(int M, int N, int K) {
+  BCBF_REQUIRE(M > 0 && N > 0 && K > 0, "bcbf_oz_gemm_reserve: M=%d N=%d K=%d", M, N, K);
+  void* p = nullptr;
+  int rc;
+  if ((rc = oz::workspace(5, (size_t)ceil_div(M, oz::TM) * ceil_div(K, oz::KSTEP) * oz::A_STEP, &p))) return rc;
+  if ((rc = oz::workspace(6, (size_t)ceil_div(N, oz::TN) * ceil_div(K, oz::KSTEP) * oz::B_STEP, &p))) return rc;
+  if ((rc = oz::workspace(7, sizeof(double) * (size_t)M, &p))) return rc;
+  return oz::workspace(8, 16 * ((size_t)N + (size_t)K), &p);
+}
+
+extern "C" int bcbf_oz_gemm(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                            double* C, int ldc, int tri, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(A && B && C, "bcbf_oz_gemm: null pointer");
+  BCBF_REQUIRE(M > 0 && N > 0 && K > 0 && M % oz::TM == 0 && N % oz::TN == 0 && K % oz::KSTEP == 0 && K <= oz::kMaxNpad,
+               "bcbf_oz_gemm: M=%d (multiple of 128), N=%d (of 64), K=%d (of 32, <= %d)", M, N, K, oz::kMaxNpad);
+  BCBF_REQUIRE(lda >= K && ldb >= N && ldc >= N && ldc % 2 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+               "bcbf_oz_gemm: lda=%d ldb=%d ldc=%d (ldc even, C 16-byte aligned)", lda, ldb, ldc);
+  BCBF_REQUIRE(tri >= 0 && tri <= 2 && (tri != oz::kTriGemmALower || M == K) && (tri != oz::kTriGemmBLower || K == N),
+               "bcbf_oz_gemm: tri=%d needs a square triangular operand", tri);
+  return oz::run_gemm(M, N, K, alpha, A, lda, B, ldb, C, ldc, tri, stream);
 }
 
 // CTAs per cluster of oz_var_kernel: 1 (default) or 2 (the pair multicasts the L^-1 digits to each other).

@@ -206,6 +206,19 @@ def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, w
     return Mk, Bk
 
 
+def oz_gemm(A, B, alpha=1.0, tri=0, out=None):
+    """C = alpha A B on the int8 tensor cores, FP64-accurate (bcbf_oz_gemm).  A (M,K), B (K,N) row-major views (last
+    stride 1); M % 128 == 0, N % 64 == 0, K % 32 == 0.  tri: 0, 1 (A lower triangular), 2 (B lower triangular)."""
+    assert A.is_cuda and B.is_cuda and A.dtype is torch.float64 and B.dtype is torch.float64
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    M, K = A.shape
+    N = B.shape[1]
+    C = torch.empty(M, N, dtype=torch.float64, device=A.device) if out is None else out
+    check(_lib.load().bcbf_oz_gemm(M, N, K, float(alpha), _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(C), C.stride(0),
+                                   int(tri), _stream()))
+    return C
+
+
 def oz_max_npad():
     return _lib.load().bcbf_oz_max_npad()
 

@@ -114,6 +114,9 @@ int bcbf_check_info(const int* info, void* stream);
  * control_affine_model.py:545,565,575,1053).                                                              */
 int bcbf_trtri(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad,
                void* stream);
+/* The levels of the divide-and-conquer inverse with half-size >= 2048 run on the int8 tensor cores (bcbf_oz_gemm) by
+ * default; 0 keeps every level on the FP64 pipe. */
+int bcbf_set_trtri_i8(int on);
 
 /* C (M,Ncols; ldc) = alpha * op(A) * B + beta * C  with A = a lower-triangular factor-sized matrix
  * (Npad,Npad; lda): op = identity (trans=0) or transpose (trans=1).  B (Npad,Ncols; ldb).
@@ -182,6 +185,14 @@ int bcbf_posterior_blocks_i8(const void* digits, const double* rowscale, int Npa
 int bcbf_oz_set_cluster(int ctas);
 /* Development aid: pipeline counters of oz_var_kernel (see csrc/ozaki.cu). */
 int bcbf_oz_debug_counters(int enable, unsigned long long out[8]);
+/* General FP64-accurate GEMM on the int8 tensor cores (same digit splitting; csrc/ozaki.cu: oz_gemm_kernel):
+ *   C (M,N; ldc) = alpha * A (M,K; lda) * B (K,N; ldb),  row-major, M % 128 == 0, N % 64 == 0, K % 32 == 0, K <= bcbf_oz_max_npad();
+ *   tri = 0, or 1: A is square lower triangular (its strictly upper storage is not read), or 2: B is square lower triangular.
+ * bcbf_trtri uses it for the large levels of the triangular inverse.                                                  */
+int bcbf_oz_gemm(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                 int tri, void* stream);
+/* Pre-size bcbf_oz_gemm's internal workspaces for products up to (M,K) x (K,N). */
+int bcbf_oz_gemm_reserve(int M, int N, int K);
 /* CUDA-event timing of oz_var_kernel launches (bench.py's roofline leg), like bcbf_profile_enable/read. */
 int bcbf_oz_profile_enable(int on);
 int bcbf_oz_profile_read(double* total_ms, int* launches);

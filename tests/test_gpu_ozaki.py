@@ -169,3 +169,66 @@ def test_model_handle_int8_other_control_dimensions(n, m):
     assert np.abs(out['Bk'] - Bk_o.numpy()).max() / prior < 1e-9
     assert np.abs(out['svar'] - svar_o.numpy()).max() / prior < 1e-8
     assert np.abs(out['Mk'] - Mk_o.numpy()).max() < 1e-6 * np.abs(Mk_o.numpy()).max()
+
+
+@pytest.mark.parametrize('M,N,K,tri', [(256, 192, 160, 0), (384, 128, 384, 1), (128, 256, 256, 2), (1024, 1024, 1024, 0),
+                                       (2048, 2048, 2048, 1), (2048, 2048, 2048, 2)])
+def test_oz_gemm_matches_float64_matmul(M, N, K, tri):
+    """bcbf_oz_gemm against torch float64 matmul on operands with a wide dynamic range inside rows / columns; error
+    measured against |A| |B| (the quantity FP64 rounding errors scale with)."""
+    from bayesian_cbf_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K + tri)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64) * torch.exp2(torch.randint(-12, 4, (M, K), generator=g).double())
+    B = torch.randn(K, N, generator=g, dtype=torch.float64) * torch.exp2(torch.randint(-12, 4, (K, N), generator=g).double())
+    junk = 1e300                                         # the unread triangle may hold anything
+    if tri == 1:
+        A = torch.tril(A) + torch.triu(torch.full_like(A, junk), 1)
+    if tri == 2:
+        B = torch.tril(B) + torch.triu(torch.full_like(B, junk), 1)
+    C = ops.oz_gemm(A.cuda(), B.cuda(), alpha=-0.75, tri=tri).cpu()
+    Ar = torch.tril(A) if tri == 1 else A
+    Br = torch.tril(B) if tri == 2 else B
+    ref = -0.75 * (Ar @ Br)
+    assert torch.isfinite(C).all()
+    # 56-bit digits below a per-row / per-column power-of-two scale: the error scales with rowmax_i * colmax_j (not with
+    # |A||B| entry by entry); worst case 10 K 2^-58 of scale_i scale_j <= K 2^-50 rowmax colmax
+    bound = Ar.abs().amax(1, keepdim=True) * Br.abs().amax(0, keepdim=True)
+    assert ((C - ref).abs() / bound).max().item() < K * 2.0 ** -50
+    if tri == 0:  # full rows and columns: also within a few hundred ulps of what FP64 rounding errors scale with
+        assert ((C - ref).abs() / (Ar.abs() @ Br.abs()).clamp_min(1e-300)).max().item() < 1e-13
+    # embedded in a larger buffer (leading dimensions > extents, as bcbf_trtri calls it)
+    big = torch.zeros(M + 128, N + 64, dtype=torch.float64, device='cuda')
+    Ab = torch.zeros(M, K + 32, dtype=torch.float64, device='cuda')
+    Ab[:, :K] = A.cuda()
+    ops.oz_gemm(Ab[:, :K], B.cuda(), alpha=-0.75, tri=tri, out=big[128:, 64:])
+    assert torch.equal(big[128:, 64:].cpu(), C) and big[:128].abs().max().item() == 0.0
+
+
+def test_trtri_large_levels_on_int8_match_the_fp64_pipe():
+    """bcbf_trtri runs its levels with half-size >= 2048 through bcbf_oz_gemm: same inverse as the all-DMMA run to the
+    conditioning-limited level, and the same residual |L^-1 L - I|."""
+    from bayesian_cbf_b200 import _lib, ops
+    lib = _lib.load()
+    N = 4200                                            # Npad = 4224: one full 2048 pair, a clipped 4096 pair
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(17, N, 3, 2, 8, box=3.0)
+    UH = O.homogeneous(U)
+    res = {}
+    try:
+        for on in (0, 1):
+            assert lib.bcbf_set_trtri_i8(on) == 0
+            Kb = ops.gram_train(_d(X), _d(UH), _d(hyp.B), _d(hyp.lengthscale), float(hyp.outputscale))
+            L, dinv = ops.potrf_(Kb, N, _d(jit), 1e-5)
+            res[on] = (L, ops.trtri(L, dinv))
+    finally:
+        lib.bcbf_set_trtri_i8(1)
+    L, Linv0 = res[0]
+    Linv1 = res[1][1]
+    scale = Linv0.abs().max().item()
+    assert (Linv1 - Linv0).abs().max().item() < 1e-9 * scale
+    assert torch.equal(torch.triu(Linv1, 1), torch.zeros_like(Linv1))
+    Npad = L.shape[0]
+    I = torch.eye(Npad, dtype=torch.float64, device='cuda')
+    r0 = (Linv0 @ L - I).abs().max().item()
+    r1 = (Linv1 @ L - I).abs().max().item()
+    # measured 6.1e-11 against 1.5e-11 (without the inner-dimension balancing of bcbf_oz_gemm: 6.4e-9)
+    assert r1 < 10 * r0 + 1e-12, (r0, r1)
