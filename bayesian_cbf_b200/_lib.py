@@ -96,7 +96,10 @@ _SIGNATURES = {
     'bcbf_oz_debug_counters': (c_int, [c_int, POINTER(ctypes.c_ulonglong * 8)]),
     'bcbf_oz_gemm': (c_int, [c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
     'bcbf_oz_gemm_reserve': (c_int, [c_int, c_int, c_int]),
+    'bcbf_oz_update': (c_int, [c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
+    'bcbf_oz_update_reserve': (c_int, [c_int, c_int, c_int]),
     'bcbf_set_trtri_i8': (c_int, [c_int]),
+    'bcbf_set_potrf_i8': (c_int, [c_int]),
     'bcbf_oz_set_cluster': (c_int, [c_int]),
     'bcbf_oz_profile_enable': (c_int, [c_int]),
     'bcbf_oz_profile_read': (c_int, [POINTER(c_double), POINTER(c_int)]),

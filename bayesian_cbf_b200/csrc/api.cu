@@ -415,6 +415,7 @@ extern "C" int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int 
     while (2 * hmax < Npad) hmax *= 2;
     int rc = bcbf_oz_gemm_reserve(hmax, hmax, hmax);
     if (rc) return rc;
+    if ((rc = bcbf_oz_update_reserve(Npad, Npad, 512))) return rc;  // bcbf_potrf's trailing updates
   }
   // hyper-parameter block on the device: [lengthscale(8) | B(16) | C(32) | Ct(32) | A(64)]
   double hbuf[256];

@@ -342,6 +342,15 @@ static LookAhead* get_lookahead() {
 
 // R independent factorisations of equal size (R = 1: the single-matrix entry point).  Strides in elements:
 // sA between matrices, sD between dinv blocks sets, sJ between jitter vectors; info is int[R].
+// Trailing updates of bcbf_potrf with at least kPotrfI8MinRows rows run on the int8 tensor cores (csrc/ozaki.cu);
+// bcbf_set_potrf_i8(0) keeps everything on the FP64 pipe.
+static int g_potrf_i8 = 1;
+constexpr int kPotrfI8MinRows = 1024;
+extern "C" int bcbf_set_potrf_i8(int on) {
+  g_potrf_i8 = on ? 1 : 0;
+  return BCBF_OK;
+}
+
 static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale, double* dinv,
                       int* info, int R, long long sA, long long sD, long long sJ, cudaStream_t stream) {
   BCBF_REQUIRE(A && dinv && info, "bcbf_potrf: null pointer");
@@ -412,11 +421,19 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
         BCBF_CUDA(cudaEventRecord(look->panels_done, cs));
         BCBF_CUDA(cudaStreamWaitEvent(stream, look->panels_done, 0));
         const double* P2 = P + (long long)strip * ld;
-        GemmArgs t2{};
-        t2.A = P2; t2.lda = ld; t2.B = P2; t2.ldb = ld;
-        t2.C = A + (long long)(c1 + strip) * (ld + 1); t2.ldc = ld;
-        t2.M = rows - strip; t2.N = rows - strip; t2.K = Kp; t2.alpha = -1.0; t2.beta = 1.0; t2.tri = kTriLowerOut;
-        BCBF_CUDA((launch_gemm<true, true>(t2, 1, stream)));
+        if (g_potrf_i8 && rows - strip >= kPotrfI8MinRows && Kp % 32 == 0) {
+          // the bulk of the N^3/3 flops: lower tiles -= P2 P2^T on the int8 tensor cores (bcbf_oz_update, FP64-accurate,
+          // one short-lived CTA per tile so that the high-priority sweep keeps finding free SMs)
+          int rc = bcbf_oz_update(rows - strip, rows - strip, Kp, -1.0, P2, ld, P2, ld,
+                                  A + (long long)(c1 + strip) * (ld + 1), ld, 1, stream);
+          if (rc) return rc;
+        } else {
+          GemmArgs t2{};
+          t2.A = P2; t2.lda = ld; t2.B = P2; t2.ldb = ld;
+          t2.C = A + (long long)(c1 + strip) * (ld + 1); t2.ldc = ld;
+          t2.M = rows - strip; t2.N = rows - strip; t2.K = Kp; t2.alpha = -1.0; t2.beta = 1.0; t2.tri = kTriLowerOut;
+          BCBF_CUDA((launch_gemm<true, true>(t2, 1, stream)));
+        }
         BCBF_CUDA(cudaEventRecord(look->t2_done, stream));
       } else {
         if (look) BCBF_CUDA(cudaStreamWaitEvent(cs, look->t2_done, 0));

@@ -465,8 +465,8 @@ struct Ws {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-static Ws g_ws[9][64];  // 0: frakB digits, 1: colmax, 2: colscale, 3: Spart, 4: mean partials; GEMM: 5: A digits,
-                         // 6: B digits, 7: row scales, 8: column maxima + scales
+static Ws g_ws[12][64];  // 0: frakB digits, 1: colmax, 2: colscale, 3: Spart, 4: mean partials; GEMM: 5: A digits,
+                         // 6: B digits, 7: row scales, 8: column maxima + scales; update: 9: PA digits, 10: PB digits, 11: scales
 
 static int workspace(int slot, size_t bytes, void** out) {
   int dev = 0;
@@ -650,28 +650,31 @@ __global__ void rowscale_rect_kernel(const double* __restrict__ A, int lda, int 
   if (row >= M) return;
   const int kend = tri == kTriGemmALower ? min(K, row + 1) : K;
   double mx = 0.0;
-  for (int k = lane; k < kend; k += 32) mx = fmax(mx, fabs(A[(long long)row * lda + k]) * kscale[k]);
+  for (int k = lane; k < kend; k += 32) mx = fmax(mx, fabs(A[(long long)row * lda + k]) * (kscale ? kscale[k] : 1.0));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) rowscale[row] = scale_of(mx);
 }
 
-// A D (M,K) row-major -> blobs [(I nks + ks)] of [digit][row group 16][k chunk 2][row 8][16 B]; entries with k > row are
-// taken as zero when A is lower triangular (the strictly upper part of the storage is not read)
-__global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ A, int lda, int K, int tri,
-                                                         const double* __restrict__ kscale,
-                                                         const double* __restrict__ rowscale,
-                                                         int8_t* __restrict__ blob) {
-  const int kc = blockIdx.x, I = blockIdx.y;  // 128-wide k block, 128-row block
+// A D (M,K) row-major -> blobs [(I nks + ks)] of [digit][row group ROWS/8][k chunk 2][row 8][16 B]; entries with k > row
+// are taken as zero when A is lower triangular (the strictly upper part of the storage is not read).  ROWS = 128: the
+// MMA's M-side operand; ROWS = 64: the N-side operand of a product with A^T (rank-k updates C += alpha P P^T).
+template <int ROWS>
+__global__ void __launch_bounds__(2 * ROWS) split_rows_kernel(const double* __restrict__ A, int lda, int K, int tri,
+                                                              const double* __restrict__ kscale,
+                                                              const double* __restrict__ rowscale,
+                                                              int8_t* __restrict__ blob) {
+  constexpr int STEP = S * ROWS * KSTEP;
+  const int kc = blockIdx.x, I = blockIdx.y;  // 128-wide k block, ROWS-row block
   const int nks = K / KSTEP;
-  const int r = threadIdx.x % TM, half = threadIdx.x / TM;
-  const long long row = (long long)I * TM + r;
+  const int r = threadIdx.x % ROWS, half = threadIdx.x / ROWS;
+  const long long row = (long long)I * ROWS + r;
   const double inv = 1.0 / rowscale[row];
-  int8_t* base = blob + ((long long)I * nks + 4LL * kc) * A_STEP;
+  int8_t* base = blob + ((long long)I * nks + 4LL * kc) * STEP;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const int c16 = half * 4 + c;
-    const int k0 = kc * TM + c16 * 16;
+    const int k0 = kc * 128 + c16 * 16;
     if (k0 >= K) break;
     const double* src = A + row * lda + k0;
     uint32_t w[S][4];
@@ -679,16 +682,17 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
     for (int s = 0; s < S; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const double v = (tri == kTriGemmALower && k0 + k > row) ? 0.0 : src[k] * __ldg(kscale + k0 + k);
+      const double v =
+          (tri == kTriGemmALower && k0 + k > row) ? 0.0 : src[k] * (kscale ? __ldg(kscale + k0 + k) : 1.0);
       int d[S];
       digits_of(v * inv, d);
 #pragma unroll
       for (int s = 0; s < S; ++s) w[s][k / 4] |= static_cast<uint32_t>(d[s] & 0xFF) << (8 * (k % 4));
     }
-    int8_t* dst = base + (long long)(c16 / 2) * A_STEP + (r / 8) * 256 + (c16 % 2) * 128 + (r % 8) * 16;
+    int8_t* dst = base + (long long)(c16 / 2) * STEP + (r / 8) * 256 + (c16 % 2) * 128 + (r % 8) * 16;
 #pragma unroll
     for (int s = 0; s < S; ++s)
-      *reinterpret_cast<uint4*>(dst + s * (TM * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+      *reinterpret_cast<uint4*>(dst + s * (ROWS * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
   }
 }
 
@@ -897,7 +901,7 @@ static int run_gemm(int M, int N, int K, double alpha, const double* A, int lda,
   BCBF_LAUNCH_CHECK();
   rowscale_rect_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(A, lda, M, K, tri, kscale, static_cast<double*>(rows));
   BCBF_LAUNCH_CHECK();
-  split_rows_kernel<<<dim3(ceil_div(K, TM), nI), 256, 0, stream>>>(A, lda, K, tri, kscale,
+  split_rows_kernel<TM><<<dim3(ceil_div(K, TM), nI), 256, 0, stream>>>(A, lda, K, tri, kscale,
                                                                   static_cast<const double*>(rows),
                                                                   static_cast<int8_t*>(ablob));
   BCBF_LAUNCH_CHECK();
@@ -927,6 +931,171 @@ static int run_gemm(int M, int N, int K, double alpha, const double* A, int lda,
   BCBF_CUDA(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int grid = a.total_tiles < sms ? static_cast<int>(a.total_tiles) : sms;
   oz_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+// ======================================================================================================================
+// Rank-K update on the int8 tensor cores:  C (M,N) += alpha PA (M,K) PB (N,K)^T, all tiles or only those that touch the
+// lower triangle (the Cholesky trailing update A22 -= L21 L21^T, make_psd's factorisation control_affine_model.py:907).
+// One CTA per 128 x 64 tile, NOT persistent: the look-ahead of bcbf_potrf needs SMs to come free every few microseconds
+// for the high-priority panel kernels.  Same digit arithmetic / MMA pattern as above; the epilogue is a read-modify-write.
+// ======================================================================================================================
+struct UpdateArgs {
+  const int8_t* Ablob;
+  const int8_t* Bblob;
+  const double* rowscaleA;
+  const double* rowscaleB;
+  double* C;
+  long long ldc;
+  double alpha;
+  int nJ, nks, lower;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) oz_update_kernel(UpdateArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* tmem_full = empty + NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 2);
+  double* cs = reinterpret_cast<double*>(smem + NSTAGE * STAGE + 128);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  int I, J;
+  if (a.lower) {  // tile t = I (I + 1) + J,  0 <= J < 2 I + 2
+    const long long t = blockIdx.x;
+    I = static_cast<int>((sqrt(4.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
+    while ((long long)I * (I + 1) > t) --I;
+    while ((long long)(I + 1) * (I + 2) <= t) ++I;
+    J = static_cast<int>(t - (long long)I * (I + 1));
+  } else {
+    I = blockIdx.x / a.nJ;
+    J = blockIdx.x % a.nJ;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 4) {
+    if (lane == 0) {
+      const int8_t* ap = a.Ablob + (long long)I * a.nks * A_STEP;
+      const int8_t* bp = a.Bblob + (long long)J * a.nks * B_STEP;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ks = 0; ks < a.nks; ++ks) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        uint8_t* dst = smem + stage * STAGE;
+        mbar_arrive_expect_tx(&full[stage], STAGE);
+        bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
+        bulk_g2s(dst + A_STEP, bp + (long long)ks * B_STEP, B_STEP, &full[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ks = 0; ks < a.nks; ++ks) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE);
+        issue_kstep(tmem, sa, sa + A_STEP, ks == 0);
+        mma_commit(&empty[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    const int tid = threadIdx.x;
+    const long long row = (long long)I * TM + warp * 32 + lane;
+    double* crow = a.C + row * a.ldc + (long long)J * TN;
+#pragma unroll
+    for (int l = 0; l < TN * 8 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + l * 16));
+    if (tid < TN) cs[tid] = a.rowscaleB[(long long)J * TN + tid];
+    const double rs = a.alpha * a.rowscaleA[row];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t tbase = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+    for (int c4 = 0; c4 < TN / 16; ++c4) {
+      double2 cold[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cold[j] = *reinterpret_cast<const double2*>(crow + c4 * 16 + 2 * j);
+      double v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.0;
+#pragma unroll
+      for (int d = S - 1; d >= 0; --d) {
+        const double w = __longlong_as_double((1023LL - 8 * (d + 2)) << 52);
+        uint32_t r[16];
+        tmem_ld16(tbase + d * TN + c4 * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fma(static_cast<double>(static_cast<int>(r[j])), w, v[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<double2*>(crow + c4 * 16 + 2 * j) =
+            make_double2(fma(v[2 * j], rs * cs[c4 * 16 + 2 * j], cold[j].x),
+                         fma(v[2 * j + 1], rs * cs[c4 * 16 + 2 * j + 1], cold[j].y));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+// PA (M,K; lda), PB (N,K; ldb) row-major; PB == PA (same pointer, N <= M) shares the row scales
+static int run_update(int M, int N, int K, double alpha, const double* PA, int lda, const double* PB, int ldb, double* C,
+                      int ldc, int lower, cudaStream_t stream) {
+  const int nI = M / TM, nJ = N / TN, nks = K / KSTEP;
+  void *ablob, *bblob, *scales;
+  int rc;
+  if ((rc = workspace(9, (size_t)nI * nks * A_STEP, &ablob))) return rc;
+  if ((rc = workspace(10, (size_t)nJ * nks * B_STEP, &bblob))) return rc;
+  if ((rc = workspace(11, sizeof(double) * ((size_t)M + (size_t)N), &scales))) return rc;
+  double* rsA = static_cast<double*>(scales);
+  double* rsB = rsA + M;
+  rowscale_rect_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(PA, lda, M, K, kTriGemmNone, nullptr, rsA);
+  BCBF_LAUNCH_CHECK();
+  if (PB == PA && ldb == lda) {
+    rsB = rsA;
+  } else {
+    rowscale_rect_kernel<<<ceil_div(N, 8), 256, 0, stream>>>(PB, ldb, N, K, kTriGemmNone, nullptr, rsB);
+    BCBF_LAUNCH_CHECK();
+  }
+  split_rows_kernel<TM><<<dim3(ceil_div(K, 128), nI), 2 * TM, 0, stream>>>(PA, lda, K, kTriGemmNone, nullptr, rsA,
+                                                                           static_cast<int8_t*>(ablob));
+  BCBF_LAUNCH_CHECK();
+  split_rows_kernel<TN><<<dim3(ceil_div(K, 128), nJ), 2 * TN, 0, stream>>>(PB, ldb, K, kTriGemmNone, nullptr, rsB,
+                                                                           static_cast<int8_t*>(bblob));
+  BCBF_LAUNCH_CHECK();
+  UpdateArgs a{};
+  a.Ablob = static_cast<const int8_t*>(ablob);
+  a.Bblob = static_cast<const int8_t*>(bblob);
+  a.rowscaleA = rsA;
+  a.rowscaleB = rsB;
+  a.C = C;
+  a.ldc = ldc;
+  a.alpha = alpha;
+  a.nJ = nJ;
+  a.nks = nks;
+  a.lower = lower;
+  const long long tiles = lower ? (long long)nI * (nI + 1) : (long long)nI * nJ;
+  BCBF_CUDA(cudaFuncSetAttribute(oz_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  oz_update_kernel<<<static_cast<unsigned>(tiles), kThreads, kSmemBytes, stream>>>(a);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }
@@ -1003,6 +1172,26 @@ extern "C" int bcbf_oz_debug_counters(int enable, unsigned long long out[8]) {
     oz::g_dbg = nullptr;
   }
   return BCBF_OK;
+}
+
+extern "C" int bcbf_oz_update(int M, int N, int K, double alpha, const double* PA, int lda, const double* PB, int ldb,
+                              double* C, int ldc, int lower, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(PA && PB && C, "bcbf_oz_update: null pointer");
+  BCBF_REQUIRE(M > 0 && N > 0 && K > 0 && M % oz::TM == 0 && N % oz::TN == 0 && K % oz::KSTEP == 0 && K <= oz::kMaxNpad,
+               "bcbf_oz_update: M=%d (multiple of 128), N=%d (of 64), K=%d (of 32, <= %d)", M, N, K, oz::kMaxNpad);
+  BCBF_REQUIRE(lda >= K && ldb >= K && ldc >= N && ldc % 2 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+               "bcbf_oz_update: lda=%d ldb=%d ldc=%d (ldc even, C 16-byte aligned)", lda, ldb, ldc);
+  BCBF_REQUIRE(!lower || N == M, "bcbf_oz_update: lower-triangle mode needs a square C (M=%d, N=%d)", M, N);
+  return oz::run_update(M, N, K, alpha, PA, lda, PB, ldb, C, ldc, lower ? 1 : 0, stream);
+}
+
+extern "C" int bcbf_oz_update_reserve(int M, int N, int K) {
+  void* p = nullptr;
+  int rc;
+  if ((rc = oz::workspace(9, (size_t)ceil_div(M, oz::TM) * ceil_div(K, oz::KSTEP) * oz::A_STEP, &p))) return rc;
+  if ((rc = oz::workspace(10, (size_t)ceil_div(N, oz::TN) * ceil_div(K, oz::KSTEP) * oz::B_STEP, &p))) return rc;
+  return oz::workspace(11, sizeof(double) * ((size_t)M + (size_t)N), &p);
 }
 
 // Pre-size the operand-digit workspaces of bcbf_oz_gemm (so that a timed caller does not pay cudaMalloc).

@@ -219,6 +219,16 @@ def oz_gemm(A, B, alpha=1.0, tri=0, out=None):
     return C
 
 
+def oz_update_(C, PA, PB, alpha=-1.0, lower=False):
+    """C += alpha PA PB^T in place on the int8 tensor cores (bcbf_oz_update); lower: only tiles touching the lower triangle."""
+    assert C.is_cuda and PA.stride(1) == 1 and PB.stride(1) == 1 and C.stride(1) == 1
+    M, K = PA.shape
+    N = PB.shape[0]
+    check(_lib.load().bcbf_oz_update(M, N, K, float(alpha), _ptr(PA), PA.stride(0), _ptr(PB), PB.stride(0), _ptr(C),
+                                     C.stride(0), 1 if lower else 0, _stream()))
+    return C
+
+
 def oz_max_npad():
     return _lib.load().bcbf_oz_max_npad()
 

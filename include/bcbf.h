@@ -107,6 +107,9 @@ int bcbf_gram_backward_layout(int* out_elems, int* max_n, int* max_p);
 int bcbf_potrf(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale, double* dinv,
                int* info, void* stream);
 int bcbf_check_info(const int* info, void* stream);
+/* The large trailing updates of bcbf_potrf (single matrix, >= 1024 rows left) run on the int8 tensor cores
+ * (bcbf_oz_update) by default; 0 keeps them on the FP64 pipe. */
+int bcbf_set_potrf_i8(int on);
 
 /* Linv = L^{-1} (lower; strictly-upper blocks are zero) from L and the diagonal-block inverses of bcbf_potrf.
  * scratch: Npad*Npad doubles.  Everything downstream (alpha, v = L \ kb*, posterior covariance) multiplies by
@@ -191,6 +194,13 @@ int bcbf_oz_debug_counters(int enable, unsigned long long out[8]);
  * bcbf_trtri uses it for the large levels of the triangular inverse.                                                  */
 int bcbf_oz_gemm(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                  int tri, void* stream);
+/* Rank-K update on the int8 tensor cores (oz_update_kernel):  C (M,N; ldc) += alpha * PA (M,K; lda) * PB (N,K; ldb)^T,
+ * row-major, M % 128 == 0, N % 64 == 0, K % 32 == 0; lower != 0 (M == N): only the 128 x 64 tiles that touch the lower
+ * triangle are updated (whole tiles, so the part of a diagonal tile above the diagonal receives the symmetric values).
+ * bcbf_potrf uses it for the trailing update A22 -= L21 L21^T.                                                       */
+int bcbf_oz_update(int M, int N, int K, double alpha, const double* PA, int lda, const double* PB, int ldb, double* C,
+                   int ldc, int lower, void* stream);
+int bcbf_oz_update_reserve(int M, int N, int K);
 /* Pre-size bcbf_oz_gemm's internal workspaces for products up to (M,K) x (K,N). */
 int bcbf_oz_gemm_reserve(int M, int N, int K);
 /* CUDA-event timing of oz_var_kernel launches (bench.py's roofline leg), like bcbf_profile_enable/read. */

@@ -232,3 +232,57 @@ def test_trtri_large_levels_on_int8_match_the_fp64_pipe():
     r1 = (Linv1 @ L - I).abs().max().item()
     # measured 6.1e-11 against 1.5e-11 (without the inner-dimension balancing of bcbf_oz_gemm: 6.4e-9)
     assert r1 < 10 * r0 + 1e-12, (r0, r1)
+
+
+@pytest.mark.parametrize('M,N,K,lower', [(384, 128, 96, False), (1024, 512, 512, False), (640, 640, 512, True),
+                                         (2048, 2048, 512, True)])
+def test_oz_update_rank_k(M, N, K, lower):
+    """bcbf_oz_update (the Cholesky trailing update on the int8 tensor cores) against float64: C += alpha PA PB^T on every
+    tile, or only on the 128 x 64 tiles that touch the lower triangle."""
+    from bayesian_cbf_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    PA = torch.randn(M, K, generator=g, dtype=torch.float64) * torch.exp2(torch.randint(-6, 3, (M, 1), generator=g).double())
+    PB = PA if lower else torch.randn(N, K, generator=g, dtype=torch.float64)
+    C0 = torch.randn(M, N, generator=g, dtype=torch.float64)
+    big = torch.zeros(M + 128, N + 64, dtype=torch.float64, device='cuda')
+    big[128:, 64:] = C0.cuda()
+    PAd = PA.cuda()
+    C = ops.oz_update_(big[128:, 64:], PAd, PAd if lower else PB.cuda(), alpha=-1.0, lower=lower).cpu()
+    ref = C0 - PA @ PB.T
+    touched = torch.ones(M, N, dtype=torch.bool)
+    if lower:
+        i = torch.arange(M).unsqueeze(1) // 128
+        j = torch.arange(N).unsqueeze(0) // 64
+        touched = j <= 2 * i + 1
+    bound = PA.abs().amax(1, keepdim=True) * PB.abs().amax(1, keepdim=True).T
+    err = ((C - ref).abs() / bound)[touched].max().item()
+    assert err < K * 2.0 ** -50 + 2e-16, err
+    assert torch.equal(C[~touched], C0[~touched])
+    assert big[:128].abs().max().item() == 0.0 and big[:, :64].abs().max().item() == 0.0
+
+
+def test_potrf_trailing_updates_on_int8_match_the_fp64_pipe():
+    """bcbf_potrf with its large trailing updates on bcbf_oz_update: same backward error |L L^T - (Kb + jitter)| as the
+    all-DMMA factorisation, factors equal to the conditioning-limited level."""
+    from bayesian_cbf_b200 import _lib, ops
+    lib = _lib.load()
+    N = 4200
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(23, N, 3, 2, 8, box=3.0)
+    UH = O.homogeneous(U)
+    res = {}
+    try:
+        for on in (0, 1):
+            assert lib.bcbf_set_potrf_i8(on) == 0
+            Kb = ops.gram_train(_d(X), _d(UH), _d(hyp.B), _d(hyp.lengthscale), float(hyp.outputscale))
+            Kfull = Kb.clone()
+            L, dinv = ops.potrf_(Kb, N, _d(jit), 1e-5)
+            res[on] = L
+    finally:
+        lib.bcbf_set_potrf_i8(1)
+    Npad = Kfull.shape[0]
+    jpad = torch.zeros(Npad, dtype=torch.float64, device='cuda')
+    jpad[:N] = 1e-5 * _d(jit)
+    target = Kfull + torch.diag(jpad)
+    back = [((res[on] @ res[on].T - target).abs().max() / target.abs().max()).item() for on in (0, 1)]
+    assert back[1] < 3 * back[0] + 1e-15 and back[1] < 1e-13, back
+    assert ((res[1] - res[0]).abs().max() / res[0].abs().max()).item() < 1e-7
