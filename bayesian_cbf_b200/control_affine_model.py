@@ -426,7 +426,13 @@ class ControlAffineRegressor(DynamicsModel):
             Ypad = torch.zeros(Npad, Y.shape[1], dtype=torch.float64, device=Y.device)
             Ypad[:N] = Y
             z = ops.trmm_lower(Linv, Ypad)
-            self._cache['_alpha'] = ops.trmm_lower(Linv, z.contiguous(), trans=True).contiguous()   # Kb^-1 Y (:545)
+            alpha = ops.trmm_lower(Linv, z.contiguous(), trans=True).contiguous()                   # Kb^-1 Y (:545)
+            # one refinement step against the factor itself (the explicit inverse carries eps * cond(L) of forward
+            # error; the residual Y - L L^T alpha does not): predicts like the reference's cholesky_solve
+            Lpad = self._cache['_Lpad']
+            r = Ypad - ops.trmm_lower(Lpad, ops.trmm_lower(Lpad, alpha, trans=True).contiguous())
+            z = ops.trmm_lower(Linv, r.contiguous())
+            self._cache['_alpha'] = (alpha + ops.trmm_lower(Linv, z.contiguous(), trans=True)).contiguous()
             G = torch.zeros(Npad, B.shape[0], dtype=torch.float64, device=Y.device)
             G[:N] = UH64 @ B
             self._cache['_G'] = G

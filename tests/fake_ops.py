@@ -170,3 +170,16 @@ def socp_solve(w, c, d, A, b, rho, r=None, tol=1e-9):
         y[p] = torch.from_numpy(yo)
         status[p], iters[p] = st, it
     return y, status, iters
+
+
+# ---- int8 tensor-core path (csrc/ozaki.cu): on the CPU stand-in the "digits" are the inverse factor itself
+def oz_max_npad():
+    return 18432
+
+
+def oz_split_factor(Linv):
+    return Linv, torch.ones(Linv.shape[0], dtype=torch.float64)
+
+
+def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, want_cov=True):
+    return posterior_blocks(digits, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=want_mean, want_cov=want_cov)
