@@ -340,8 +340,6 @@ static LookAhead* get_lookahead() {
   return &l;
 }
 
-// R independent factorisations of equal size (R = 1: the single-matrix entry point).  Strides in elements:
-// sA between matrices, sD between dinv blocks sets, sJ between jitter vectors; info is int[R].
 // Trailing updates of bcbf_potrf with at least kPotrfI8MinRows rows run on the int8 tensor cores (csrc/ozaki.cu);
 // bcbf_set_potrf_i8(0) keeps everything on the FP64 pipe.
 static int g_potrf_i8 = 1;
@@ -351,6 +349,8 @@ extern "C" int bcbf_set_potrf_i8(int on) {
   return BCBF_OK;
 }
 
+// R independent factorisations of equal size (R = 1: the single-matrix entry point).  Strides in elements:
+// sA between matrices, sD between dinv blocks sets, sJ between jitter vectors; info is int[R].
 static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale, double* dinv,
                       int* info, int R, long long sA, long long sD, long long sJ, cudaStream_t stream) {
   BCBF_REQUIRE(A && dinv && info, "bcbf_potrf: null pointer");
