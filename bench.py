@@ -212,6 +212,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # NCCL's banner / debug lines go to stderr: stdout carries the ONE JSON line and nothing else
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     N, QS, K, W = args.n_train, args.queries_per_step, args.steps, args.warmup
