@@ -173,7 +173,18 @@ __global__ void __launch_bounds__(256) tri_mv_n_kernel(const double* __restrict_
 #pragma unroll
   for (int c = 0; c < kMvMaxC; ++c) acc[c] = 0.0;
   const double* t = T + (long long)row * ld;
-  for (int k = lane; k <= row; k += 32) {
+  int k = lane;
+  for (; k + 96 <= row; k += 128) {  // four independent row segments in flight per lane
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = t[k + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int c = 0; c < kMvMaxC; ++c)
+        if (c < nc) acc[c] = fma(v[u], x[(long long)(k + 32 * u) * ldx + c], acc[c]);
+  }
+  for (; k <= row; k += 32) {
     const double v = t[k];
 #pragma unroll
     for (int c = 0; c < kMvMaxC; ++c)

@@ -616,7 +616,15 @@ __global__ void colmax_of_a_kernel(const double* __restrict__ A, int lda, int M,
   const int i1 = min(M, i0 + rows_per_block);
   if (tri == kTriGemmALower) i0 = max(i0, k);
   double mx = 0.0;
-  for (int i = i0; i < i1; ++i) mx = fmax(mx, fabs(A[(long long)i * lda + k]));
+  int i = i0;
+  for (; i + 8 <= i1; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = A[(long long)(i + u) * lda + k];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) mx = fmax(mx, fabs(v[u]));
+  }
+  for (; i < i1; ++i) mx = fmax(mx, fabs(A[(long long)i * lda + k]));
   atomicMax(amax + k, static_cast<unsigned long long>(__double_as_longlong(mx)));
 }
 
@@ -705,7 +713,15 @@ __global__ void colmax_rect_kernel(const double* __restrict__ B, int ldb, int K,
   const int k1 = min(K, k0 + rows_per_block);
   if (tri == kTriGemmBLower) k0 = max(k0, j);
   double mx = 0.0;
-  for (int k = k0; k < k1; ++k) mx = fmax(mx, fabs(B[(long long)k * ldb + j]) / __ldg(kscale + k));
+  int k = k0;
+  for (; k + 8 <= k1; k += 8) {  // eight independent loads in flight
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = B[(long long)(k + u) * ldb + j];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) mx = fmax(mx, fabs(v[u]) / __ldg(kscale + k + u));
+  }
+  for (; k < k1; ++k) mx = fmax(mx, fabs(B[(long long)k * ldb + j]) / __ldg(kscale + k));
   atomicMax(colmax + j, static_cast<unsigned long long>(__double_as_longlong(mx)));
 }
 

@@ -14,6 +14,9 @@
  *   - N  = number of training points, Npad = N rounded up to a multiple of 128 (bcbf_padded()); factor-sized
  *     buffers are Npad x Npad with leading dimension ld >= Npad, the pad region holds the identity;
  *   - n  = state dim, m = control dim, p = 1 + m (homogeneous control [1;u]);
+ *   - the library keeps per-device scratch buffers (posterior partial sums, operand digits of the int8 kernels): entry
+ *     points that use them (posterior_*, oz_*, potrf, trtri, model_*) must not run concurrently on different streams of the
+ *     same device; one caller thread per device, as in the reference (single-threaded Python);
  *   - return value: BCBF_OK (0) or a negative error code; bcbf_last_error() describes the last failure
  *     of the calling thread.  There is NO CPU fallback anywhere: without a CUDA device every compute
  *     entry point returns BCBF_ERR_CUDA.
