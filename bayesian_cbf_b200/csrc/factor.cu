@@ -317,7 +317,8 @@ extern "C" long long bcbf_dinv_elems(int Npad) { return (long long)(Npad / kBlk)
 // higher-priority stream gets the SM that a retiring GEMM CTA frees.  One set per device, created on demand.
 struct LookAhead {
   cudaStream_t side = nullptr;   // high priority: critical path
-  cudaEvent_t panels_done = nullptr, t2_done = nullptr, start = nullptr;
+  cudaStream_t side2 = nullptr;  // high priority: panel solves / in-block updates below the next diagonal block
+  cudaEvent_t panels_done = nullptr, t2_done = nullptr, start = nullptr, mini_done = nullptr, rest_done = nullptr;
 };
 static LookAhead g_look[64];
 
@@ -329,7 +330,10 @@ static LookAhead* get_lookahead() {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically least = greatest priority
     if (cudaStreamCreateWithPriority(&l.side, cudaStreamNonBlocking, hi) != cudaSuccess) { l.side = nullptr; return nullptr; }
-    if (cudaEventCreateWithFlags(&l.panels_done, cudaEventDisableTiming) != cudaSuccess ||
+    if (cudaStreamCreateWithPriority(&l.side2, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.mini_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.rest_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.panels_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&l.start, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&l.t2_done, cudaEventDisableTiming) != cudaSuccess) {
       cudaStreamDestroy(l.side);
@@ -377,6 +381,7 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
   }
   for (int J = 0; J < nb; J += kOuter) {
     const int jend = (J + kOuter < nb) ? J + kOuter : nb;  // exclusive, in blocks
+    bool rest_pending = false;  // a "rest" step of this outer block is in flight on the second critical stream
     for (int k = J; k < jend; ++k) {
       const int k0 = k * kBlk;
       double* dk = dinv + (long long)k * kBlk * kBlk;
@@ -385,6 +390,42 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
       const int rows = Npad - (k0 + kBlk);
       if (rows <= 0) break;
       double* panel = A + (long long)(k0 + kBlk) * ld + k0;
+      const int w = (jend - (k + 1)) * kBlk;
+      if (look && w > 0) {
+        // Inner look-ahead.  The next diagonal factorisation (one CTA, ~170 us, the serial chain of the whole
+        // algorithm) needs only row block k+1: its panel solve and the update of its diagonal block ("mini", here);
+        // the solve and update of all rows below ("rest") run on a second high-priority stream next to it.
+        if (rest_pending) BCBF_CUDA(cudaStreamWaitEvent(cs, look->rest_done, 0));   // rest(k-1) wrote row block k+1
+        GemmArgs g{};
+        g.A = panel; g.lda = ld; g.B = dk; g.ldb = kBlk; g.C = panel; g.ldc = ld;
+        g.M = kBlk; g.N = kBlk; g.K = kBlk; g.alpha = 1.0; g.beta = 0.0; g.tri = kTriNone;
+        BCBF_CUDA((launch_gemm<true, true>(g, 1, cs)));
+        GemmArgs u{};
+        u.A = panel; u.lda = ld; u.B = panel; u.ldb = ld;
+        u.C = A + (long long)(k0 + kBlk) * (ld + 1); u.ldc = ld;
+        u.M = kBlk; u.N = kBlk; u.K = kBlk; u.alpha = -1.0; u.beta = 1.0; u.tri = kTriNone;
+        BCBF_CUDA((launch_gemm<true, true>(u, 1, cs)));
+        BCBF_CUDA(cudaEventRecord(look->mini_done, cs));
+        if (rows > kBlk) {
+          BCBF_CUDA(cudaStreamWaitEvent(look->side2, look->mini_done, 0));
+          double* below = panel + (long long)kBlk * ld;
+          GemmArgs g2 = g;
+          g2.A = below; g2.C = below; g2.M = rows - kBlk;
+          BCBF_CUDA((launch_gemm<true, true>(g2, 1, look->side2)));
+          GemmArgs u2 = u;
+          u2.A = below; u2.B = panel;
+          u2.C = A + (long long)(k0 + 2 * kBlk) * ld + (k0 + kBlk);
+          u2.M = rows - kBlk; u2.N = w;
+          BCBF_CUDA((launch_gemm<true, true>(u2, 1, look->side2)));
+          BCBF_CUDA(cudaEventRecord(look->rest_done, look->side2));
+          rest_pending = true;
+        }
+        continue;
+      }
+      if (rest_pending) {
+        BCBF_CUDA(cudaStreamWaitEvent(cs, look->rest_done, 0));
+        rest_pending = false;
+      }
       GemmArgs g{};
       // panel <- panel * Dinv_k^T       (L_ik = A_ik L_kk^{-T})
       g.A = panel; g.lda = ld; g.B = dk; g.ldb = kBlk; g.C = panel; g.ldc = ld;
@@ -392,7 +433,6 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
       g.sA = sA; g.sB = sD; g.sC = sA;
       BCBF_CUDA((launch_gemm<true, true>(g, R, cs)));
       // inside the outer block column: columns (k+1)*128 .. jend*128, all rows below  -= panel panel^T
-      const int w = (jend - (k + 1)) * kBlk;
       if (w > 0) {
         GemmArgs u{};
         u.A = panel; u.lda = ld; u.B = panel; u.ldb = ld;
@@ -402,6 +442,7 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
         BCBF_CUDA((launch_gemm<true, true>(u, R, cs)));
       }
     }
+    if (rest_pending) BCBF_CUDA(cudaStreamWaitEvent(cs, look->rest_done, 0));
     const int c1 = jend * kBlk, rows = Npad - c1;
     if (rows > 0) {
       // trailing (lower tiles) -= P P^T,  P = A[c1:, J*128 : c1]   (K up to 512)
