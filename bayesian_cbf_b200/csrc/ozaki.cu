@@ -454,7 +454,7 @@ __global__ void finalize_kernel(const double* __restrict__ Spart, int Qpad, int 
     for (int j = i; j < p; ++j) {
       double s = 0.0;
       for (int sp = 0; sp < nb; ++sp) s += Spart[((long long)sp * Qpad + q) * npair + e];
-      const double v = kss * Bmat[i * p + j] - s;
+      const double v = __dmul_rn(kss, Bmat[i * p + j]) - s;  // no FMA contraction: two roundings, reproducible on the host
       Bk[((long long)q * p + i) * p + j] = v;
       Bk[((long long)q * p + j) * p + i] = v;
       ++e;

@@ -286,3 +286,57 @@ def test_potrf_trailing_updates_on_int8_match_the_fp64_pipe():
     back = [((res[on] @ res[on].T - target).abs().max() / target.abs().max()).item() for on in (0, 1)]
     assert back[1] < 3 * back[0] + 1e-15 and back[1] < 1e-13, back
     assert ((res[1] - res[0]).abs().max() / res[0].abs().max()).item() < 1e-7
+
+
+@pytest.mark.parametrize('M,N,K,tri', [(256, 192, 160, 0), (384, 128, 384, 1), (128, 256, 256, 2)])
+def test_oz_gemm_is_bit_identical_to_the_cpu_restatement(M, N, K, tri):
+    """Integer digit products are exact and every FP64 step of the kernel is a single rounding in a fixed order:
+    bcbf_oz_gemm must equal oracle/ozaki_oracle.py:gemm bit for bit (scales, balancing, digits, recombination)."""
+    from bayesian_cbf_b200 import ops
+    from oracle import ozaki_oracle as Z
+    g = torch.Generator().manual_seed(5 * M + N + K + tri)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64) * torch.exp2(torch.randint(-20, 6, (M, K), generator=g).double())
+    B = torch.randn(K, N, generator=g, dtype=torch.float64) * torch.exp2(torch.randint(-20, 6, (K, N), generator=g).double())
+    A[3] = 0.0                                           # an all-zero row and column: unit scale, zero digits
+    B[:, 5] = 0.0
+    C = ops.oz_gemm(A.cuda(), B.cuda(), alpha=-0.75, tri=tri).cpu().numpy()
+    ref = Z.gemm(A.numpy(), B.numpy(), alpha=-0.75, tri=tri)
+    assert np.array_equal(C, ref)
+
+
+@pytest.mark.parametrize('lower', [False, True])
+def test_oz_update_is_bit_identical_to_the_cpu_restatement(lower):
+    from bayesian_cbf_b200 import ops
+    from oracle import ozaki_oracle as Z
+    g = torch.Generator().manual_seed(77 + lower)
+    M, K = 384, 96
+    PA = torch.randn(M, K, generator=g, dtype=torch.float64) * torch.exp2(torch.randint(-9, 4, (M, K), generator=g).double())
+    PB = PA if lower else torch.randn(128, K, generator=g, dtype=torch.float64)
+    C0 = torch.randn(M, PB.shape[0], generator=g, dtype=torch.float64)
+    C = C0.clone().cuda()
+    PAd = PA.cuda()
+    ops.oz_update_(C, PAd, PAd if lower else PB.cuda(), alpha=-1.0, lower=lower)
+    ref = Z.update(C0.numpy(), PA.numpy(), PB.numpy(), alpha=-1.0)
+    touched = np.ones(ref.shape, dtype=bool)
+    if lower:
+        touched = (np.arange(ref.shape[1])[None, :] // 64) <= 2 * (np.arange(M)[:, None] // 128) + 1
+    got = C.cpu().numpy()
+    assert np.array_equal(got[touched], ref[touched])
+    assert np.array_equal(got[~touched], C0.numpy()[~touched])
+
+
+@pytest.mark.parametrize('N,n,m,Q', [(300, 3, 2, 50), (200, 2, 1, 70)])
+def test_posterior_var_i8_is_bit_identical_to_the_cpu_restatement(N, n, m, Q):
+    """oz_var_kernel + its split / finalize kernels against oracle/ozaki_oracle.py:posterior_bk on the same L^-1, K*, G
+    (downloaded from the device): scales, digits, integer accumulation, recombination, warp-butterfly Gram reduction
+    and the fixed-order sum over row blocks are all reproduced, so B_k agrees bit for bit."""
+    from bayesian_cbf_b200 import ops
+    from oracle import ozaki_oracle as Z
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(41, N, n, m, Q, box=2.0)
+    p = m + 1
+    L, Linv, G, alpha, W = _fit_on_gpu(X, U, Xdot, hyp, jit)
+    Ks = ops.cross_gram(_d(X), _d(Xq), _d(hyp.lengthscale), float(hyp.outputscale))
+    digits, rowscale = ops.oz_split_factor(Linv)
+    Bk = ops.posterior_var_i8(digits, rowscale, Ks, G, _d(hyp.B), float(hyp.outputscale), p, Q).cpu().numpy()
+    ref = Z.posterior_bk(Linv.cpu().numpy(), Ks.cpu().numpy()[:, :Q], G.cpu().numpy(), hyp.B.numpy(), float(hyp.outputscale))
+    assert np.array_equal(Bk, ref)
