@@ -212,9 +212,18 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        # NCCL's banner / debug lines go to stderr: stdout carries the ONE JSON line and nothing else
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner with printf when NCCL_DEBUG=VERSION is in the environment: keep file
+        # descriptor 1 pointed at stderr while the communicator is created, so that stdout carries the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     lib = _lib.load()
     N, QS, K, W = args.n_train, args.queries_per_step, args.steps, args.warmup
     X, U, Xdot, hyp, jitter = make_workload(N)

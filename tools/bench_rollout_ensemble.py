@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""BASELINE configs[4] shape on one GPU: R independent `learning_helps_avoid_getting_stuck` rollouts
+"""BASELINE configs[4] shape, R rollouts per GPU (run under torchrun for several GPUs: the rollouts are independent, every
+rank takes its own R with its own seeds, no data-path collective; rank 0 prints the aggregate): R independent `learning_helps_avoid_getting_stuck` rollouts
 (reference unicycle_move_to_pose.py:1948-1969: true Ackermann L=1, prior L=12 with kernel_diag_A=[1,1,1], learning on,
 2 obstacles, PiecewiseLinearPlanner, dt=0.001), each with its own MVGP refitted every `--train-every` steps on at most
 200 of its own samples.  Per control step and rollout: ensemble posterior (HBM-bound kernel) -> CBC/CLC cone terms ->
@@ -25,6 +26,21 @@ def main():
     ap.add_argument('--eager', action='store_true', help='no CUDA graph')
     ap.add_argument('--adam-iters', type=int, default=0, help='Adam steps per refit on every rollout (reference: 100)')
     a = ap.parse_args()
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)          # NCCL's printf banner (NCCL_DEBUG=VERSION) goes to stderr, not into the JSON
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            dist.all_reduce(torch.zeros(1, device='cuda'))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     from bayesian_cbf_b200 import unicycle as U
     R, dt, numSteps = a.rollouts, 0.001, 2000
     x0 = [-3.0, -1.0, -math.pi / 4]
@@ -32,10 +48,10 @@ def main():
     planner = U.PiecewiseLinearPlanner(x0, xg, numSteps, dt, frac_time_to_reach_goal=0.95)
     cbfs = U.obstacles_at_mid_from_start_and_goal(x0, xg, term_weights=(0.7, 0.3))
     learner = U.EnsembleLearner(R, dt, model_L=12.0, max_train=a.max_train, train_every_n_steps=a.train_every,
-                                lengthscale=(1.0, 1.0, 0.7), outputscale=1.0, adam_iters=a.adam_iters)
+                                lengthscale=(1.0, 1.0, 0.7), outputscale=1.0, adam_iters=a.adam_iters, seed=rank)
     ctrl = U.BayesCBFController(planner, U.CLFCartesian(Kp=(0.9, 1.5, 0.0)), cbfs, [5.0, 5.0], model_L=12.0,
                                 clf_gamma=10.0, max_risk=0.01, posterior=learner.posterior)
-    g = torch.Generator().manual_seed(0)
+    g = torch.Generator().manual_seed(rank)          # rollout r of rank k: its own start perturbation and jitter stream
     X0 = (torch.tensor(x0, dtype=torch.float64).repeat(R, 1)
           + 0.05 * (torch.rand(R, 3, generator=g, dtype=torch.float64) - 0.5)).cuda()
     U.rollout(ctrl, X0, 5, dt, true_L=1.0)          # warm-up launches
@@ -62,8 +78,18 @@ def main():
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     alive = int(out['alive'].sum())
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                 # slowest rank
+        al = torch.tensor([alive], dtype=torch.int64, device='cuda')
+        dist.all_reduce(al, op=dist.ReduceOp.SUM)
+        wall, alive = float(t.item()), int(al.item())
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    R = R * world
     print(json.dumps(dict(metric='controlled rollout steps/sec (posterior + CBC terms + SOCP per step)',
-                          value=R * a.steps / wall, unit='rollout-steps/s', rollouts=R, steps=a.steps,
+                          value=R * a.steps / wall, unit='rollout-steps/s', rollouts=R, n_gpus=world, steps=a.steps,
                           ms_per_step=1e3 * wall / a.steps, refits=learner.refits, cuda_graph=not a.eager, adam_iters_per_refit=a.adam_iters, alive_at_end=alive,
                           n_train_last=getattr(learner.ens, 'N', 0),
                           config=dict(workload='ensemble of %d unicycle learning rollouts (BASELINE configs[4] shape), '
