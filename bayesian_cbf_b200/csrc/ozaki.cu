@@ -22,6 +22,12 @@
 // K step instead of 28, which keeps the shared-memory operand reads under the 128 B/clk limit (measured: 920 cycles per
 // K step against a tensor-pipe floor of 896, tools/microbench/umma_i8_probe.cu); warps 0-3 drain TMEM, recombine in
 // FP64, apply the scales and reduce the Gram over the 128 rows.
+//
+// The same digit arithmetic, MMA pattern and pipeline serve two more kernels further down: oz_gemm_kernel (general
+// C = alpha A B with an optional triangular operand and inner-dimension balancing; the large levels of bcbf_trtri) and
+// oz_update_kernel (rank-K update C += alpha P P^T, one short-lived CTA per tile; the trailing updates of bcbf_potrf).
+// oracle/ozaki_oracle.py restates the arithmetic on the CPU with exact integers; all three kernels reproduce it bit for bit
+// (tests/test_gpu_ozaki.py).
 #include "../../include/bcbf.h"
 #include "common.cuh"
 #include "tc5.cuh"
