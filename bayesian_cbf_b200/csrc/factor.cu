@@ -565,7 +565,7 @@ static int trtri_impl(const double* L, const double* dinv, double* Linv, double*
         stride = sL;
       }
       if (batch == 0) continue;
-      if (R == 1 && g_trtri_i8 && h >= kTrtriI8MinH && M2 % kBlk == 0) {
+      if (R == 1 && g_trtri_i8 && h >= kTrtriI8MinH && h <= bcbf_oz_max_npad() && M2 % kBlk == 0) {
         // large levels (94 % of the flops): the two products on the int8 tensor cores (bcbf_oz_gemm, FP64-accurate)
         for (int b = 0; b < batch; ++b) {
           const long long o = r0 + (long long)b * 2 * h;
