@@ -140,10 +140,34 @@ class MVGPEnsemble:
 # =====================================================================================================================
 # Per-rollout hyper-parameter fits: R log marginal likelihoods + gradients in the same launches
 # =====================================================================================================================
+def _small_cholesky(A):
+    """Lower Cholesky factors of R small (n x n, n <= 8) SPD matrices with elementwise torch ops (column by column)."""
+    n = A.shape[-1]
+    L = torch.zeros_like(A)
+    for j in range(n):
+        d = A[:, j, j] - (L[:, j, :j] ** 2).sum(-1)
+        L[:, j, j] = torch.sqrt(d)        # a non-positive pivot gives NaN, which the caller's NaN check reports (no sync here)
+        if j + 1 < n:
+            L[:, j + 1:, j] = (A[:, j + 1:, j] - (L[:, j + 1:, :j] * L[:, j:j + 1, :j]).sum(-1)) / L[:, j:j + 1, j]
+    return L
+
+
+def _small_lower_inverse(L):
+    """Inverses of R small lower-triangular matrices by forward substitution on the identity."""
+    n = L.shape[-1]
+    X = torch.zeros_like(L)
+    for i in range(n):
+        e = torch.zeros(L.shape[0], n, dtype=L.dtype, device=L.device)
+        e[:, i] = 1.0
+        X[:, i, :] = (e - (L[:, i, :i].unsqueeze(-1) * X[:, :i, :]).sum(1)) / L[:, i, i].unsqueeze(-1)
+    return X
+
+
 class _EnsembleLogMarginal(torch.autograd.Function):
     """log N(vec Xdot_r; vec(UH_r C_r), Kb_r (x) A_r) for r < R (values (R,)) with the closed-form adjoints of mll.py,
     batched: ens Gram -> batched Cholesky (psd-safe escalation per call) -> batched inverse -> batched Kb^-1 = L^-T L^-1
     -> batched fused adjoint reduction (bcbf_ens_gram_backward)."""
+    last_jitter = 0.0
 
     @staticmethod
     def forward(ctx, ls, s, A, B, C, X, UH, Xdot):
@@ -160,13 +184,16 @@ class _EnsembleLogMarginal(torch.autograd.Function):
         ones = torch.ones(R, N, **f64)
         dinv = torch.empty(R, lib.bcbf_dinv_elems(Npad), **f64)
         info = torch.zeros(R, dtype=torch.int32, device=dev)
-        jitter = 0.0
+        # start from the jitter the previous call needed (gpytorch's psd_safe_cholesky escalation, 1e-8, 1e-7, ...):
+        # inside one Adam run the matrices barely move, and a failed first attempt costs a Gram + factorisation + sync
+        jitter = _EnsembleLogMarginal.last_jitter
         for attempt in range(7):
             L = torch.empty(R, Npad, Npad, **f64)
             check(lib.bcbf_ens_gram(_ptr(X), _ptr(UH), _ptr(ls_d), _ptr(s_d), _ptr(B_d), R, N, n, p, _ptr(L), Npad, st))
             check(lib.bcbf_potrf_batched(_ptr(L), Npad, Npad, N, _ptr(ones) if jitter > 0 else None, jitter, _ptr(dinv),
                                          _ptr(info), R, st))
             if int(info.abs().max()) == 0:
+                _EnsembleLogMarginal.last_jitter = jitter
                 break
             if attempt == 6:
                 raise _lib.NotPositiveDefiniteError(-3, "linalg.cholesky: ensemble log marginal: a Gram matrix is not "
@@ -185,12 +212,12 @@ class _EnsembleLogMarginal(torch.autograd.Function):
         alpha = al[:, :N, :n].contiguous()                               # Kb^-1 Y
         zz = z[:, :N, :n]
         YtA = zz.transpose(1, 2) @ zz                                    # Y^T Kb^-1 Y   (R,n,n)
-        A_h = A.detach().cpu()
-        La_h = torch.linalg.cholesky(A_h)                                # n x n glue, on the host
-        Ai = torch.cholesky_inverse(La_h).to(dev)
+        La = _small_cholesky(A.detach())                                 # n x n glue, R at once, no host round trip
+        Lai = _small_lower_inverse(La)
+        Ai = Lai.transpose(1, 2) @ Lai
         quad = torch.einsum('rij,rji->r', Ai, YtA)
         logdetK = 2.0 * torch.log(torch.diagonal(L, dim1=1, dim2=2)[:, :N]).sum(1)
-        logdetA = (2.0 * torch.log(torch.diagonal(La_h, dim1=1, dim2=2)).sum(1)).to(dev)
+        logdetA = 2.0 * torch.log(torch.diagonal(La, dim1=1, dim2=2)).sum(1)
         value = -0.5 * (quad + n * logdetK + N * logdetA + N * n * math.log(2 * math.pi))
         # Kb^-1 = L^-T L^-1 for every rollout, then the fused adjoint reduction
         Pinv = scratch                                                   # reuse
@@ -261,9 +288,14 @@ def fit_ensemble_hyperparameters(hp, X, U, Xdot, training_iter=100, lr=0.1, gene
     opt = torch.optim.Adam(hp.parameters(), lr=lr)
     sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=(torch.tensor([0.3, 0.6, 0.8, 0.90]) * training_iter).tolist())
     loss_r = None
+    # the 1e-6 target noise of every iteration comes from a device generator seeded from the caller's (CPU) generator:
+    # reproducible from the same seed without a 2.4 MB host draw + copy per iteration
+    seed = int(torch.randint(2 ** 62, (1,), generator=generator)) if generator is not None else torch.seed()
+    dgen = torch.Generator(device=X.device).manual_seed(seed)
+    _EnsembleLogMarginal.last_jitter = 0.0
     for _ in range(training_iter):
         opt.zero_grad()
-        noise = torch.rand(Xdot.shape, dtype=torch.float64, generator=generator).to(X.device)
+        noise = torch.rand(Xdot.shape, dtype=torch.float64, device=X.device, generator=dgen)
         ls, s, A, B, C = hp.constrained()
         logp = ensemble_log_marginal(ls, s, A, B, C, X, UH, Xdot * (1 + 1e-6 * noise))
         loss_r = -logp / (N * n)
