@@ -95,6 +95,7 @@ _SIGNATURES = {
                                          _P]),
     'bcbf_oz_debug_counters': (c_int, [c_int, POINTER(ctypes.c_ulonglong * 8)]),
     'bcbf_oz_gemm': (c_int, [c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
+    'bcbf_oz_gemm_tn': (c_int, [c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
     'bcbf_oz_gemm_reserve': (c_int, [c_int, c_int, c_int]),
     'bcbf_oz_update': (c_int, [c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
     'bcbf_oz_update_reserve': (c_int, [c_int, c_int, c_int]),

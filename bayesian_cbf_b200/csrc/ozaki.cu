@@ -609,6 +609,7 @@ static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, con
 // (T = L21 X11, X21 = -X22 T: control_affine_model.py:565's solves become products with L^-1).
 // ======================================================================================================================
 constexpr int kTriGemmNone = 0, kTriGemmALower = 1, kTriGemmBLower = 2;
+constexpr int kTriGemmTnLower = 3;  // C = A^T B with A and B lower triangular: term k contributes only for k >= max(i, j)
 
 // Inner-dimension balancing: C = (A D)(D^-1 B) for any diagonal D.  With one scale per row of A and per column of B, an
 // operand whose magnitude falls steeply along k (rows of a Cholesky factor) loses the bits of its small entries even
@@ -725,22 +726,25 @@ __global__ void colmax_rect_kernel(const double* __restrict__ B, int ldb, int K,
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = B[(long long)(k + u) * ldb + j];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) mx = fmax(mx, fabs(v[u]) / __ldg(kscale + k + u));
+    for (int u = 0; u < 8; ++u) mx = fmax(mx, kscale ? fabs(v[u]) / __ldg(kscale + k + u) : fabs(v[u]));
   }
-  for (; k < k1; ++k) mx = fmax(mx, fabs(B[(long long)k * ldb + j]) / __ldg(kscale + k));
+  for (; k < k1; ++k) mx = fmax(mx, kscale ? fabs(B[(long long)k * ldb + j]) / __ldg(kscale + k) : fabs(B[(long long)k * ldb + j]));
   atomicMax(colmax + j, static_cast<unsigned long long>(__double_as_longlong(mx)));
 }
 
-// D^-1 B (K,N) row-major -> blobs [(J nks + ks)] of [digit][column group 8][k chunk 2][column 8][16 B], one thread per
-// column and 16 consecutive k
+// D^-1 B (K,N) row-major -> blobs [(J nks + ks)] of [digit][column group COLS/8][k chunk 2][column 8][16 B], one thread
+// per column and 16 consecutive k.  COLS = 64: the MMA's N-side operand; COLS = 128: the M-side operand of a product with
+// B^T on the left (C = A^T B).
+template <int COLS>
 __global__ void __launch_bounds__(128) split_cols_kernel(const double* __restrict__ B, int ldb, int K, int N, int tri,
                                                          const double* __restrict__ kscale,
                                                          const unsigned long long* __restrict__ colmax,
                                                          int8_t* __restrict__ blob, double* __restrict__ colscale) {
+  constexpr int STEP = S * COLS * KSTEP;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
   const int k0 = blockIdx.y * 16;
-  const int J = j / TN, c = j % TN;
+  const int J = j / COLS, c = j % COLS;
   const double sc = scale_of(__longlong_as_double(static_cast<long long>(colmax[j])));
   const double inv = 1.0 / sc;
   if (blockIdx.y == 0) colscale[j] = sc;
@@ -750,19 +754,19 @@ __global__ void __launch_bounds__(128) split_cols_kernel(const double* __restric
   if (!(tri == kTriGemmBLower && k0 + 15 < j)) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const double v =
-          (tri == kTriGemmBLower && k0 + k < j) ? 0.0 : B[(long long)(k0 + k) * ldb + j] / __ldg(kscale + k0 + k);
+      double v = (tri == kTriGemmBLower && k0 + k < j) ? 0.0 : B[(long long)(k0 + k) * ldb + j];
+      if (kscale) v /= __ldg(kscale + k0 + k);
       int d[S];
       digits_of(v * inv, d);
 #pragma unroll
       for (int s = 0; s < S; ++s) w[s][k / 4] |= static_cast<uint32_t>(d[s] & 0xFF) << (8 * (k % 4));
     }
   }
-  int8_t* dst = blob + ((long long)J * (K / KSTEP) + k0 / KSTEP) * B_STEP + ((k0 / 16) % 2) * 128 + (c / 8) * 256 +
+  int8_t* dst = blob + ((long long)J * (K / KSTEP) + k0 / KSTEP) * STEP + ((k0 / 16) % 2) * 128 + (c / 8) * 256 +
                 (c % 8) * 16;
 #pragma unroll
   for (int s = 0; s < S; ++s)
-    *reinterpret_cast<uint4*>(dst + s * (TN * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    *reinterpret_cast<uint4*>(dst + s * (COLS * KSTEP)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
 }
 
 struct GemmI8Args {
@@ -786,7 +790,7 @@ __device__ __forceinline__ bool gemm_tile_of(const GemmI8Args& a, long long t, i
   const int ii = ((r & 3) + static_cast<int>((t >> 2) & 3)) & 3;
   I = a.nI - 1 - (4 * g + ii);
   if (I < 0) return false;
-  ks0 = a.tri == kTriGemmBLower ? (J * TN) / KSTEP : 0;
+  ks0 = a.tri == kTriGemmBLower ? (J * TN) / KSTEP : (a.tri == kTriGemmTnLower ? max(I * TM, J * TN) / KSTEP : 0);
   ks1 = a.tri == kTriGemmALower ? min(a.nks, 4 * (I + 1)) : a.nks;
   return ks1 > ks0;
 }
@@ -931,7 +935,7 @@ static int run_gemm(int M, int N, int K, double alpha, const double* A, int lda,
   colmax_rect_kernel<<<dim3(ceil_div(N, 128), ceil_div(K, 256)), 128, 0, stream>>>(B, ldb, K, N, tri, 256, kscale,
                                                                                    colmax);
   BCBF_LAUNCH_CHECK();
-  split_cols_kernel<<<dim3(ceil_div(N, 128), K / 16), 128, 0, stream>>>(B, ldb, K, N, tri, kscale, colmax,
+  split_cols_kernel<TN><<<dim3(ceil_div(N, 128), K / 16), 128, 0, stream>>>(B, ldb, K, N, tri, kscale, colmax,
                                                                        static_cast<int8_t*>(bblob), colscale);
   BCBF_LAUNCH_CHECK();
   GemmI8Args a{};
@@ -946,6 +950,57 @@ static int run_gemm(int M, int N, int K, double alpha, const double* A, int lda,
   a.nJ = nJ;
   a.nks = nks;
   a.tri = tri;
+  a.total_tiles = (long long)ceil_div(nI, 4) * 4 * nJ;
+  int dev = 0, sms = 148;
+  BCBF_CUDA(cudaGetDevice(&dev));
+  BCBF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  BCBF_CUDA(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const int grid = a.total_tiles < sms ? static_cast<int>(a.total_tiles) : sms;
+  oz_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+// C (M,N) = alpha A^T B with A (K,M) and B (K,N) row-major.  lower != 0: both are square lower triangular (K = M = N), the
+// K steps below max(i, j) are skipped (Kb^-1 = L^-T L^-1 of the log-marginal gradient).  Both operands are
+// split by columns; no inner balancing (for A = B the two K profiles coincide).
+static int run_gemm_tn(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C,
+                       int ldc, int lower, cudaStream_t stream) {
+  const int nI = M / TM, nJ = N / TN, nks = K / KSTEP;
+  const int tri = lower ? kTriGemmBLower : kTriGemmNone;
+  void *ablob, *bblob, *cols;
+  int rc;
+  if ((rc = workspace(5, (size_t)nI * nks * A_STEP, &ablob))) return rc;
+  if ((rc = workspace(6, (size_t)nJ * nks * B_STEP, &bblob))) return rc;
+  if ((rc = workspace(8, 16 * ((size_t)N + (size_t)M), &cols))) return rc;
+  unsigned long long* cmB = static_cast<unsigned long long*>(cols);
+  double* csB = reinterpret_cast<double*>(cmB + N);
+  unsigned long long* cmA = reinterpret_cast<unsigned long long*>(csB + N);
+  double* csA = reinterpret_cast<double*>(cmA + M);
+  BCBF_CUDA(cudaMemsetAsync(cmB, 0, sizeof(unsigned long long) * (size_t)N, stream));
+  BCBF_CUDA(cudaMemsetAsync(cmA, 0, sizeof(unsigned long long) * (size_t)M, stream));
+  colmax_rect_kernel<<<dim3(ceil_div(M, 128), ceil_div(K, 256)), 128, 0, stream>>>(A, lda, K, M, tri, 256, nullptr, cmA);
+  BCBF_LAUNCH_CHECK();
+  split_cols_kernel<TM><<<dim3(ceil_div(M, 128), K / 16), 128, 0, stream>>>(A, lda, K, M, tri, nullptr, cmA,
+                                                                           static_cast<int8_t*>(ablob), csA);
+  BCBF_LAUNCH_CHECK();
+  colmax_rect_kernel<<<dim3(ceil_div(N, 128), ceil_div(K, 256)), 128, 0, stream>>>(B, ldb, K, N, tri, 256, nullptr, cmB);
+  BCBF_LAUNCH_CHECK();
+  split_cols_kernel<TN><<<dim3(ceil_div(N, 128), K / 16), 128, 0, stream>>>(B, ldb, K, N, tri, nullptr, cmB,
+                                                                           static_cast<int8_t*>(bblob), csB);
+  BCBF_LAUNCH_CHECK();
+  GemmI8Args a{};
+  a.Ablob = static_cast<const int8_t*>(ablob);
+  a.Bblob = static_cast<const int8_t*>(bblob);
+  a.rowscale = csA;
+  a.colscale = csB;
+  a.C = C;
+  a.ldc = ldc;
+  a.alpha = alpha;
+  a.nI = nI;
+  a.nJ = nJ;
+  a.nks = nks;
+  a.tri = lower ? kTriGemmTnLower : kTriGemmNone;
   a.total_tiles = (long long)ceil_div(nI, 4) * 4 * nJ;
   int dev = 0, sms = 148;
   BCBF_CUDA(cudaGetDevice(&dev));
@@ -1194,6 +1249,18 @@ extern "C" int bcbf_oz_debug_counters(int enable, unsigned long long out[8]) {
     oz::g_dbg = nullptr;
   }
   return BCBF_OK;
+}
+
+extern "C" int bcbf_oz_gemm_tn(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                               double* C, int ldc, int lower, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(A && B && C, "bcbf_oz_gemm_tn: null pointer");
+  BCBF_REQUIRE(M > 0 && N > 0 && K > 0 && M % oz::TM == 0 && N % oz::TN == 0 && K % oz::KSTEP == 0 && K <= oz::kMaxNpad,
+               "bcbf_oz_gemm_tn: M=%d (multiple of 128), N=%d (of 64), K=%d (of 32, <= %d)", M, N, K, oz::kMaxNpad);
+  BCBF_REQUIRE(lda >= M && ldb >= N && ldc >= N && ldc % 2 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+               "bcbf_oz_gemm_tn: lda=%d ldb=%d ldc=%d (ldc even, C 16-byte aligned)", lda, ldb, ldc);
+  BCBF_REQUIRE(!lower || (M == K && N == K), "bcbf_oz_gemm_tn: lower-triangular mode needs square operands");
+  return oz::run_gemm_tn(M, N, K, alpha, A, lda, B, ldb, C, ldc, lower ? 1 : 0, stream);
 }
 
 extern "C" int bcbf_oz_update(int M, int N, int K, double alpha, const double* PA, int lda, const double* PB, int ldb,

@@ -62,7 +62,10 @@ class _MVGPLogMarginal(torch.autograd.Function):
         logdetA = (2.0 * torch.log(torch.diagonal(La_h)).sum()).to(dev)
         value = -0.5 * (quad + nout * logdetK + N * logdetA + N * nout * math.log(2 * math.pi))
         # ---- gradients (always needed by fit; computed eagerly) -----------------------------------------------
-        Pinv = ops.gemm(Linv, Linv, transa=True)                     # Kb^-1 = L^-T L^-1  (Npad, Npad)
+        if Linv.shape[0] >= 2048 and Linv.shape[0] <= ops.oz_max_npad():
+            Pinv = ops.oz_gemm_tn(Linv, Linv, lower=True)               # the same on the int8 tensor cores (exact digits)
+        else:
+            Pinv = ops.gemm(Linv, Linv, transa=True)                 # Kb^-1 = L^-T L^-1  (Npad, Npad)
         alphaAi = (alpha @ Ai).contiguous()
         g_s, g_ls, g_B = ops.gram_train_backward(X, UH, B_d, ls_d, s_f, Pinv.contiguous(), alphaAi, alpha)
         g_A = 0.5 * (Ai @ YtA @ Ai - N * Ai)

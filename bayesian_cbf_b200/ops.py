@@ -219,6 +219,17 @@ def oz_gemm(A, B, alpha=1.0, tri=0, out=None):
     return C
 
 
+def oz_gemm_tn(A, B, alpha=1.0, lower=False):
+    """C = alpha A^T B on the int8 tensor cores (bcbf_oz_gemm_tn); lower: A and B square lower triangular."""
+    assert A.is_cuda and B.is_cuda and A.stride(1) == 1 and B.stride(1) == 1
+    K, M = A.shape
+    N = B.shape[1]
+    C = torch.empty(M, N, dtype=torch.float64, device=A.device)
+    check(_lib.load().bcbf_oz_gemm_tn(M, N, K, float(alpha), _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(C), C.stride(0),
+                                      1 if lower else 0, _stream()))
+    return C
+
+
 def oz_update_(C, PA, PB, alpha=-1.0, lower=False):
     """C += alpha PA PB^T in place on the int8 tensor cores (bcbf_oz_update); lower: only tiles touching the lower triangle."""
     assert C.is_cuda and PA.stride(1) == 1 and PB.stride(1) == 1 and C.stride(1) == 1

@@ -197,6 +197,10 @@ int bcbf_oz_debug_counters(int enable, unsigned long long out[8]);
  * bcbf_trtri uses it for the large levels of the triangular inverse.                                                  */
 int bcbf_oz_gemm(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                  int tri, void* stream);
+/* C (M,N; ldc) = alpha * A^T B with A (K,M; lda), B (K,N; ldb) row-major, same size rules; lower != 0: A and B are square
+ * lower triangular (Kb^-1 = L^-T L^-1 of the log-marginal gradient; replaces the dense product in mll.py for N >= 2048). */
+int bcbf_oz_gemm_tn(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C,
+                    int ldc, int lower, void* stream);
 /* Rank-K update on the int8 tensor cores (oz_update_kernel):  C (M,N; ldc) += alpha * PA (M,K; lda) * PB (N,K; ldb)^T,
  * row-major, M % 128 == 0, N % 64 == 0, K % 32 == 0; lower != 0 (M == N): only the 128 x 64 tiles that touch the lower
  * triangle are updated (whole tiles, so the part of a diagonal tile above the diagonal receives the symmetric values).

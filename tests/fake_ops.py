@@ -183,3 +183,7 @@ def oz_split_factor(Linv):
 
 def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, want_cov=True):
     return posterior_blocks(digits, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=want_mean, want_cov=want_cov)
+
+
+def oz_gemm_tn(A, B, alpha=1.0, lower=False):
+    return alpha * (A.T @ B)

@@ -340,3 +340,20 @@ def test_posterior_var_i8_is_bit_identical_to_the_cpu_restatement(N, n, m, Q):
     Bk = ops.posterior_var_i8(digits, rowscale, Ks, G, _d(hyp.B), float(hyp.outputscale), p, Q).cpu().numpy()
     ref = Z.posterior_bk(Linv.cpu().numpy(), Ks.cpu().numpy()[:, :Q], G.cpu().numpy(), hyp.B.numpy(), float(hyp.outputscale))
     assert np.array_equal(Bk, ref)
+
+
+def test_oz_gemm_tn_lower_is_bit_identical_and_accurate():
+    """Kb^-1 = L^-T L^-1 through bcbf_oz_gemm_tn (column-split operands, K steps below max(i, j) skipped): bit-identical to
+    the CPU restatement, symmetric, and at FP64 level against the float64 product."""
+    from bayesian_cbf_b200 import ops
+    from oracle import ozaki_oracle as Z
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(51, 300, 3, 2, 4, box=2.0)
+    L, Linv, G, alpha, W = _fit_on_gpu(X, U, Xdot, hyp, jit)
+    P = ops.oz_gemm_tn(Linv, Linv, lower=True).cpu().numpy()
+    Lh = Linv.cpu().numpy()
+    ref = Z.gemm(Lh.T.copy(), Lh, balance=False)
+    assert np.array_equal(P, ref)
+    assert np.array_equal(P, P.T)
+    exact = (Lh.T.astype(np.longdouble) @ Lh.astype(np.longdouble)).astype(np.float64)
+    bound = np.abs(Lh).max(0)[:, None] * np.abs(Lh).max(0)[None, :]
+    assert (np.abs(P - exact) / bound).max() < Lh.shape[0] * 2.0 ** -50
