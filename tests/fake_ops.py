@@ -147,7 +147,8 @@ def installed(monkeypatch):
     me = globals()
     for name in ('padded', 'query_pad', 'gram_train', 'cross_gram', 'gram_ca', 'rbf_blocks', 'potrf_', 'trtri',
                  'trmm_lower', 'gemm', 'posterior_blocks', 'contract_u', 'socp_factor', 'cbc1_terms',
-                 'gram_train_backward', 'socp_solve'):
+                 'gram_train_backward', 'socp_solve', 'oz_max_npad', 'oz_split_factor', 'posterior_blocks_i8',
+                 'oz_gemm_tn'):
         monkeypatch.setattr(ops, name, me[name])
     import bayesian_cbf_b200.mll as mll
     monkeypatch.setattr(mll, '_need_cuda', lambda *t: None)
