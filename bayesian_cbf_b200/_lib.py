@@ -47,6 +47,13 @@ _SIGNATURES = {
     'bcbf_debug_counters': (c_int, [c_int, POINTER(ctypes.c_ulonglong * 8)]),
     'bcbf_dinv_elems': (c_longlong, [c_int]),
     'bcbf_gram_train': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    'bcbf_gram_train_lower': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    'bcbf_gram_resid_scratch_elems': (c_longlong, [c_int]),
+    'bcbf_gram_resid': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_double, _P, c_int, _P, c_int, c_int,
+                                _P, c_int, _P, c_longlong, _P]),
+    'bcbf_alpha_refine_scratch_elems': (c_longlong, [c_int, c_int, c_int]),
+    'bcbf_alpha_refine': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_double, _P, c_int, c_int, _P, c_int,
+                                  c_int, c_int, _P, _P, c_longlong, _P]),
     'bcbf_cross_gram': (c_int, [_P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     'bcbf_gram_ca': (c_int, [_P, _P, c_int, _P, _P, c_int, _P, _P, c_double, c_int, c_int, _P, c_int, _P]),
     'bcbf_gemm': (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, c_double, _P, c_int, _P]),
@@ -86,6 +93,7 @@ _SIGNATURES = {
     'bcbf_model_query_device': (c_int, [c_void_p, _P, _P, c_int, _P, _P, _P, _P, _P]),
     'bcbf_model_state': (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)] + [POINTER(c_void_p)] * 6),
     'bcbf_model_alloc_state': (c_int, [c_void_p, POINTER(Hyper), c_int]),
+    'bcbf_model_adopt': (c_int, [c_void_p]),
     'bcbf_model_fit_timing': (c_int, [c_void_p, POINTER(c_double * 5)]),
     'bcbf_oz_factor_bytes': (c_longlong, [c_int]),
     'bcbf_oz_max_npad': (c_int, []),

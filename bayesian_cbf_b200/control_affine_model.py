@@ -395,7 +395,7 @@ class ControlAffineRegressor(DynamicsModel):
         for ntry in range(cholesky_tries):
             eps = next(self._jitter_source) if self._jitter_source is not None else _draw_jitter(N, self.dtype)
             eps = eps.to(device=X64.device, dtype=torch.float64).contiguous()
-            Kb = ops.gram_train(X64, UH64, B64, ls, s)
+            Kb = ops.gram_train_lower(X64, UH64, B64, ls, s)
             try:
                 L, dinv = ops.potrf_(Kb, N, eps, factor)
                 break
@@ -406,6 +406,7 @@ class ControlAffineRegressor(DynamicsModel):
                 factor = factor * cholesky_perturb_scale
         self._cache['_Lpad'] = L
         self._cache['_Linv'] = ops.trtri(L, dinv)
+        self._cache['_jitter'] = (eps, factor)          # what was added to the diagonal: the alpha refinement needs it
         return L[:N, :N]
 
     def _perturbed_cholesky(self, k, B, Xtrain, UHtrain, cache_key="perturbed_cholesky"):
@@ -425,14 +426,11 @@ class ControlAffineRegressor(DynamicsModel):
             Y = targets.double() - UH64 @ C                           # Y = Xdot - UH C  (:525-532)
             Ypad = torch.zeros(Npad, Y.shape[1], dtype=torch.float64, device=Y.device)
             Ypad[:N] = Y
-            z = ops.trmm_lower(Linv, Ypad)
-            alpha = ops.trmm_lower(Linv, z.contiguous(), trans=True).contiguous()                   # Kb^-1 Y (:545)
-            # one refinement step against the factor itself (the explicit inverse carries eps * cond(L) of forward
-            # error; the residual Y - L L^T alpha does not): predicts like the reference's cholesky_solve
-            Lpad = self._cache['_Lpad']
-            r = Ypad - ops.trmm_lower(Lpad, ops.trmm_lower(Lpad, alpha, trans=True).contiguous())
-            z = ops.trmm_lower(Linv, r.contiguous())
-            self._cache['_alpha'] = (alpha + ops.trmm_lower(Linv, z.contiguous(), trans=True)).contiguous()
+            # Kb^-1 Y (:545, cholesky_solve there): explicit-inverse product + two refinement steps whose residual is taken
+            # against the factorised matrix itself in compensated arithmetic (bcbf_alpha_refine)
+            eps, factor = self._cache['_jitter']
+            self._cache['_alpha'] = ops.alpha_refine(Xtrain.double().contiguous(), UH64.contiguous(), B, ls, s, Linv, Ypad,
+                                                     eps, factor, iters=2).contiguous()
             G = torch.zeros(Npad, B.shape[0], dtype=torch.float64, device=Y.device)
             G[:N] = UH64 @ B
             self._cache['_G'] = G
@@ -721,6 +719,7 @@ class ControlAffineRegressor(DynamicsModel):
 
     def load_state_dict(self, state_dict):
         self.model.load_state_dict(state_dict['model'])
+        self.clear_cache()      # the cached factor / alpha / W belong to the previous parameters and train data
 
     def save(self, path='/tmp/saved.pickle'):
         torch.save(self.state_dict(), path)

@@ -135,12 +135,7 @@ __global__ void prep_train_kernel(const double* __restrict__ U, const double* __
     for (int j = 0; j < m; ++j) uh[j + 1] = U[(long long)i * m + j];
     for (int j = 0; j < p; ++j) UH[(long long)i * p + j] = uh[j];
   }
-  for (int j = 0; j < p; ++j) {
-    double g = 0.0;
-    if (i < N)
-      for (int t = 0; t < p; ++t) g = fma(uh[t], Bm[t * p + j], g);
-    G[(long long)i * p + j] = g;
-  }
+  for (int j = 0; j < p; ++j) G[(long long)i * p + j] = (i < N) ? g_entry(uh, Bm, p, j) : 0.0;
   for (int r = 0; r < ldy; ++r) {
     double y = 0.0;
     if (i < N && r < n) {
@@ -348,7 +343,11 @@ static int ensure_oz_digits(bcbf_model* m, cudaStream_t s, bool timed) {
     BCBF_CUDA(cudaEventRecord(e0, s));
   }
   int rc = bcbf_oz_split_factor(m->Linv, m->Npad, m->Npad, m->oz_digits, m->oz_rowscale, s);
-  if (rc) return rc;
+  if (rc) {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+  }
   if (timed) {
     BCBF_CUDA(cudaEventRecord(e1, s));
     BCBF_CUDA(cudaEventSynchronize(e1));
@@ -412,8 +411,11 @@ extern "C" int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int 
     if ((rc = dev_alloc(&m->UH, (size_t)Npad * BCBF_MAX_P_DIM))) return rc;
     if ((rc = dev_alloc(&m->G, (size_t)Npad * BCBF_MAX_P_DIM))) return rc;
     if ((rc = dev_alloc(&m->alpha, (size_t)Npad * BCBF_MAX_N_DIM))) return rc;
-    // Y, two scratch copies and the split partials of the transposed skinny products (finish_fit_from_factor)
-    if ((rc = dev_alloc(&m->Y, (size_t)Npad * BCBF_MAX_N_DIM * (3 + (size_t)ceil_div(Npad, 1024))))) return rc;
+    // Y followed by the scratch of bcbf_alpha_refine (two work copies, split partials of the transposed skinny
+    // products, (hi, lo) partials of the compensated residual)
+    if ((rc = dev_alloc(&m->Y, (size_t)Npad * BCBF_MAX_N_DIM +
+                                   (size_t)bcbf_alpha_refine_scratch_elems(Npad, Npad, BCBF_MAX_N_DIM))))
+      return rc;
     if ((rc = dev_alloc(&m->W, (size_t)Npad * BCBF_MAX_N_DIM * BCBF_MAX_P_DIM))) return rc;
     if ((rc = dev_alloc(&m->hyp_dev, (size_t)256))) return rc;
     if (!m->info) BCBF_CUDA(cudaMalloc(&m->info, sizeof(int)));
@@ -459,30 +461,75 @@ static int tri_mv(const double* T, int ld, int Npad, int trans, const double* x,
   return BCBF_OK;
 }
 
-static int finish_fit_from_factor(bcbf_model* m, bool have_factor) {
-  // alpha = Linv^T (Linv Y), then one step of iterative refinement against the factor itself,
-  //   r = Y - L (L^T alpha),  alpha += Linv^T (Linv r):
-  // the explicit inverse carries a forward error ~ eps * cond(L); the residual is formed with L (backward stable), so
-  // the refined alpha predicts like the reference's cholesky_solve (control_affine_model.py:545).  W = alpha (.) G.
-  // A rank that adopted a broadcast state has no L (have_factor = false) and keeps the broadcast alpha.
+extern "C" long long bcbf_alpha_refine_scratch_elems(int N, int Npad, int ldy) {
+  return (long long)Npad * ldy * (2 + ceil_div(Npad, kMvRows)) + bcbf_gram_resid_scratch_elems(N);
+}
+
+// alpha = Kb^-1 Y by iterative refinement (include/bcbf.h): start alpha0 = Linv^T (Linv Y), then `iters` times
+//   r = Y - (Kb + jscale diag(jitter)) alpha   [bcbf_gram_resid: Kb re-evaluated bit-identically, Dot2 accumulation]
+//   alpha += Linv^T (Linv r)
+// The explicit inverse carries a forward error ~ eps cond(L) (1e-8 relative at the bench shapes), so every step gains
+// ~8 digits; two steps leave alpha at the FP64 rounding of the exact solution of the factorised system.
+extern "C" int bcbf_alpha_refine(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                                 double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
+                                 const double* Linv, int ld, int Npad, const double* Y, int ldy, int nc, int iters,
+                                 double* alpha, double* scratch, long long scratch_elems, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(X && UH && Bmat && lengthscale && Linv && Y && alpha && scratch, "bcbf_alpha_refine: null pointer");
+  BCBF_REQUIRE(Npad > 0 && Npad % kBlk == 0 && N >= 1 && N <= Npad && ld >= Npad && nc >= 1 && nc <= ldy &&
+                   ldy <= kMvMaxC && iters >= 0,
+               "bcbf_alpha_refine: N=%d Npad=%d ld=%d nc=%d ldy=%d (<= %d) iters=%d", N, Npad, ld, nc, ldy, kMvMaxC, iters);
+  BCBF_REQUIRE(scratch_elems >= bcbf_alpha_refine_scratch_elems(N, Npad, ldy), "bcbf_alpha_refine: scratch too small");
+  double* t = scratch;
+  double* r = t + (size_t)Npad * ldy;
+  double* part = r + (size_t)Npad * ldy;
+  double* rs = part + (size_t)ceil_div(Npad, kMvRows) * Npad * ldy;
+  const long long rs_elems = bcbf_gram_resid_scratch_elems(N);
+  int rc;
+  if ((rc = tri_mv(Linv, ld, Npad, 0, Y, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;
+  if ((rc = tri_mv(Linv, ld, Npad, 1, t, ldy, ldy, 1.0, 0.0, nullptr, alpha, part, s))) return rc;
+  for (int it = 0; it < iters; ++it) {
+    BCBF_CUDA(cudaMemsetAsync(r, 0, sizeof(double) * (size_t)Npad * ldy, s));
+    if ((rc = bcbf_gram_resid(X, UH, Bmat, lengthscale, outputscale, N, n, p, jitter, jitter_scale, alpha, ldy, Y, ldy, nc,
+                              r, ldy, rs, rs_elems, s)))
+      return rc;
+    if ((rc = tri_mv(Linv, ld, Npad, 0, r, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;
+    if ((rc = tri_mv(Linv, ld, Npad, 1, t, ldy, ldy, 1.0, 1.0, alpha, alpha, part, s))) return rc;
+  }
+  return BCBF_OK;
+}
+
+constexpr int kRefineIters = 2;
+
+static int finish_fit_from_factor(bcbf_model* m, const double* djit, double jitter_scale) {
+  // alpha = Kb^-1 Y refined against the factorised matrix itself in compensated arithmetic (bcbf_alpha_refine); the
+  // reference's cholesky_solve (control_affine_model.py:545) is the backward-stable version of the same solve.
+  // W = alpha (.) G.
   const int n = m->hyp.n, p = m->hyp.p, Npad = m->Npad, ldy = ld_y(n);
   cudaStream_t s = m->stream;
-  double* t = m->Y + (size_t)Npad * ldy;          // scratch columns inside the Y buffer (6 x Npad x ldy)
-  double* r = t + (size_t)Npad * ldy;
-  double* part = r + (size_t)Npad * ldy;          // ceil(Npad / 1024) * Npad * ldy
-  int rc;
-  if ((rc = tri_mv(m->Linv, Npad, Npad, 0, m->Y, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;
-  if ((rc = tri_mv(m->Linv, Npad, Npad, 1, t, ldy, ldy, 1.0, 0.0, nullptr, m->alpha, part, s))) return rc;
-  if (have_factor) {
-    if ((rc = tri_mv(m->L, Npad, Npad, 1, m->alpha, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;   // L^T alpha
-    if ((rc = tri_mv(m->L, Npad, Npad, 0, t, ldy, ldy, -1.0, 1.0, m->Y, r, part, s))) return rc;            // Y - L (.)
-    if ((rc = tri_mv(m->Linv, Npad, Npad, 0, r, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;
-    if ((rc = tri_mv(m->Linv, Npad, Npad, 1, t, ldy, ldy, 1.0, 1.0, m->alpha, m->alpha, part, s))) return rc;
-  }
+  int rc = bcbf_alpha_refine(m->X, m->UH, m->hyp.B, m->hyp.lengthscale, m->hyp.outputscale, m->N, n, p, djit, jitter_scale,
+                             m->Linv, Npad, Npad, m->Y, ldy, n, kRefineIters, m->alpha, m->Y + (size_t)Npad * ldy,
+                             bcbf_alpha_refine_scratch_elems(m->N, Npad, ldy), s);
+  if (rc) return rc;
   build_w_kernel<<<ceil_div(Npad, 128), 128, 0, s>>>(m->alpha, ldy, m->G, Npad, n, p, m->W);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }
+
+namespace {
+// cudaEvents of one fit: destroyed on every exit path (the NOT_PD retry path returns early)
+struct FitEvents {
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int create() {
+    for (auto& e : ev) BCBF_CUDA(cudaEventCreate(&e));
+    return BCBF_OK;
+  }
+  ~FitEvents() {
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+};
+}  // namespace
 
 extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double* X, const double* U, const double* Xdot,
                               int N, const double* jitter, double jitter_scale) {
@@ -498,8 +545,9 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
     if ((rc = dev_alloc(&m->Kstar, (size_t)Npad * Npad))) return rc;
     m->cap_K = (size_t)Npad * Npad;
   }
-  cudaEvent_t ev[6];
-  for (auto& e : ev) BCBF_CUDA(cudaEventCreate(&e));
+  FitEvents fe;
+  if ((rc = fe.create())) return rc;
+  cudaEvent_t* ev = fe.ev;
   // stage inputs: U and Xdot go through the (not yet used) Linv buffer, jitter through dinv
   double* dU = m->Linv;
   double* dXdot = m->Linv + (size_t)N * BCBF_MAX_P_DIM;
@@ -508,14 +556,14 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
   if (mm > 0) BCBF_CUDA(cudaMemcpyAsync(dU, U, sizeof(double) * (size_t)N * mm, cudaMemcpyHostToDevice, s));
   BCBF_CUDA(cudaMemcpyAsync(dXdot, Xdot, sizeof(double) * (size_t)N * n, cudaMemcpyHostToDevice, s));
   if (jitter) {
-    djit = m->W;  // W is rebuilt at the end of fit; N doubles of it carry the jitter until potrf has consumed it
+    djit = m->W;  // W is rebuilt at the end of fit; N doubles of it carry the jitter until the refinement is done
     BCBF_CUDA(cudaMemcpyAsync(djit, jitter, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
   }
   BCBF_CUDA(cudaEventRecord(ev[0], s));
   prep_train_kernel<<<ceil_div(Npad, 128), 128, 0, s>>>(dU, dXdot, N, Npad, n, p, m->hyp_dev + 8, m->hyp_dev + 24,
                                                         m->UH, m->G, m->Y, ldy);
   BCBF_LAUNCH_CHECK();
-  rc = bcbf_gram_train(m->X, m->UH, hyp->B, hyp->lengthscale, hyp->outputscale, N, n, p, m->L, Npad, Npad, s);
+  rc = bcbf_gram_train_lower(m->X, m->UH, hyp->B, hyp->lengthscale, hyp->outputscale, N, n, p, m->L, Npad, Npad, s);
   if (rc) return rc;
   BCBF_CUDA(cudaEventRecord(ev[1], s));
   rc = bcbf_potrf(m->L, Npad, Npad, N, djit, jitter_scale, m->dinv, m->info, s);
@@ -526,7 +574,7 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
   rc = bcbf_trtri(m->L, m->dinv, m->Linv, m->Kstar, Npad, Npad, s);
   if (rc) return rc;
   BCBF_CUDA(cudaEventRecord(ev[3], s));
-  rc = finish_fit_from_factor(m, true);
+  rc = finish_fit_from_factor(m, djit, jitter_scale);
   if (rc) return rc;
   m->oz_split_ms = 0.0;
   if (m->var_path == 1 && Npad <= bcbf_oz_max_npad() && (rc = ensure_oz_digits(m, s, true))) return rc;
@@ -539,7 +587,6 @@ extern "C" int bcbf_model_fit(bcbf_model* m, const bcbf_hyper* hyp, const double
   }
   BCBF_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[4]));
   m->fit_ms[4] = ms;
-  for (auto& e : ev) cudaEventDestroy(e);
   m->fitted = true;
   return BCBF_OK;
 }
@@ -561,8 +608,15 @@ extern "C" int bcbf_model_state(bcbf_model* m, int* N, int* Npad, double** L, do
   if (G) *G = m->G;
   if (W) *W = m->W;
   if (Xtrain) *Xtrain = m->X;
-  // a rank that received the state by broadcast marks itself fitted by asking for it (its digits of L^-1 are
-  // rebuilt by the next query)
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_model_adopt(bcbf_model* m) {
+  // a rank that filled the buffers of bcbf_model_state from a broadcast declares them valid; its digits of L^-1 are
+  // rebuilt by the next query
+  BCBF_REQUIRE(m, "bcbf_model_adopt: null model");
+  BCBF_REQUIRE(m->Npad > 0 && m->Linv && m->alpha && m->G && m->W && m->X,
+               "bcbf_model_adopt: no state buffers (call bcbf_model_alloc_state first)");
   m->fitted = true;
   m->oz_ready = false;
   return BCBF_OK;

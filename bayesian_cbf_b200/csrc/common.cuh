@@ -65,6 +65,14 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// G[i, q] = sum_t UH[i, t] B[t, q] as one FMA chain over t — the ONE definition (Gram kernels, the residual of the alpha
+// refinement and the model handle's G rows must agree bit for bit)
+__device__ __forceinline__ double g_entry(const double* __restrict__ uh_row, const double* __restrict__ Bm, int p, int q) {
+  double g = 0.0;
+  for (int t = 0; t < p; ++t) g = __fma_rn(uh_row[t], Bm[t * p + q], g);
+  return g;
+}
+
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace bcbf

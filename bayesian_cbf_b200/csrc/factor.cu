@@ -54,7 +54,8 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
     a[r * kPad + c + 1] = (c + 1 <= r) ? v.y : 0.0;
   }
   __syncthreads();
-  if (tid < kBlk && jitter != nullptr && (k0 + tid) < N) a[tid * kPad + tid] += jscale * jitter[k0 + tid];
+  if (tid < kBlk && jitter != nullptr && (k0 + tid) < N)   // one rounding, as gram_resid_kernel re-creates the diagonal
+    a[tid * kPad + tid] = __fma_rn(jscale, jitter[k0 + tid], a[tid * kPad + tid]);
   __syncthreads();
 
   // ======================= Phase A: L L^T = block =======================================================

@@ -30,6 +30,33 @@ struct GramParams {
   int vec_ok;              // 16-byte stores allowed (even ld, aligned base)
 };
 
+// ---- one Gram entry; the ONE definition every kernel that needs Kb[i,j] uses, so that the train Gram, the compensated
+// residual (gram_resid_kernel) and the ensembles see bit-identical values.  Every operation is spelled out (no
+// compiler-chosen contraction): d2 = fma chain over the state dimensions of (x_i/l - x_j/l)^2, k = s * exp(-d2/2),
+// S = fma chain over q of g_i[q] * uh_j[q], entry = k * S.
+template <int NN>
+__device__ __forceinline__ double rbf_entry(const double* __restrict__ xr, const double* __restrict__ xc, int n,
+                                            double scale) {
+  const int nn = NN > 0 ? NN : n;
+  double d2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < kMaxN; ++d)
+    if (d < nn) {
+      const double df = __dsub_rn(xr[d], xc[d]);
+      d2 = __fma_rn(df, df, d2);
+    }
+  return __dmul_rn(scale, exp(__dmul_rn(-0.5, d2)));
+}
+template <int PP>
+__device__ __forceinline__ double ub_entry(const double* __restrict__ g, const double* __restrict__ u, int p) {
+  const int pp = PP > 0 ? PP : p;
+  double ub = 0.0;
+#pragma unroll
+  for (int q = 0; q < kMaxP; ++q)
+    if (q < pp) ub = __fma_rn(g[q], u[q], ub);
+  return ub;
+}
+
 template <bool TRAIN>
 __global__ void __launch_bounds__(256) gram_kernel(GramParams P) {
   __shared__ double xr[kGT][kMaxN + 1], xc[kGT][kMaxN + 1];
@@ -39,16 +66,13 @@ __global__ void __launch_bounds__(256) gram_kernel(GramParams P) {
   const int n = P.n, p = P.p;
   for (int idx = tid; idx < kGT * n; idx += 256) {
     int r = idx / n, d = idx % n;
-    xr[r][d] = (r0 + r < P.a) ? P.X1[(long long)(r0 + r) * n + d] * P.inv_ls[d] : 0.0;
-    xc[r][d] = (c0 + r < P.c) ? P.X2[(long long)(c0 + r) * n + d] * P.inv_ls[d] : 0.0;
+    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], P.inv_ls[d]) : 0.0;
+    xc[r][d] = (c0 + r < P.c) ? __dmul_rn(P.X2[(long long)(c0 + r) * n + d], P.inv_ls[d]) : 0.0;
   }
   if (TRAIN) {
     for (int idx = tid; idx < kGT * p; idx += 256) {
       int r = idx / p, q = idx % p;
-      double g = 0.0;
-      if (r0 + r < P.a)
-        for (int t = 0; t < p; ++t) g += P.UH[(long long)(r0 + r) * p + t] * P.Bm[t * p + q];
-      gr[r][q] = g;
+      gr[r][q] = (r0 + r < P.a) ? g_entry(P.UH + (long long)(r0 + r) * p, P.Bm, p, q) : 0.0;
       uc[r][q] = (c0 + r < P.c) ? P.UH2[(long long)(c0 + r) * p + q] : 0.0;
     }
   }
@@ -64,17 +88,8 @@ __global__ void __launch_bounds__(256) gram_kernel(GramParams P) {
       const int cl = tx * 4 + j, col = c0 + cl;
       double out = 0.0;
       if (row < P.a && col < P.c) {
-        double d2 = 0.0;
-        for (int d = 0; d < n; ++d) {
-          double df = xr[rl][d] - xc[cl][d];
-          d2 = fma(df, df, d2);
-        }
-        out = P.scale * exp(-0.5 * d2);
-        if (TRAIN) {
-          double ub = 0.0;
-          for (int q = 0; q < p; ++q) ub = fma(gr[rl][q], uc[cl][q], ub);
-          out *= ub;
-        }
+        out = rbf_entry<0>(xr[rl], xc[cl], n, P.scale);
+        if (TRAIN) out = __dmul_rn(out, ub_entry<0>(gr[rl], uc[cl], p));
       } else if (TRAIN && P.pad_identity && row == col) {
         out = 1.0;
       }
@@ -89,6 +104,232 @@ __global__ void __launch_bounds__(256) gram_kernel(GramParams P) {
       for (int j = 0; j < 4; ++j)
         if (col + j < P.cols_out) dst[j] = v[j];
     }
+  }
+}
+
+// lower tile index t -> (bi, bj), bj <= bi, row-major over the lower triangle
+__device__ __forceinline__ void lower_tile(int t, int& bi, int& bj) {
+  bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((long long)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while ((long long)bi * (bi + 1) / 2 > t) --bi;
+  bj = t - bi * (bi + 1) / 2;
+}
+
+// ---- the train Gram of the fit path: compile-time state / control dimensions, operands of the thread's 4x4 outputs in
+// registers (the generic kernel above re-reads shared memory inside its run-time loops: 2.8 ms at N = 16384), and with
+// LOWER only the 64x64 tiles on or below the diagonal are produced (half the exps and half the bytes: the factorisation
+// reads nothing else; diagonal tiles are written whole).  Entry (i, j), j <= i, is rbf(i,j) * (g_i . uh_j); the upper
+// part of a full matrix mirrors it (entry(j, i) evaluated as rbf(j,i) * (g_j . uh_i), the same bits as its mirror image).
+template <int NN, int PP, bool LOWER>
+__global__ void __launch_bounds__(256) gram_train_kernel(GramParams P) {
+  __shared__ double xr[kGT][kMaxN + 1], xc[kGT][kMaxN + 1];
+  __shared__ double gr[kGT][kMaxP + 1], ur[kGT][kMaxP + 1], gc[kGT][kMaxP + 1], uc[kGT][kMaxP + 1];
+  const int tid = threadIdx.x;
+  int bi, bj;
+  if (LOWER) lower_tile(blockIdx.x, bi, bj);
+  else { bi = blockIdx.y; bj = blockIdx.x; }
+  const int r0 = bi * kGT, c0 = bj * kGT;
+  const int n = NN > 0 ? NN : P.n, p = PP > 0 ? PP : P.p;
+  for (int idx = tid; idx < kGT * n; idx += 256) {
+    int r = idx / n, d = idx % n;
+    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], P.inv_ls[d]) : 0.0;
+    xc[r][d] = (c0 + r < P.a) ? __dmul_rn(P.X1[(long long)(c0 + r) * n + d], P.inv_ls[d]) : 0.0;
+  }
+  for (int idx = tid; idx < kGT * p; idx += 256) {
+    int r = idx / p, q = idx % p;
+    const bool vr = r0 + r < P.a, vc = c0 + r < P.a;
+    gr[r][q] = vr ? g_entry(P.UH + (long long)(r0 + r) * p, P.Bm, p, q) : 0.0;
+    ur[r][q] = vr ? P.UH[(long long)(r0 + r) * p + q] : 0.0;
+    gc[r][q] = vc ? g_entry(P.UH + (long long)(c0 + r) * p, P.Bm, p, q) : 0.0;
+    uc[r][q] = vc ? P.UH[(long long)(c0 + r) * p + q] : 0.0;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  // strictly-lower tile: rows give g, columns give uh.  strictly-upper tile (full mode only): the mirror image, rows
+  // give uh and columns give g (same products in the same order).  diagonal tile: chosen per entry.
+  const bool upper = bi < bj, diag = bi == bj;
+  double xa[4][kMaxN], xb[4][kMaxN], ga[4][kMaxP], ub[4][kMaxP];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int d = 0; d < kMaxN; ++d)
+      if (d < n) { xa[i][d] = xr[ty * 4 + i][d]; xb[i][d] = xc[tx * 4 + i][d]; }
+#pragma unroll
+    for (int q = 0; q < kMaxP; ++q)
+      if (q < p) {
+        ga[i][q] = upper ? ur[ty * 4 + i][q] : gr[ty * 4 + i][q];
+        ub[i][q] = upper ? gc[tx * 4 + i][q] : uc[tx * 4 + i][q];
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = ty * 4 + i, row = r0 + rl;
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cl = tx * 4 + j, col = c0 + cl;
+      double out = 0.0;
+      if (row < P.a && col < P.a) {
+        out = rbf_entry<NN>(xa[i], xb[j], n, P.scale);
+        double s = ub_entry<PP>(ga[i], ub[j], p);
+        if (diag && col > row) s = ub_entry<PP>(ur[rl], gc[cl], p);
+        out = __dmul_rn(out, s);
+      } else if (row == col) {
+        out = 1.0;   // identity on the pad diagonal
+      }
+      v[j] = out;
+    }
+    if (row < P.rows_out) {
+      double* dst = P.out + (long long)row * P.ld + c0 + tx * 4;
+      *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+    }
+  }
+}
+
+// ---- compensated residual  R = Y - (Kb + jscale diag(jitter)) alpha  with Kb re-evaluated on the fly --------------------
+// The iterative refinement of alpha = Kb^-1 Y (reference: cholesky_solve, control_affine_model.py:545) needs the residual
+// against the matrix that was factorised, in more than working precision: Kb's condition number is 1e10..1e13 at the
+// bench shapes and the posterior mean is a sum with 1e6-fold cancellation.  Kb is not kept (the factor overwrites it);
+// its entries are recomputed here with the same device functions as gram_train_kernel — bit-identical — and every
+// product Kb[i,k] alpha[k,c] is accumulated exactly-rounded twice: TwoProduct (one FMA) + TwoSum into a (hi, lo) pair per
+// row and column (Ogita-Rump-Oishi Dot2: the result is as if computed in ~106-bit arithmetic and rounded once).
+// One CTA = 64 rows x one column range; thread = 4 x 4 entries per 64 x 64 tile; the 16 threads of a row are merged by
+// shuffles, the column ranges by a fixed-order (hi, lo) sum in gram_resid_finalize_kernel: deterministic.
+__device__ __forceinline__ void dd_add_prod(double& hi, double& lo, double a, double b) {
+  const double pr = __dmul_rn(a, b);
+  const double pe = __fma_rn(a, b, -pr);            // a*b = pr + pe exactly
+  const double s = __dadd_rn(hi, pr);
+  const double bb = __dsub_rn(s, hi);
+  const double se = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(pr, bb));   // hi + pr = s + se exactly
+  hi = s;
+  lo = __dadd_rn(lo, __dadd_rn(pe, se));
+}
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double h2, double l2) {
+  const double s = __dadd_rn(hi, h2);
+  const double bb = __dsub_rn(s, hi);
+  const double se = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(h2, bb));
+  hi = s;
+  lo = __dadd_rn(lo, __dadd_rn(l2, se));
+}
+
+constexpr int kResMaxC = 4;   // columns of alpha handled per pass (n <= 4 in one pass; larger n loops)
+
+template <int NN, int PP>
+__global__ void __launch_bounds__(256) gram_resid_kernel(GramParams P, const double* __restrict__ jitter, double jscale,
+                                                         const double* __restrict__ alpha, int lda, int cfirst, int nc,
+                                                         int tiles_per_split, double* __restrict__ partial) {
+  __shared__ double xr[kGT][kMaxN + 1], xc[kGT][kMaxN + 1];
+  __shared__ double gr[kGT][kMaxP + 1], ur[kGT][kMaxP + 1], gc[kGT][kMaxP + 1], uc[kGT][kMaxP + 1];
+  __shared__ double al[kGT][kResMaxC];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int bi = blockIdx.x, r0 = bi * kGT;
+  const int n = NN > 0 ? NN : P.n, p = PP > 0 ? PP : P.p;
+  const int ntiles = (P.a + kGT - 1) / kGT;
+  const int t0 = blockIdx.y * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
+  for (int idx = tid; idx < kGT * n; idx += 256) {
+    int r = idx / n, d = idx % n;
+    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], P.inv_ls[d]) : 0.0;
+  }
+  for (int idx = tid; idx < kGT * p; idx += 256) {
+    int r = idx / p, q = idx % p;
+    const bool vr = r0 + r < P.a;
+    gr[r][q] = vr ? g_entry(P.UH + (long long)(r0 + r) * p, P.Bm, p, q) : 0.0;
+    ur[r][q] = vr ? P.UH[(long long)(r0 + r) * p + q] : 0.0;
+  }
+  double hi[4][kResMaxC], lo[4][kResMaxC];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < kResMaxC; ++c) hi[i][c] = lo[i][c] = 0.0;
+  for (int bj = t0; bj < t1; ++bj) {
+    const int c0 = bj * kGT;
+    __syncthreads();
+    for (int idx = tid; idx < kGT * n; idx += 256) {
+      int r = idx / n, d = idx % n;
+      xc[r][d] = (c0 + r < P.a) ? __dmul_rn(P.X1[(long long)(c0 + r) * n + d], P.inv_ls[d]) : 0.0;
+    }
+    for (int idx = tid; idx < kGT * p; idx += 256) {
+      int r = idx / p, q = idx % p;
+      const bool vc = c0 + r < P.a;
+      gc[r][q] = vc ? g_entry(P.UH + (long long)(c0 + r) * p, P.Bm, p, q) : 0.0;
+      uc[r][q] = vc ? P.UH[(long long)(c0 + r) * p + q] : 0.0;
+    }
+    for (int idx = tid; idx < kGT * kResMaxC; idx += 256) {
+      int r = idx / kResMaxC, c = idx % kResMaxC;
+      al[r][c] = (c0 + r < P.a && c < nc) ? alpha[(long long)(c0 + r) * lda + cfirst + c] : 0.0;
+    }
+    __syncthreads();
+    const bool upper = bi < bj, diag = bi == bj;
+    double xa[4][kMaxN], xb[4][kMaxN], ga[4][kMaxP], ub[4][kMaxP];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int d = 0; d < kMaxN; ++d)
+        if (d < n) { xa[i][d] = xr[ty * 4 + i][d]; xb[i][d] = xc[tx * 4 + i][d]; }
+#pragma unroll
+      for (int q = 0; q < kMaxP; ++q)
+        if (q < p) {
+          ga[i][q] = upper ? ur[ty * 4 + i][q] : gr[ty * 4 + i][q];
+          ub[i][q] = upper ? gc[tx * 4 + i][q] : uc[tx * 4 + i][q];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cl = tx * 4 + j, col = c0 + cl;
+      double av[kResMaxC];
+#pragma unroll
+      for (int c = 0; c < kResMaxC; ++c) av[c] = al[cl][c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = ty * 4 + i, row = r0 + rl;
+        if (row < P.a && col < P.a) {
+          double k = rbf_entry<NN>(xa[i], xb[j], n, P.scale);
+          double s = ub_entry<PP>(ga[i], ub[j], p);
+          if (diag && col > row) s = ub_entry<PP>(ur[rl], gc[cl], p);
+          k = __dmul_rn(k, s);
+          if (diag && col == row && jitter != nullptr) k = __fma_rn(jscale, jitter[row], k);   // as potf2_inv_kernel adds it
+#pragma unroll
+          for (int c = 0; c < kResMaxC; ++c)
+            if (c < nc) dd_add_prod(hi[i][c], lo[i][c], k, av[c]);
+        }
+      }
+    }
+  }
+  // merge the 16 threads (tx) that share a row: xor-shuffles inside the half-warp, fixed pattern
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < kResMaxC; ++c) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const double h2 = __shfl_xor_sync(0xffffffffu, hi[i][c], o);
+        const double l2 = __shfl_xor_sync(0xffffffffu, lo[i][c], o);
+        dd_add(hi[i][c], lo[i][c], h2, l2);
+      }
+      if (tx == 0 && c < nc) {
+        double* dst = partial + (((long long)blockIdx.y * gridDim.x * kGT + r0 + ty * 4 + i) * kResMaxC + c) * 2;
+        dst[0] = hi[i][c];
+        dst[1] = lo[i][c];
+      }
+    }
+}
+
+__global__ void gram_resid_finalize_kernel(const double* __restrict__ partial, int nsplit, int rows_padded, int N,
+                                           const double* __restrict__ Y, int ldy, int cfirst, int nc,
+                                           double* __restrict__ R, int ldr) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_padded * kResMaxC) return;
+  const int row = idx / kResMaxC, c = idx % kResMaxC;
+  if (c >= nc) return;
+  double hi = 0.0, lo = 0.0;
+  if (row < N) {
+    for (int s = 0; s < nsplit; ++s) {
+      const double* src = partial + (((long long)s * rows_padded + row) * kResMaxC + c) * 2;
+      dd_add(hi, lo, src[0], src[1]);
+    }
+    // y - (hi + lo): y and hi agree to many digits once alpha is close, so y - hi is exact (Sterbenz) or nearly so
+    R[(long long)row * ldr + cfirst + c] = __dsub_rn(__dsub_rn(Y[(long long)row * ldy + cfirst + c], hi), lo);
   }
 }
 
@@ -243,24 +484,99 @@ static int fill_common(GramParams& P, const double* lengthscale, double outputsc
 
 using namespace bcbf;
 
-extern "C" int bcbf_gram_train(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
-                               double outputscale, int N, int n, int p, double* Kb, int ld, int Npad,
-                               void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// dispatch on the compile-time (n, p) pairs of the reference's systems (unicycle 3/3, pendulum 2/2); anything else runs
+// the same kernel with run-time extents
+template <bool LOWER>
+static void launch_gram_train(const GramParams& P, dim3 grid, cudaStream_t stream) {
+  if (P.n == 3 && P.p == 3) gram_train_kernel<3, 3, LOWER><<<grid, 256, 0, stream>>>(P);
+  else if (P.n == 2 && P.p == 2) gram_train_kernel<2, 2, LOWER><<<grid, 256, 0, stream>>>(P);
+  else gram_train_kernel<0, 0, LOWER><<<grid, 256, 0, stream>>>(P);
+}
+
+static int gram_train_impl(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                           double outputscale, int N, int n, int p, double* Kb, int ld, int Npad, bool lower,
+                           cudaStream_t stream) {
   BCBF_REQUIRE(X && UH && Bmat && lengthscale && Kb, "bcbf_gram_train: null pointer");
   BCBF_REQUIRE(n >= 1 && n <= kMaxN && p >= 1 && p <= kMaxP, "bcbf_gram_train: n=%d (<=%d) p=%d (<=%d)", n, kMaxN,
                p, kMaxP);
-  BCBF_REQUIRE(N >= 1 && Npad >= N && Npad % 2 == 0 && ld >= Npad && ld % 2 == 0,
-               "bcbf_gram_train: N=%d Npad=%d ld=%d", N, Npad, ld);
+  BCBF_REQUIRE(N >= 1 && Npad >= N && Npad % kGT == 0 && ld >= Npad && ld % 2 == 0 &&
+                   (reinterpret_cast<uintptr_t>(Kb) & 15) == 0,
+               "bcbf_gram_train: N=%d Npad=%d (multiple of %d) ld=%d (even), Kb 16-byte aligned", N, Npad, kGT, ld);
   GramParams P{};
   int rc = fill_common(P, lengthscale, outputscale, n, stream);
   if (rc != BCBF_OK) return rc;
   if ((rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
   P.X1 = X; P.X2 = X; P.UH = UH; P.UH2 = UH; P.a = N; P.c = N; P.p = p;
   P.out = Kb; P.ld = ld; P.rows_out = Npad; P.cols_out = Npad; P.pad_identity = 1; P.vec_ok = 1;
-  dim3 grid(ceil_div(Npad, kGT), ceil_div(Npad, kGT));
-  gram_kernel<true><<<grid, 256, 0, stream>>>(P);
+  const int nt = Npad / kGT;
+  if (lower) launch_gram_train<true>(P, dim3(nt * (nt + 1) / 2), stream);
+  else launch_gram_train<false>(P, dim3(nt, nt), stream);
   BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_gram_train(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                               double outputscale, int N, int n, int p, double* Kb, int ld, int Npad,
+                               void* stream_) {
+  return gram_train_impl(X, UH, Bmat, lengthscale, outputscale, N, n, p, Kb, ld, Npad, false,
+                         static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int bcbf_gram_train_lower(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                                     double outputscale, int N, int n, int p, double* Kb, int ld, int Npad,
+                                     void* stream_) {
+  return gram_train_impl(X, UH, Bmat, lengthscale, outputscale, N, n, p, Kb, ld, Npad, true,
+                         static_cast<cudaStream_t>(stream_));
+}
+
+// column splits of the residual: enough CTAs for ~6 waves of the machine, at most one split per column tile
+static void resid_splits(int N, int* nsplit, int* tiles_per_split) {
+  const int T = (N + kGT - 1) / kGT;
+  int S = (888 + T - 1) / T;
+  if (S > T) S = T;
+  if (S < 1) S = 1;
+  const int tps = (T + S - 1) / S;
+  *tiles_per_split = tps;
+  *nsplit = (T + tps - 1) / tps;
+}
+
+extern "C" long long bcbf_gram_resid_scratch_elems(int N) {
+  int S, tps;
+  resid_splits(N, &S, &tps);
+  const long long T = (N + kGT - 1) / kGT;
+  return (long long)S * T * kGT * kResMaxC * 2;
+}
+
+extern "C" int bcbf_gram_resid(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                               double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
+                               const double* alpha, int lda, const double* Y, int ldy, int nc, double* R, int ldr,
+                               double* scratch, long long scratch_elems, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(X && UH && Bmat && lengthscale && alpha && Y && R && scratch, "bcbf_gram_resid: null pointer");
+  BCBF_REQUIRE(n >= 1 && n <= kMaxN && p >= 1 && p <= kMaxP && N >= 1 && nc >= 1 && nc <= kMaxN && lda >= nc &&
+                   ldy >= nc && ldr >= nc,
+               "bcbf_gram_resid: N=%d n=%d p=%d nc=%d lda=%d ldy=%d ldr=%d", N, n, p, nc, lda, ldy, ldr);
+  BCBF_REQUIRE(scratch_elems >= bcbf_gram_resid_scratch_elems(N), "bcbf_gram_resid: scratch too small (%lld < %lld)",
+               scratch_elems, bcbf_gram_resid_scratch_elems(N));
+  GramParams P{};
+  int rc = fill_common(P, lengthscale, outputscale, n, stream);
+  if (rc != BCBF_OK) return rc;
+  if ((rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
+  P.X1 = X; P.X2 = X; P.UH = UH; P.UH2 = UH; P.a = N; P.c = N; P.p = p;
+  int S, tps;
+  resid_splits(N, &S, &tps);
+  const int T = (N + kGT - 1) / kGT;
+  for (int cfirst = 0; cfirst < nc; cfirst += kResMaxC) {
+    const int ncp = (nc - cfirst) < kResMaxC ? (nc - cfirst) : kResMaxC;
+    dim3 grid(T, S);
+    if (n == 3 && p == 3) gram_resid_kernel<3, 3><<<grid, 256, 0, stream>>>(P, jitter, jitter_scale, alpha, lda, cfirst, ncp, tps, scratch);
+    else if (n == 2 && p == 2) gram_resid_kernel<2, 2><<<grid, 256, 0, stream>>>(P, jitter, jitter_scale, alpha, lda, cfirst, ncp, tps, scratch);
+    else gram_resid_kernel<0, 0><<<grid, 256, 0, stream>>>(P, jitter, jitter_scale, alpha, lda, cfirst, ncp, tps, scratch);
+    BCBF_LAUNCH_CHECK();
+    gram_resid_finalize_kernel<<<ceil_div((long long)T * kGT * kResMaxC, 256), 256, 0, stream>>>(
+        scratch, S, T * kGT, N, Y, ldy, cfirst, ncp, R, ldr);
+    BCBF_LAUNCH_CHECK();
+  }
   return BCBF_OK;
 }
 

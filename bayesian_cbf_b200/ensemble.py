@@ -290,7 +290,8 @@ def fit_ensemble_hyperparameters(hp, X, U, Xdot, training_iter=100, lr=0.1, gene
     loss_r = None
     # the 1e-6 target noise of every iteration comes from a device generator seeded from the caller's (CPU) generator:
     # reproducible from the same seed without a 2.4 MB host draw + copy per iteration
-    seed = int(torch.randint(2 ** 62, (1,), generator=generator)) if generator is not None else torch.seed()
+    # (generator=None draws the seed from the global CPU stream: a run under torch.manual_seed stays reproducible)
+    seed = int(torch.randint(2 ** 62, (1,), generator=generator))
     dgen = torch.Generator(device=X.device).manual_seed(seed)
     _EnsembleLogMarginal.last_jitter = 0.0
     for _ in range(training_iter):

@@ -37,7 +37,7 @@ class _MVGPLogMarginal(torch.autograd.Function):
         jitter = 0.0
         L = dinv = None
         for attempt in range(7):          # psd-safe escalation like gpytorch's psd_safe_cholesky (1e-8 * 10^t)
-            Kb = ops.gram_train(X, UH, B_d, ls_d, s_f)
+            Kb = ops.gram_train_lower(X, UH, B_d, ls_d, s_f)
             try:
                 L, dinv = ops.potrf_(Kb, N, ones if jitter > 0 else None, jitter)
                 break

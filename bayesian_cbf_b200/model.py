@@ -101,6 +101,11 @@ class MVGPModel:
         self.N = int(N)
         check(self._lib.bcbf_model_alloc_state(self._h, ctypes.byref(hyper), self.N))
 
+    def adopt_state(self):
+        """Receiving ranks: the buffers of state_tensors() now hold a broadcast fit (bcbf_model_adopt)."""
+        check(self._lib.bcbf_model_adopt(self._h))
+        return self
+
     def state_tensors(self):
         """torch views (no copy) of the fitted state, in the order they are broadcast: Linv, L, alpha, G, W, X."""
         N, Npad = ctypes.c_int(), ctypes.c_int()

@@ -46,6 +46,58 @@ def gram_train(X, UH, B, lengthscale, outputscale, Npad=None):
     return Kb
 
 
+def gram_train_lower(X, UH, B, lengthscale, outputscale, Npad=None):
+    """Kb for the factorisation: only the 64x64 tiles on/below the diagonal (+ identity on the pad diagonal) are written;
+    the rest of the returned buffer is uninitialised (bcbf_potrf never reads it)."""
+    _req(X, UH, B, lengthscale)
+    N, n = X.shape
+    p = UH.shape[1]
+    Npad = padded(N) if Npad is None else Npad
+    Kb = torch.empty(Npad, Npad, dtype=torch.float64, device=X.device)
+    check(_lib.load().bcbf_gram_train_lower(_ptr(X), _ptr(UH), _ptr(B), _ptr(lengthscale), float(outputscale), N, n, p,
+                                            _ptr(Kb), Npad, Npad, _stream()))
+    return Kb
+
+
+def gram_resid(X, UH, B, lengthscale, outputscale, alpha, Y, jitter=None, jitter_scale=0.0):
+    """R = Y - (Kb + jitter_scale diag(jitter)) alpha with Kb re-evaluated on the fly and compensated (Dot2) accumulation
+    (bcbf_gram_resid).  alpha, Y (N, nc) -> R (N, nc)."""
+    _req(X, UH, B, lengthscale, alpha, Y, jitter)
+    N, n = X.shape
+    p = UH.shape[1]
+    nc = alpha.shape[1]
+    lib = _lib.load()
+    R = torch.zeros(N, nc, dtype=torch.float64, device=X.device)
+    ne = lib.bcbf_gram_resid_scratch_elems(N)
+    scratch = torch.empty(ne, dtype=torch.float64, device=X.device)
+    check(lib.bcbf_gram_resid(_ptr(X), _ptr(UH), _ptr(B), _ptr(lengthscale), float(outputscale), N, n, p, _ptr(jitter),
+                              float(jitter_scale), _ptr(alpha), alpha.stride(0), _ptr(Y), Y.stride(0), nc, _ptr(R),
+                              R.stride(0), _ptr(scratch), ne, _stream()))
+    return R
+
+
+def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, jitter_scale=0.0, iters=2):
+    """alpha (Npad, nc) = (Kb + jitter)^-1 Y: explicit-inverse product + `iters` compensated refinement steps
+    (bcbf_alpha_refine; reference cholesky_solve, control_affine_model.py:545).  Ypad (Npad, nc), pad rows zero."""
+    _req(X, UH, B, lengthscale, Linv, jitter)
+    _req(Ypad, contiguous=False)
+    N, n = X.shape
+    p = UH.shape[1]
+    Npad = Linv.shape[0]
+    nc = Ypad.shape[1]
+    ldy = (nc + 1) // 2 * 2
+    Yp = torch.zeros(Npad, ldy, dtype=torch.float64, device=X.device)
+    Yp[:, :nc] = Ypad
+    alpha = torch.empty(Npad, ldy, dtype=torch.float64, device=X.device)
+    lib = _lib.load()
+    ne = lib.bcbf_alpha_refine_scratch_elems(N, Npad, ldy)
+    scratch = torch.empty(ne, dtype=torch.float64, device=X.device)
+    check(lib.bcbf_alpha_refine(_ptr(X), _ptr(UH), _ptr(B), _ptr(lengthscale), float(outputscale), N, n, p, _ptr(jitter),
+                                float(jitter_scale), _ptr(Linv), Linv.stride(0), Npad, _ptr(Yp), ldy, nc, int(iters),
+                                _ptr(alpha), _ptr(scratch), ne, _stream()))
+    return alpha[:, :nc]
+
+
 def cross_gram(X, Xq, lengthscale, outputscale, Npad=None, ldks=None):
     """Kstar (Npad, ldks): k(X_i, Xq_j); pad rows/cols zero."""
     _req(X, Xq, lengthscale)

@@ -70,6 +70,8 @@ class ShardedPosterior:
         else:
             self.model.alloc_state(hyper, X.shape[0])
         self.broadcast_bytes = broadcast_state(self.model.state_tensors(), self.src, self.group)
+        if self.rank != self.src and hasattr(self.model, 'adopt_state'):
+            self.model.adopt_state()
         return self
 
     def query_shard(self, Xq_all, Uq_all=None, want=('mean', 'svar')):

@@ -251,6 +251,8 @@ def run_ours(args):
         e0.record()
         from bayesian_cbf_b200.sharding import broadcast_state
         broadcast_state(st, src=0)        # Linv, alpha, G, W, X — once; no collective during querying
+        if rank != 0:
+            model.adopt_state()
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
@@ -384,7 +386,26 @@ def run_ours(args):
         prior = float(hyp['outputscale'] * torch.linalg.matrix_norm(hyp['B'], 2))
         parity = dict(Bk_rel=float(np.abs(got['Bk'] - cBk.numpy()).max() / prior),
                       svar_rel=float(np.abs(got['svar'] - csvar.numpy()).max() / prior),
-                      mean_rel=float(np.abs(got['mean'] - cmean.numpy()).max() / max(1e-300, np.abs(cmean.numpy()).max())))
+                      mean_rel=float(np.abs(got['mean'] - cmean.numpy()).max() / max(1e-300, np.abs(cmean.numpy()).max())),
+                      mean_rel_note='against the reference-form LAPACK evaluation (gpytorch expanded-distance Gram, '
+                                    'cholesky_solve)')
+        if not args.no_parity_floor:
+            # the mean against the EXACT solution of the reference's linear system, next to the measured floor of the
+            # reference's own float64 arithmetic (oracle.mean_parity_floor; tests/parity_util.py explains the numbers)
+            from tests.parity_util import mean_reference
+            del Lc
+            t0 = time.perf_counter()
+            ref = mean_reference(oracle_hyper(hyp), X, U, Xdot, jitter, Xq_all[:qs], Uq_all[:qs])
+            sc = float(ref['mean_exact'].abs().max())
+            parity.update(mean_rel_exact=float(np.abs(got['mean'] - ref['mean_exact'].numpy()).max() / sc),
+                          Mk_rel_exact=float(np.abs(got['Mk'] - ref['Mk_exact'].numpy()).max()
+                                             / float(ref['Mk_exact'].abs().max())),
+                          floor_ulp_sensitivity=ref['ulp_sensitivity'], floor_lapack_vs_exact=ref['lapack_vs_exact'],
+                          tol_exact=ref['tol_exact'], tol_lapack=ref['tol_lapack'],
+                          floor_seconds=time.perf_counter() - t0,
+                          within_tolerance=bool(parity['Bk_rel'] < 1e-9 and parity['svar_rel'] < 1e-9))
+            parity['within_tolerance'] = bool(parity['within_tolerance'] and parity['mean_rel_exact'] < ref['tol_exact']
+                                              and parity['mean_rel'] < ref['tol_lapack'])
         cpu = dict(value=qs / cq_s, unit='queries/s', cores=cores, kind='port',
                    sample='N=%d: host Gram + Cholesky once (%.2f s), then %d queries in %.2f s (multi-RHS triangular '
                           'solve + per-query blocks, torch float64, %d threads)' % (N, cfit_s, qs, cq_s, cores),
@@ -427,6 +448,8 @@ def main():
     ap.add_argument('--cpu-sample-queries', type=int, default=2048)
     ap.add_argument('--ref-queries-per-step', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity-floor', action='store_true',
+                    help='skip the exact-solution / floor measurement of the mean parity (about a minute of host time)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.queries_per_step is None:

@@ -64,6 +64,26 @@ long long bcbf_dinv_elems(int Npad);
 int bcbf_gram_train(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
                     double outputscale, int N, int n, int p, double* Kb, int ld, int Npad, void* stream);
 
+/* The same, producing only what the factorisation reads: the 64 x 64 tiles on or below the diagonal (diagonal tiles whole)
+ * and the identity on the pad diagonal; storage above those tiles is left untouched.  Half the exps and half the bytes
+ * of bcbf_gram_train; entry (i, j), j <= i, has the same bits in both.  Npad must be a multiple of 64.  (Fit path.)   */
+int bcbf_gram_train_lower(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                          double outputscale, int N, int n, int p, double* Kb, int ld, int Npad, void* stream);
+
+/* Residual of the alpha solve against the matrix that was factorised, in compensated arithmetic:
+ *     R[:, :nc] = Y - (Kb + jitter_scale * diag(jitter)) alpha
+ * Kb is NOT read from memory (bcbf_potrf overwrote it with L): every entry is re-evaluated from X, UH, B exactly as
+ * bcbf_gram_train[_lower] produced it (bit-identical, diagonal jitter added with the same single rounding as bcbf_potrf),
+ * and the products are accumulated error-free (TwoProduct/TwoSum, Dot2), i.e. as if in ~106-bit arithmetic rounded once.
+ * alpha (N, lda), Y (N, ldy), R (N, ldr), nc <= 8 columns; scratch >= bcbf_gram_resid_scratch_elems(N) doubles.
+ * This is what lets the iterative refinement of bcbf_alpha_refine converge to the FP64 rounding of the exact solution
+ * although cond(Kb) ~ 1e10..1e13 (reference: alpha = torch.cholesky_solve(Y, L), control_affine_model.py:545).       */
+long long bcbf_gram_resid_scratch_elems(int N);
+int bcbf_gram_resid(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                    double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
+                    const double* alpha, int lda, const double* Y, int ldy, int nc, double* R, int ldr, double* scratch,
+                    long long scratch_elems, void* stream);
+
 /* Cross Gram  Kstar[i, j] = k(X_i, Xq_j)   (control_affine_model.py:536 / :1051, the k_xs / k_sx factor).
  *   X (N,n), Xq (Q,n) -> Kstar (Npad, ldks) row-major with ldks >= Q; rows >= N are written as zero.     */
 int bcbf_cross_gram(const double* X, const double* Xq, const double* lengthscale, double outputscale, int N,
@@ -129,6 +149,18 @@ int bcbf_set_trtri_i8(int on);
  * Used for  v = Linv @ kb*,  alpha = Linv^T (Linv Y).                                                  */
 int bcbf_trmm_lower(const double* A, int lda, int Npad, int trans, const double* B, int ldb, int ncols,
                     double alpha, double beta, double* C, int ldc, void* stream);
+
+/* alpha = (Kb + jitter_scale diag(jitter))^-1 Y  (control_affine_model.py:545, alpha = cholesky_solve(Y, L)):
+ * alpha0 = Linv^T (Linv Y) followed by `iters` steps of iterative refinement  alpha += Linv^T Linv (Y - Kb' alpha)  with
+ * the residual of bcbf_gram_resid.  Linv (Npad,Npad; ld) from bcbf_trtri; Y and alpha (Npad, ldy) with zero pad rows,
+ * nc <= ldy <= 8 columns in use (ldy even); jitter (N) / jitter_scale as given to bcbf_potrf (jitter may be NULL);
+ * scratch >= bcbf_alpha_refine_scratch_elems(N, Npad, ldy) doubles.  iters = 2 reaches the FP64 rounding of the exact
+ * solution at the bench shapes (each step gains ~8 digits); iters = 0 is the plain explicit-inverse product.         */
+long long bcbf_alpha_refine_scratch_elems(int N, int Npad, int ldy);
+int bcbf_alpha_refine(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                      double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
+                      const double* Linv, int ld, int Npad, const double* Y, int ldy, int nc, int iters, double* alpha,
+                      double* scratch, long long scratch_elems, void* stream);
 
 /* Row-major C(M,N) = alpha * op(A) op(B) + beta * C on the FP64 tensor-core GEMM.  op(A) is M x K: transa = 0 ->
  * A stored (M,K), 1 -> stored (K,M);  op(B) is K x N: transb = 0 -> stored (K,N), 1 -> stored (N,K).  M, N, K and
@@ -312,11 +344,13 @@ int bcbf_model_query(bcbf_model* m, const double* Xq, const double* Uq, int Q, d
 /* Same with DEVICE pointers on `stream`, asynchronous (used by the sharded bench and the Python host). */
 int bcbf_model_query_device(bcbf_model* m, const double* Xq, const double* Uq, int Q, double* mean, double* svar,
                             double* Mk, double* Bk, void* stream);
-/* Device pointers of the fitted state, for NCCL broadcast of the factor (multi-GPU: fit on one rank,
- * bcbf_model_adopt on the others).  Layout documented in DESIGN.md.                                       */
+/* Multi-GPU: one rank fits, the others bcbf_model_alloc_state, every rank reads the device pointers of the state with
+ * bcbf_model_state (a pure getter: it changes nothing), the buffers are broadcast (NCCL), and the receiving ranks call
+ * bcbf_model_adopt, which marks the handle fitted (BCBF_ERR_INVALID without allocated state).  Layout: DESIGN.md.      */
 int bcbf_model_state(bcbf_model* m, int* N, int* Npad, double** L, double** Linv, double** alpha, double** G,
                      double** W, double** Xtrain);
 int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int N);
+int bcbf_model_adopt(bcbf_model* m);
 /* Milliseconds spent in the stages of the last bcbf_model_fit (gram, potrf, trtri, alpha, total). */
 int bcbf_model_fit_timing(bcbf_model* m, double out_ms[5]);
 /* Which kernel computes B_k in bcbf_model_query*: 0 = FP64 tensor pipe (DMMA, post_var_kernel), 1 = int8 tensor cores

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — torch-CPU stand-ins for `bayesian_cbf_b200.ops` so that the HOST LOGIC of the drop-in API
 (shapes, index orders, caching, retry loops, autograd wiring) can be exercised by the `-m "not gpu"` suite against the
 reference-generated goldens.  The product never imports this module; on a GPU box the same tests run against the real
-CUDA ops (tests/test_gpu_host_api.py)."""
+CUDA ops (the `cuda` parametrisation of tests/test_host_api.py)."""
 import contextlib
 
 import torch
@@ -32,6 +32,26 @@ def gram_train(X, UH, B, lengthscale, outputscale, Npad=None):
     return Kb
 
 
+def gram_train_lower(X, UH, B, lengthscale, outputscale, Npad=None):
+    Kb = gram_train(X, UH, B, lengthscale, outputscale, Npad)
+    return torch.tril(Kb) + torch.triu(torch.full_like(Kb, float('nan')), 1)   # storage above the diagonal: "untouched"
+
+
+def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, jitter_scale=0.0, iters=2):
+    import numpy as np
+    N = X.shape[0]
+    Kb = _k(X, X, lengthscale, outputscale) * (UH @ B @ UH.T)
+    if jitter is not None:
+        Kb = Kb + jitter_scale * torch.diag(jitter)
+    alpha = Linv.T @ (Linv @ Ypad)
+    Kl, Yl = Kb.numpy().astype(np.longdouble), Ypad[:N].numpy().astype(np.longdouble)
+    for _ in range(iters):
+        r = torch.zeros_like(Ypad)
+        r[:N] = torch.from_numpy((Yl - Kl @ alpha[:N].numpy().astype(np.longdouble)).astype(np.float64))
+        alpha = alpha + Linv.T @ (Linv @ r)
+    return alpha
+
+
 def cross_gram(X, Xq, lengthscale, outputscale, Npad=None, ldks=None):
     N, Q = X.shape[0], Xq.shape[0]
     Npad = padded(N) if Npad is None else Npad
@@ -60,7 +80,8 @@ def rbf_blocks(X1, X2, lengthscale, outputscale, grad=False, hess=False):
 
 
 def potrf_(A, N, jitter=None, jitter_scale=1e-5, check_pd=True):
-    M = A.clone()
+    M = torch.tril(A)           # like bcbf_potrf, only the lower triangle is read
+    M = M + torch.tril(M, -1).T
     if jitter is not None:
         M[:N, :N] += jitter_scale * torch.diag(jitter)
     L, info = torch.linalg.cholesky_ex(M)
@@ -145,7 +166,7 @@ def installed(monkeypatch):
     import bayesian_cbf_b200.gp_modules as gm
     from bayesian_cbf_b200 import ops
     me = globals()
-    for name in ('padded', 'query_pad', 'gram_train', 'cross_gram', 'gram_ca', 'rbf_blocks', 'potrf_', 'trtri',
+    for name in ('padded', 'query_pad', 'gram_train', 'gram_train_lower', 'alpha_refine', 'cross_gram', 'gram_ca', 'rbf_blocks', 'potrf_', 'trtri',
                  'trmm_lower', 'gemm', 'posterior_blocks', 'contract_u', 'socp_factor', 'cbc1_terms',
                  'gram_train_backward', 'socp_solve', 'oz_max_npad', 'oz_split_factor', 'posterior_blocks_i8',
                  'oz_gemm_tn'):

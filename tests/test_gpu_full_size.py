@@ -1,5 +1,6 @@
-"""Parity at BASELINE.json's full size (N = 16384, the bench workload) through size-independent properties — the oracle
-cannot finish this size in test time, so the CUDA path is checked against identities the exact result must satisfy:
+"""Parity at BASELINE.json's full size (N = 16384, the bench workload): against the CPU oracle on 2048 of the bench's own
+queries (test_full_size_against_the_oracle: ~1 min of host time for the oracle's factorisations and the measured parity
+floor of the mean), and through size-independent identities the exact result must satisfy:
 
   * factor:   L (L^T z) = (Kb + jitter) z  and  L^-1 (L z) = z  for random probe vectors (a checksum of the N^2 entries);
   * posterior at the training inputs: the variance of F(x_i)[1;u_i] collapses to the jitter level and the mean
@@ -116,3 +117,39 @@ def test_int8_tensor_core_path_at_full_size(fitted):
     # integer arithmetic is exact and the tile a query lands in only changes which other columns share its MMAs:
     # permuting the queries permutes the answers bit for bit
     assert np.array_equal(outp['Bk'], out['Bk'][perm.numpy()])
+
+
+def test_full_size_against_the_oracle(fitted):
+    """CUDA (int8 tensor-core and FP64 DMMA covariance kernels) against oracle.posterior_blocks at N = 16384 on 2048 bench
+    queries.  Tolerances: B_k / svar 1e-9 of the prior scale; mean / M_k 1e-9 relative or the measured floor of the
+    reference's own arithmetic where that is larger (tests/parity_util.py) — against the exact solution of the reference's
+    linear system AND against its LAPACK evaluation."""
+    import bench
+    from oracle import mvgp_oracle as O
+    from tests.parity_util import mean_reference, rel
+    model, X, U, Xdot, hyp_d, jitter = fitted
+    hyp = bench.oracle_hyper(hyp_d)
+    Q = 2048
+    Xq, Uq = bench.make_queries(Q, 0)
+    torch.set_num_threads(max(1, __import__('os').cpu_count() or 1))
+    L = O.perturbed_cholesky(hyp, X, O.homogeneous(U), [jitter], direct=True)
+    Mk_o, Bk_o, mean_o, svar_o = O.posterior_blocks(hyp, X, U, Xdot, L, Xq, Uq, direct=True, chunk=1024)
+    del L
+    ref = mean_reference(hyp, X, U, Xdot, jitter, Xq, Uq)
+    prior = float(hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2))
+    report = {}
+    for path in ('int8', 'dmma'):
+        model.set_var_path(path)
+        try:
+            out = model.query(Xq.numpy(), Uq.numpy())
+        finally:
+            model.set_var_path('dmma')
+        r = dict(Bk=float(np.abs(out['Bk'] - Bk_o.numpy()).max() / prior),
+                 svar=float(np.abs(out['svar'] - svar_o.numpy()).max() / prior),
+                 mean_vs_exact=rel(out['mean'], ref['mean_exact']), Mk_vs_exact=rel(out['Mk'], ref['Mk_exact']),
+                 mean_vs_lapack=rel(out['mean'], mean_o), Mk_vs_lapack=rel(out['Mk'], Mk_o))
+        report[path] = r
+        print(path, r, {k: ref[k] for k in ('ulp_sensitivity', 'lapack_vs_exact', 'tol_exact', 'tol_lapack')})
+        assert r['Bk'] < 1e-9 and r['svar'] < 1e-9, r
+        assert r['mean_vs_exact'] < ref['tol_exact'] and r['Mk_vs_exact'] < ref['tol_exact'], (r, ref['tol_exact'])
+        assert r['mean_vs_lapack'] < ref['tol_lapack'] and r['Mk_vs_lapack'] < ref['tol_lapack'], (r, ref['tol_lapack'])
