@@ -56,6 +56,7 @@ _SIGNATURES = {
                                   c_int, c_int, _P, _P, c_longlong, _P]),
     'bcbf_cross_gram': (c_int, [_P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     'bcbf_gram_ca': (c_int, [_P, _P, c_int, _P, _P, c_int, _P, _P, c_double, c_int, c_int, _P, c_int, _P]),
+    'bcbf_ca_weight': (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P]),
     'bcbf_gemm': (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, c_double, _P, c_int, _P]),
     'bcbf_gram_train_backward': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, c_int,
                                          _P, c_longlong, _P, _P]),

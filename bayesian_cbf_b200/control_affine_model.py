@@ -464,9 +464,8 @@ class ControlAffineRegressor(DynamicsModel):
         """Posterior of F(x)[UHfill;u] with u folded in before the solve (reference :390-613, R&W Alg. 2.1):
         returns (mean (b,n), cov (1, b*n, b'*n) = scalar_var (x) A)  [or scalar_var (b,b') if scalar_var_only]."""
         if grad_gp:
-            raise NotImplementedError(
-                "grad_gp=True (reference :447-477, not exercised by its callers) is not provided; differentiate "
-                "custom_predict through autograd (GradientGP) or use ops.rbf_blocks for the closed-form blocks")
+            return self._custom_predict_grad(Xtest_in, Utest_in, UHfill, Xtestp_in, Utestp_in, UHfillp, compute_cov,
+                                             scalar_var_only)
         _need_cuda(self.device)
         Xtest = self._ensure_device_dtype(Xtest_in)
         Xtestp = self._ensure_device_dtype(Xtestp_in) if Xtestp_in is not None else Xtest
@@ -504,6 +503,64 @@ class ControlAffineRegressor(DynamicsModel):
         if scalar_var_only:
             return mean.to(out_dt), scalar_var.to(out_dt)
         return mean.to(out_dt), torch_kron(scalar_var.unsqueeze(0), A.unsqueeze(0)).to(out_dt)   # (:602)
+
+    def _custom_predict_grad(self, Xtest_in, Utest_in, UHfill, Xtestp_in, Utestp_in, UHfillp, compute_cov,
+                             scalar_var_only):
+        """custom_predict(grad_gp=True): posterior of the GRADIENT process d/dx [F(x)[UHfill;u]] (reference :447-477).
+
+        mean (b, n*n): entry [t, r*n + d] = d mean_r(x_t; u_t) / d x_{t,d}  (the layout of the reference's
+        `fu_mean_test` reshape, :486-493); covariance: the scalar part is d^2/dx dx' [kb**(x,x') - v(x)^T v(x')],
+        a (b*n, b'*n) matrix with rows (t, d) and columns (t', d'), Kronecker-expanded with A like the value process.
+        Closed-form derivative kernel blocks from bcbf_rbf_blocks replace the reference's autograd closures
+        grad_ksx / grad_kxs / Hessian_kxx.  Deviation, on purpose: the reference's grad_kxs calls
+        autograd.grad(list(k(Xtrain, x*)), x*), which SUMS the kernel gradient over the training points before it is
+        weighted by (uh_i B uh*) and alpha_i; that expression is not the gradient of anything, its one caller is
+        commented out (tests/test_control_affine_regression.py:184,191), and for n > 1 it stops on a shape error.
+        This method returns what that commented-out test compares against: the gradient of `fu_func_mean`."""
+        _need_cuda(self.device)
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        Xtestp = self._ensure_device_dtype(Xtestp_in) if Xtestp_in is not None else Xtest
+        UHtest = self._uh(Xtest, Utest_in, UHfill)
+        UHtestp = UHtest if Utestp_in is None else self._uh(Xtestp, Utestp_in, UHfillp)
+        out_dt = self.dtype
+        ls, s, A, B, C = self._hyper64()
+        Xq, Xp, UHq, UHp = Xtest.double().contiguous(), Xtestp.double().contiguous(), UHtest.double(), UHtestp.double()
+        b, n = Xq.shape
+        bp_ = Xp.shape[0]
+
+        def hess_prior():                       # d^2 k(x_t, x'_t') / dx dx'^T * (uh_t B uh'_t'): rows (t,d), cols (t',d')
+            _, _, d2K = ops.rbf_blocks(Xq, Xp, ls, s, hess=True)                    # (b, b', n, n)
+            w = (UHq @ B @ UHp.transpose(0, 1)).unsqueeze(-1).unsqueeze(-1)
+            return (d2K * w).permute(0, 2, 1, 3).reshape(b * n, bp_ * n)
+
+        mean = Xq.new_zeros(b, n * n)           # the constant prior mean has zero gradient (:452-461)
+        if self.model.train_inputs is None:
+            scalar_var = hess_prior()
+            cov = scalar_var if scalar_var_only else torch_kron(scalar_var.unsqueeze(0), A.unsqueeze(0))
+            return mean.to(out_dt), cov.to(out_dt)
+        Xtrain, UHtrain, _ = self._train_data()
+        X64 = Xtrain.double().contiguous()
+        N = X64.shape[0]
+        Linv, alpha, G = self._factor_state()
+        Npad = Linv.shape[0]
+
+        def dkb(Xs, UHs):                       # d kb*(x_t)[i] / d x_{t,d}  as an (Npad, b*n) matrix, columns (t, d)
+            _, dK, _ = ops.rbf_blocks(Xs, X64, ls, s, grad=True)                    # (b, N, n), derivative w.r.t. x_t
+            w = (G[:N] @ UHs.transpose(0, 1))                                       # (N, b): uh_i^T B uh_t
+            M = (dK.permute(1, 0, 2) * w.unsqueeze(-1)).reshape(N, -1)
+            return torch.nn.functional.pad(M, (0, 0, 0, Npad - N)).contiguous()
+
+        dkb_q = dkb(Xq, UHq)
+        mean = ops.gemm(dkb_q, alpha, transa=True).reshape(b, n, -1).transpose(1, 2).reshape(b, -1)   # [t, r*n + d]
+        if not compute_cov:
+            return mean.to(out_dt), (0 * A).to(out_dt)
+        dkb_p = dkb(Xp, UHp) if (Xtestp_in is not None or Utestp_in is not None) else dkb_q
+        V = ops.trmm_lower(Linv, dkb_q)
+        Vp = ops.trmm_lower(Linv, dkb_p) if dkb_p is not dkb_q else V
+        scalar_var = ops.gemm(V, Vp, transa=True, alpha=-1.0, beta=1.0, C=hess_prior())
+        if scalar_var_only:
+            return mean.to(out_dt), scalar_var.to(out_dt)
+        return mean.to(out_dt), torch_kron(scalar_var.unsqueeze(0), A.unsqueeze(0)).to(out_dt)
 
     # ---- matrix form (class Exact in the reference; kept on the base class so that predict() can use it) ----------
     def _custom_predict_matrix(self, Xtest_in, Xtestp_in=None, compute_cov=True, _out_jitter=True):
@@ -672,6 +729,15 @@ class ControlAffineRegressor(DynamicsModel):
             mean_f = mean_f.squeeze(0)
         return mean_f.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
 
+    def _grad_fu_func_mean(self, Xtest_in, Utest_in=None):
+        """d/dx of the posterior mean of F(x)[1;u] (reference :759-771): (n*n,) for a single state, (b, n*n) batched,
+        entry r*n + d = d mean_r / d x_d."""
+        Utest = self._b(Utest_in) if Utest_in is not None else None
+        mean_f, _ = self.custom_predict(self._b(Xtest_in), Utest, compute_cov=False, grad_gp=True)
+        if Xtest_in.ndim == 1:
+            mean_f = mean_f.squeeze(0)
+        return mean_f.to(dtype=Xtest_in.dtype, device=Xtest_in.device)
+
     def fu_func_knl(self, Utest_in, Xtest_in, Xtestp_in):
         _, var_f = self.custom_predict(self._b(Xtest_in), self._b(Utest_in), Xtestp_in=self._b(Xtestp_in),
                                        compute_cov=True)
@@ -712,6 +778,32 @@ class ControlAffineRegressor(DynamicsModel):
 
     def g_func_mean(self, Xtest_in):
         return self._gu_func(Xtest_in, return_cov=False)
+
+    def _predict_flatten(self, Xtest_in, Utest_in):
+        """f(x, u) = f(x) + g(x) u for train-style rows (mask 1): mean (b, n) and covariance reshaped (b, n, n, b) as the
+        reference does with gpytorch's eval-mode output (:645-683, the raw reshape of the (b n, b n) matrix included).
+        The numbers are the closed-form posterior (custom_predict) — eval-mode gpytorch is parity-unpinned."""
+        if isinstance(Xtest_in, np.ndarray):
+            Xtest_in = torch.from_numpy(Xtest_in)
+        if isinstance(Utest_in, np.ndarray):
+            Utest_in = torch.from_numpy(Utest_in)
+        if self.model is None or self.likelihood is None:
+            raise RuntimeError("Call fit() with training data before calling predict")
+        Xtest = self._ensure_device_dtype(Xtest_in)
+        mean, cov = ControlAffineRegressor.custom_predict(self, Xtest, self._ensure_device_dtype(Utest_in))
+        b, n = Xtest.shape[0], self.x_dim
+        cov = cov.reshape(b * n, b * n).reshape(b, n, n, b)
+        return (mean.to(device=Xtest_in.device, dtype=Xtest_in.dtype), cov.to(device=Xtest_in.device, dtype=Xtest_in.dtype))
+
+    def _cbf_func(self, Xtest, grad_htest, return_cov=False):
+        """grad_h F(x) and, on request, its variance grad_h^T cov(F) grad_h (reference :853-860; there the
+        return_cov=False branch unpacks a single tensor and fails — here it returns (mean, None))."""
+        if return_cov:
+            mean_Fx, cov_Fx = self.predict(Xtest, return_cov=True)
+            cov_hFT = grad_htest.T @ cov_Fx @ grad_htest
+        else:
+            mean_Fx, cov_hFT = self.predict(Xtest, return_cov=False), None
+        return grad_htest @ mean_Fx, cov_hFT
 
     # ------------------------------------------------------------------------------------------ persistence
     def state_dict(self):

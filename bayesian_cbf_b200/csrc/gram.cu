@@ -333,6 +333,18 @@ __global__ void gram_resid_finalize_kernel(const double* __restrict__ partial, i
   }
 }
 
+// out[i,j] = K[i,j] * (uh1_i^T B uh2_j): the control-affine weighting of a data-kernel matrix that some OTHER module
+// evaluated (the plug-in contract of HetergeneousMatrixVariateKernel: any data_covar_module).  One thread per entry.
+__global__ void ca_weight_kernel(const double* __restrict__ K, int ldk, const double* __restrict__ UH1,
+                                 const double* __restrict__ UH2, GramParams P, double* __restrict__ out, int ldo) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)P.a * P.c) return;
+  const int i = (int)(idx / P.c), j = (int)(idx % P.c), p = P.p;
+  double s = 0.0;
+  for (int q = 0; q < p; ++q) s = __fma_rn(g_entry(UH1 + (long long)i * p, P.Bm, p, q), UH2[(long long)j * p + q], s);
+  out[(long long)i * ldo + j] = __dmul_rn(K[(long long)i * ldk + j], s);
+}
+
 // k, dk/dx1 (a,c,n), d2k/dx1dx2 (a,c,n,n); one thread per (i,j) pair — small-b API path only.
 __global__ void rbf_blocks_kernel(GramParams P, double* K, double* dK, double* d2K) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -617,6 +629,21 @@ extern "C" int bcbf_gram_ca(const double* X1, const double* UH1, int a, const do
   P.vec_ok = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (UH1) gram_kernel<true><<<grid, 256, 0, stream>>>(P);
   else gram_kernel<false><<<grid, 256, 0, stream>>>(P);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_ca_weight(const double* K, int ldk, const double* UH1, int a, const double* UH2, int c,
+                              const double* Bmat, int p, double* out, int ldo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(K && UH1 && UH2 && Bmat && out, "bcbf_ca_weight: null pointer");
+  BCBF_REQUIRE(a >= 1 && c >= 1 && p >= 1 && p <= kMaxP && ldk >= c && ldo >= c, "bcbf_ca_weight: a=%d c=%d p=%d ldk=%d ldo=%d",
+               a, c, p, ldk, ldo);
+  GramParams P{};
+  int rc = fetch_small(P.Bm, Bmat, p * p, stream);
+  if (rc != BCBF_OK) return rc;
+  P.a = a; P.c = c; P.p = p;
+  ca_weight_kernel<<<ceil_div((long long)a * c, 256), 256, 0, stream>>>(K, ldk, UH1, UH2, P, out, ldo);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }

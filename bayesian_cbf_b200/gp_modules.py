@@ -114,7 +114,7 @@ class RBFKernel(Kernel):
         if a.requires_grad or c.requires_grad:
             K = autograd_ops.rbf_kernel(a, c, ls.detach(), s.detach())
         else:
-            K = ops.gram_ca(a.contiguous(), c.contiguous(), ls.detach(), float(s))
+            K = ops.gram_ca(a.contiguous(), c.contiguous(), ls.detach(), float(s.detach()))
         K = K.to(x1.dtype)
         return torch.diagonal(K) if diag else K
 

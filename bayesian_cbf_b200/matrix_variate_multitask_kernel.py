@@ -60,7 +60,22 @@ def _train_end(M1s):
     return int(torch.min(idxs).item()) if idxs.numel() else M1s.size(-1)
 
 
+def _dense(t):
+    """Whatever a (plug-in) kernel module hands back -> dense torch tensor (gpytorch lazy results expose .evaluate())."""
+    if hasattr(t, 'evaluate'):
+        t = t.evaluate()
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    return t
+
+
 class HetergeneousMatrixVariateKernel(MatrixVariateKernel):
+    """Covariance of the heterogeneous observation model (reference :99-204).  The class evaluates the modules it is
+    given, like the reference: `data_covar_module.forward(X1, X2)` for the data kernel, `task_covar_module.U / .V
+    .covar_matrix` for A and B.  When the data kernel is the stock `ScaleKernel(RBFKernel)` / `RBFKernel` of
+    `gp_modules`, every block is ONE launch of the fused control-affine Gram kernel (bcbf_gram_ca) instead of a dense
+    K followed by the weighting; any other module takes the plug-in path: its dense K, then bcbf_ca_weight."""
+
     def num_outputs_per_input(self, mxu1, mxu2):
         M1, X1, _ = self.decoder.decode(mxu1)
         M1s = M1[..., 0]
@@ -69,15 +84,25 @@ class HetergeneousMatrixVariateKernel(MatrixVariateKernel):
         test_size = (M1s.size(-1) - end) * prod(self.task_covar_module.matshape)
         return (train_size + test_size) / M1s.size(-1)
 
-    # ---- the three block types (reference kernel1 / kernel2 / correlation_kernel_12, :112-134) -------------------
-    def _hyper(self, ref):
+    # ---- which evaluation path ------------------------------------------------------------------------------------
+    def _stock_rbf(self):
+        """(rbf module, outputscale float) if data_covar_module is the stock RBF-ARD (x scale) kernel, else None."""
+        from .gp_modules import RBFKernel, ScaleKernel
         dk = self.data_covar_module
-        base = getattr(dk, 'base_kernel', dk)
+        if type(dk) is ScaleKernel and type(dk.base_kernel) is RBFKernel:
+            return dk.base_kernel, float(dk.outputscale.detach())
+        if type(dk) is RBFKernel:
+            return dk, 1.0
+        return None
+
+    def _AB(self):
+        return _dense(self.task_covar_module.U.covar_matrix), _dense(self.task_covar_module.V.covar_matrix)
+
+    def _hyper(self, ref):
+        rbf, s = self._stock_rbf()
         n = ref.shape[-1]
-        ls = base.lengthscale.reshape(-1).double().expand(n).contiguous().detach()
-        s = float(dk.outputscale.detach()) if hasattr(dk, 'outputscale') else 1.0
-        A = self.task_covar_module.U.covar_matrix.evaluate()
-        B = self.task_covar_module.V.covar_matrix.evaluate()
+        ls = rbf.lengthscale.reshape(-1).double().expand(n).contiguous().detach()
+        A, B = self._AB()
         return ls, s, A, B
 
     @staticmethod
@@ -87,6 +112,8 @@ class HetergeneousMatrixVariateKernel(MatrixVariateKernel):
         E = torch.eye(p, dtype=X.dtype, device=X.device).repeat(X.shape[0], 1).contiguous()
         return Xr, E
 
+    # ---- the three block types (reference kernel1 / kernel2 / correlation_kernel_12, :112-134) -------------------
+    # Fused forms (stock data kernel): operands are the points themselves.
     def kernel1(self, X1, UH1, X2, UH2):
         ls, s, A, B = self._hyper(X1)
         Kb = ops.gram_ca(X1, X2, ls, s, UH1, UH2, B.double().contiguous())
@@ -104,17 +131,42 @@ class HetergeneousMatrixVariateKernel(MatrixVariateKernel):
         K12 = ops.gram_ca(X1, X2r, ls, s, UH1, E, B.double().contiguous())
         return torch_kron(K12.to(A.dtype), A, batch_dims=0)
 
-    def mask_dependent_covar(self, M1s, U1, M2s, U2, X1, X2):
+    # Plug-in forms (any data kernel): operands are blocks of the dense K it returned.
+    def _kernel1_dense(self, K11, UH1, UH2, A, B):
+        Kb = ops.ca_weight(K11.double().contiguous(), UH1, UH2, B.double().contiguous())        # H1 (K (x) B) H2^T
+        return torch_kron(Kb.to(A.dtype), A, batch_dims=0)
+
+    def _kernel2_dense(self, K22, A, B):
+        return torch_kron(torch_kron(K22.to(A.dtype), B, batch_dims=0), A, batch_dims=0)
+
+    def _correlation_kernel_12_dense(self, K12, UH1, A, B):
+        p = B.shape[0]
+        E = torch.eye(p, dtype=torch.float64, device=K12.device).repeat(K12.shape[1], 1).contiguous()
+        K12r = K12.double().repeat_interleave(p, dim=1).contiguous()                             # columns (point, q)
+        return torch_kron(ops.ca_weight(K12r, UH1, E, B.double().contiguous()).to(A.dtype), A, batch_dims=0)   # H1 (K12 (x) B)
+
+    def mask_dependent_covar(self, M1s, U1, M2s, U2, X1, X2, covar_xx=None):
         e1, e2 = _train_end(M1s), _train_end(M2s)
         assert (M1s[e1:] == 0).all() and (M2s[e2:] == 0).all(), "rows must be sorted train-first"
         d = lambda t: t.double().contiguous()
-        X1a, X1b, X2a, X2b = d(X1[:e1]), d(X1[e1:]), d(X2[:e2]), d(X2[e2:])
         UH1a, UH2a = d(U1[:e1]), d(U2[:e2])
-        k11 = self.kernel1(X1a, UH1a, X2a, UH2a) if (e1 and e2) else None
-        k22 = self.kernel2(X1b, X2b) if (X1b.shape[0] and X2b.shape[0]) else None
-        if k11 is not None and k22 is not None:
-            k12 = self.correlation_kernel_12(X1a, UH1a, X2b)
-            k21 = self.correlation_kernel_12(X2a, UH2a, X1b).transpose(0, 1)
+        n11 = bool(e1 and e2)
+        n22 = bool((X1.shape[0] - e1) and (X2.shape[0] - e2))
+        if covar_xx is None:            # stock data kernel: fused blocks
+            X1a, X1b, X2a, X2b = d(X1[:e1]), d(X1[e1:]), d(X2[:e2]), d(X2[e2:])
+            k11 = self.kernel1(X1a, UH1a, X2a, UH2a) if n11 else None
+            k22 = self.kernel2(X1b, X2b) if n22 else None
+            if n11 and n22:
+                k12 = self.correlation_kernel_12(X1a, UH1a, X2b)
+                k21 = self.correlation_kernel_12(X2a, UH2a, X1b).transpose(0, 1)
+        else:                           # plug-in data kernel: blocks of its dense matrix
+            A, B = self._AB()
+            k11 = self._kernel1_dense(covar_xx[:e1, :e2], UH1a, UH2a, A, B) if n11 else None
+            k22 = self._kernel2_dense(covar_xx[e1:, e2:], A, B) if n22 else None
+            if n11 and n22:
+                k12 = self._correlation_kernel_12_dense(covar_xx[:e1, e2:], UH1a, A, B)
+                k21 = self._correlation_kernel_12_dense(covar_xx[e1:, :e2].transpose(0, 1), UH2a, A, B).transpose(0, 1)
+        if n11 and n22:
             return torch.cat([torch.cat([k11, k12], dim=1), torch.cat([k21, k22], dim=1)], dim=0)
         return k22 if k11 is None else k11
 
@@ -124,5 +176,10 @@ class HetergeneousMatrixVariateKernel(MatrixVariateKernel):
             raise RuntimeError("HetergeneousMatrixVariateKernel does not accept the last dimension to be treated as a batch dimension.")
         M1, X1, U1 = self.decoder.decode(mxu1)
         M2, X2, U2 = self.decoder.decode(mxu2)
-        res = self.mask_dependent_covar(M1[..., 0], U1, M2[..., 0], U2, X1, X2).to(mxu1.dtype)
+        covar_xx = None
+        if self._stock_rbf() is None:
+            covar_xx = _dense(self.data_covar_module.forward(X1, X2, **params)).to(mxu1.device)
+            for name, value in self.data_covar_module.named_parameters():
+                assert not torch.isnan(value).any()
+        res = self.mask_dependent_covar(M1[..., 0], U1, M2[..., 0], U2, X1, X2, covar_xx).to(mxu1.dtype)
         return torch.diagonal(res) if diag else res

@@ -17,27 +17,27 @@ class HetergeneousMatrixVariateMean(MultitaskMean):
         return torch.stack([bm.constant.reshape(()) for bm in self.base_means]).reshape(*self.matshape)
 
     def mean1(self, UH, mu):
-        return (UH.unsqueeze(-2) @ mu).reshape(-1)
+        return (UH @ mu).reshape(-1) if mu.ndim == 2 else (UH.unsqueeze(-2) @ mu).reshape(-1)
 
     def mean2(self, mu):
         return mu.reshape(-1)
 
     def forward(self, MXU):
+        """Flat mean of a train-first sorted MXU: uh_i^T C (n values) per train row, then vec(C) (p*n) per test row."""
         assert not torch.isnan(MXU).any()
         Ms, _, UH = self.decoder.decode(MXU)
         assert Ms.size(-1) == 1
-        Ms = Ms[..., 0]
-        idxs = torch.nonzero(Ms - Ms.new_ones(Ms.size()))
-        idxend = int(torch.min(idxs)) if idxs.numel() else Ms.size(-1)
-        mu = self.constants().to(MXU.dtype).unsqueeze(0).expand(Ms.size(-1), *self.matshape)
-        output = None
-        if idxend != 0:
-            assert (Ms[..., idxend:] == 0).all()
-            output = self.mean1(UH[..., :idxend, :], mu[:idxend, ...])
-        if Ms.size(-1) != idxend:
-            Fmean = self.mean2(mu[idxend:, ...])
-            output = torch.cat([output, Fmean]) if output is not None else Fmean
-        return output
+        from .matrix_variate_multitask_kernel import _train_end
+        mask = Ms[..., 0]
+        ntrain, ntotal = _train_end(mask), mask.size(-1)
+        assert (mask[ntrain:] == 0).all(), "rows must be sorted train-first"
+        C = self.constants().to(MXU.dtype)
+        pieces = []
+        if ntrain:
+            pieces.append(self.mean1(UH[:ntrain], C))
+        if ntotal > ntrain:
+            pieces.append(self.mean2(C.unsqueeze(0).expand(ntotal - ntrain, *self.matshape)))
+        return torch.cat(pieces)
 
     def state_dict(self, *a, **k):
         return dict(matshape=self.matshape, decoder=self.decoder.state_dict(),

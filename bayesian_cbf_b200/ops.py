@@ -128,6 +128,16 @@ def gram_ca(X1, X2, lengthscale, outputscale, UH1=None, UH2=None, B=None, rows_p
     return buf[:, :c]
 
 
+def ca_weight(K, UH1, UH2, B):
+    """K[i,j] * (uh1_i^T B uh2_j) for a data-kernel matrix K (a,c) evaluated by some other module (bcbf_ca_weight)."""
+    _req(K, UH1, UH2, B)
+    a, c = K.shape
+    out = torch.empty(a, c, dtype=torch.float64, device=K.device)
+    check(_lib.load().bcbf_ca_weight(_ptr(K), K.stride(0), _ptr(UH1), a, _ptr(UH2), c, _ptr(B), UH1.shape[1], _ptr(out),
+                                     c, _stream()))
+    return out
+
+
 def _even_pad(t, rows, cols):
     """Zero-padded contiguous copy of a 2-D tensor with the requested (even) extents; no copy when it fits."""
     if t.shape == (rows, cols) and t.is_contiguous() and t.data_ptr() % 16 == 0:

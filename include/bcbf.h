@@ -98,6 +98,13 @@ int bcbf_gram_ca(const double* X1, const double* UH1, int a, const double* X2, c
                  const double* Bmat, const double* lengthscale, double outputscale, int n, int p, double* out,
                  int ld, void* stream);
 
+/* Control-affine weighting of a data-kernel matrix evaluated elsewhere:  out[i,j] = K[i,j] * (uh1_i^T B uh2_j).
+ * K (a,c; ldk), UH1 (a,p), UH2 (c,p), out (a,c; ldo; may alias K).  The plug-in path of HetergeneousMatrixVariateKernel
+ * (matrix_variate_multitask_kernel.py:196-204: any data_covar_module; kernel1 / correlation_kernel_12 :112-134) — the
+ * stock RBF-ARD x scale kernel takes the fused bcbf_gram_ca instead.                                                    */
+int bcbf_ca_weight(const double* K, int ldk, const double* UH1, int a, const double* UH2, int c, const double* Bmat,
+                   int p, double* out, int ldo, void* stream);
+
 /* General k(X1, X2) (a x c) dense, plus optional closed-form derivative blocks
  *   dK[i,j,:]   = d k(x1_i, x2_j) / d x1_i                      (a,c,n)     [may be NULL]
  *   d2K[i,j,:,:] = d^2 k(x1_i, x2_j) / d x1_i d x2_j^T           (a,c,n,n)   [may be NULL]

@@ -70,6 +70,10 @@ def gram_ca(X1, X2, lengthscale, outputscale, UH1=None, UH2=None, B=None, rows_p
     return K
 
 
+def ca_weight(K, UH1, UH2, B):
+    return K * (UH1 @ B @ UH2.T)
+
+
 def rbf_blocks(X1, X2, lengthscale, outputscale, grad=False, hess=False):
     K = _k(X1, X2, lengthscale, outputscale)
     il2 = 1.0 / lengthscale ** 2
@@ -166,7 +170,7 @@ def installed(monkeypatch):
     import bayesian_cbf_b200.gp_modules as gm
     from bayesian_cbf_b200 import ops
     me = globals()
-    for name in ('padded', 'query_pad', 'gram_train', 'gram_train_lower', 'alpha_refine', 'cross_gram', 'gram_ca', 'rbf_blocks', 'potrf_', 'trtri',
+    for name in ('padded', 'query_pad', 'gram_train', 'gram_train_lower', 'alpha_refine', 'ca_weight', 'cross_gram', 'gram_ca', 'rbf_blocks', 'potrf_', 'trtri',
                  'trmm_lower', 'gemm', 'posterior_blocks', 'contract_u', 'socp_factor', 'cbc1_terms',
                  'gram_train_backward', 'socp_solve', 'oz_max_npad', 'oz_split_factor', 'posterior_blocks_i8',
                  'oz_gemm_tn'):

@@ -119,6 +119,32 @@ def test_int8_tensor_core_path_at_full_size(fitted):
     assert np.array_equal(outp['Bk'], out['Bk'][perm.numpy()])
 
 
+def test_alpha_refinement_has_converged_at_full_size(fitted):
+    """bcbf_model_fit runs two compensated refinement steps on alpha; a third must not move the posterior mean."""
+    from bayesian_cbf_b200 import ops
+    import bench
+    model, X, U, Xdot, hyp, jitter = fitted
+    st = model.state_tensors()
+    N, Npad = X.shape[0], st['Linv'].shape[0]
+    UH = torch.cat([torch.ones(N, 1, dtype=torch.float64), U], dim=1).cuda()
+    Y = torch.zeros(Npad, 3, dtype=torch.float64, device='cuda')
+    Y[:N] = (Xdot - UH.cpu() @ hyp['C']).cuda()
+    args = (X.cuda(), UH, hyp['B'].cuda(), hyp['lengthscale'].cuda(), float(hyp['outputscale']), st['Linv'], Y,
+            jitter.cuda(), 1e-5)
+    a2 = ops.alpha_refine(*args, iters=2)
+    a3 = ops.alpha_refine(*args, iters=3)
+    a0 = ops.alpha_refine(*args, iters=0)
+    assert torch.equal(a2[:N], st['alpha'][:N, :3])                 # what the fit stored
+    Xq, Uq = bench.make_queries(1024, 0)
+    UHq = torch.cat([torch.ones(1024, 1, dtype=torch.float64), Uq], dim=1).cuda()
+    kb = ops.gram_ca(X.cuda(), Xq.cuda(), hyp['lengthscale'].cuda(), float(hyp['outputscale']), UH, UHq, hyp['B'].cuda())
+    m0, m2, m3 = [(kb.T @ a[:N]) for a in (a0, a2, a3)]
+    sc = m3.abs().max()
+    d23, d03 = float((m2 - m3).abs().max() / sc), float((m0 - m3).abs().max() / sc)
+    print('mean: explicit inverse only vs converged %.2e, 2 steps vs 3 steps %.2e' % (d03, d23))
+    assert d23 < 1e-10
+
+
 def test_full_size_against_the_oracle(fitted):
     """CUDA (int8 tensor-core and FP64 DMMA covariance kernels) against oracle.posterior_blocks at N = 16384 on 2048 bench
     queries.  Tolerances: B_k / svar 1e-9 of the prior scale; mean / M_k 1e-9 relative or the measured floor of the
