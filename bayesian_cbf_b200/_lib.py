@@ -87,6 +87,8 @@ _SIGNATURES = {
     'bcbf_ens_transpose': (c_int, [_P, _P, c_int, c_int, _P]),
     'bcbf_ens_posterior': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     'bcbf_socp_solve': (c_int, [c_int, c_int, c_int, c_int, c_double, _P, c_int, _P, _P, _P, _P, _P, c_double, _P, _P, _P, _P]),
+    'bcbf_socp_solve_lin': (c_int, [c_int, c_int, c_int, c_int, c_double, _P, c_int, _P, _P, _P, _P, _P, _P, c_double, _P, _P, _P,
+                                    _P]),
     'bcbf_model_create': (c_int, [POINTER(c_void_p), c_int]),
     'bcbf_model_destroy': (None, [c_void_p]),
     'bcbf_model_fit': (c_int, [c_void_p, POINTER(Hyper), _P, _P, _P, c_int, _P, c_double]),

@@ -216,6 +216,8 @@ class ControlAffineRegressor(DynamicsModel):
                                  gamma_length_scale_prior=gamma_length_scale_prior).to(device=self.device)
         self._cache = dict()
         self._jitter_source = None
+        self._fit_noise_source = None
+        self.fit_losses = []
         self._f_func_gp = GaussianProcess(self.f_func_mean, self.f_func_knl, (self.x_dim,), name="f")
 
     # ------------------------------------------------------------------------------------------ bookkeeping
@@ -255,6 +257,11 @@ class ControlAffineRegressor(DynamicsModel):
     def set_jitter_source(self, vectors):
         """Explicit U(0,1) jitter vectors (consumed in order by every make_psd attempt) instead of torch.rand."""
         self._jitter_source = None if vectors is None else iter(vectors)
+
+    def set_fit_noise_source(self, draws):
+        """Explicit U(0,1) draws for the 1e-6 multiplicative target noise of every fit iteration (one array of
+        N*n values per iteration, consumed in order) instead of torch.rand — parity tests replay the reference's draws."""
+        self._fit_noise_source = None if draws is None else iter(draws)
 
     def _ensure_device_dtype(self, X):
         if isinstance(X, np.ndarray):
@@ -350,12 +357,17 @@ class ControlAffineRegressor(DynamicsModel):
         X64 = Xtrain.double().contiguous()
         UH64 = torch.cat([Xtrain.new_ones(N, 1), Utrain], dim=1).double().contiguous()
         prior = model.input_covar.base_kernel.lengthscale_prior
+        self.fit_losses = []
         for i in range(training_iter):
             optimizer.zero_grad()
             for p in model.parameters(recurse=True):
                 assert not torch.isnan(p).any()
             # fresh multiplicative target noise every iteration (reference :318-321), drawn on the CPU generator
-            noise = torch.rand(XdotTrain.shape, dtype=XdotTrain.dtype).to(self.device)
+            if self._fit_noise_source is not None:
+                noise = torch.as_tensor(next(self._fit_noise_source)).reshape(XdotTrain.shape).to(
+                    device=self.device, dtype=XdotTrain.dtype)
+            else:
+                noise = torch.rand(XdotTrain.shape, dtype=XdotTrain.dtype).to(self.device)
             Y = (XdotTrain * (1 + 1e-6 * noise)).double()
             ls = model.input_covar.base_kernel.lengthscale
             logp = mvgp_log_marginal(ls.double().reshape(-1).expand(n), model.input_covar.outputscale.double(),
@@ -370,7 +382,9 @@ class ControlAffineRegressor(DynamicsModel):
             for p in model.parameters(recurse=True):
                 if p.grad is not None:
                     assert not torch.isnan(p.grad).any()
-            LOG.debug('Iter %d/%d - Loss: %.3f' % (i + 1, training_iter, loss.item()))
+            self.fit_losses.append(loss.detach())
+            if LOG.isEnabledFor(logging.DEBUG):
+                LOG.debug('Iter %d/%d - Loss: %.3f' % (i + 1, training_iter, loss.item()))
             optimizer.step()
             scheduler.step()
         return self

@@ -2,7 +2,7 @@
 // (reference ControllerCLFBayesian.control, unicycle_move_to_pose.py:926-964, solved there with cvxpy + GUROBI on the host;
 // SURVEY 8f-1).  One thread per problem:
 //
-//     minimise   sum_i w_i (y_i - r_i)^2                      y in R^nv           (nv <= 4: [relaxation, u])
+//     minimise   sum_i w_i (y_i - r_i)^2 + q^T y              y in R^nv           (nv <= 4: [relaxation, u]; w_i >= 0)
 //     subject to c_k^T y + d_k >= rho || A_k y + b_k ||_2      k = 0 .. K-1        (K <= 4 cones of dimension pc <= 4)
 //
 // Method: log-barrier interior point (barrier -log(t^2 - |z|^2) per cone), damped Newton with backtracking, preceded by
@@ -24,7 +24,7 @@ struct SocpProblem {
   static constexpr int MV = NV ? NV : kSV, MK = KC ? KC : kSK, MP = PC ? PC : kSP, MN = MV + 1;
   int nv_, K_, pc_;
   double rho;
-  double w[MV], r[MV];
+  double w[MV], r[MV], q[MV];
   double c[MK][MV], d[MK];
   double A[MK][MP][MV], b[MK][MP];
   __device__ __forceinline__ int nv() const { return NV ? NV : nv_; }
@@ -84,13 +84,14 @@ __device__ __forceinline__ bool socp_solve(double H[][MN], double* g, int n) {
 }
 
 // Barrier value, gradient and Hessian of  tau * f(x) - sum_k log D_k  in the variables x = (y [, s]).
-//   phase 1: f = s + eps1 * sum w (y-r)^2 ;  phase 2: f = sum w (y-r)^2
+//   phase 1: f = s + eps1 * (sum w (y-r)^2 + q^T y) ;  phase 2: f = sum w (y-r)^2 + q^T y
 template <class PT>
 __device__ __forceinline__ double socp_merit(const PT& P, const double* x, bool phase1, double tau, double eps1) {
   double t[PT::MK], z[PT::MK][PT::MP], D[PT::MK];
   if (!socp_cones(P, x, phase1 ? x[P.nv()] : 0.0, t, z, D)) return __longlong_as_double(0x7ff0000000000000LL);
   double f = 0.0;
   for (int i = 0; i < P.nv(); ++i) f = fma(P.w[i] * (x[i] - P.r[i]), (x[i] - P.r[i]), f);
+  for (int i = 0; i < P.nv(); ++i) f = fma(P.q[i], x[i], f);
   double val = phase1 ? tau * (x[P.nv()] + eps1 * f) : tau * f;
   for (int k = 0; k < P.K(); ++k) val -= log(D[k]);
   return val;
@@ -108,7 +109,7 @@ __device__ __forceinline__ void socp_grad_hess(const PT& P, const double* x, boo
   }
   const double fs = phase1 ? tau * eps1 : tau;
   for (int i = 0; i < nv; ++i) {
-    g[i] = 2.0 * fs * P.w[i] * (x[i] - P.r[i]);
+    g[i] = fs * (2.0 * P.w[i] * (x[i] - P.r[i]) + P.q[i]);
     H[i][i] = 2.0 * fs * P.w[i];
   }
   if (phase1) g[nv] = tau;
@@ -174,7 +175,8 @@ __device__ __forceinline__ int socp_center(const PT& P, double* x, bool phase1, 
 template <int NV, int KC, int PC>
 __global__ void __launch_bounds__(32) socp_solve_kernel(int Q, int nv, int K, int pc, double rho,
                                                         const double* __restrict__ w, int w_stride,
-                                                        const double* __restrict__ r, const double* __restrict__ c,
+                                                        const double* __restrict__ r, const double* __restrict__ qlin,
+                                                        const double* __restrict__ c,
                                                         const double* __restrict__ d, const double* __restrict__ A,
                                                         const double* __restrict__ b, double tol,
                                                         double* __restrict__ y_out, int* __restrict__ status,
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(32) socp_solve_kernel(int Q, int nv, int K, in
   for (int i = 0; i < P.nv(); ++i) {
     P.w[i] = w[(long long)p * w_stride + i];
     P.r[i] = r ? r[(long long)p * nv + i] : 0.0;
+    P.q[i] = qlin ? qlin[(long long)p * nv + i] : 0.0;
   }
   for (int k = 0; k < P.K(); ++k) {
     P.d[k] = d[(long long)p * K + k];
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(32) socp_solve_kernel(int Q, int nv, int K, in
   // ---- phase II ------------------------------------------------------------------------------------------------------
   if (st == 0) {
     double fscale = 1.0;
-    for (int i = 0; i < P.nv(); ++i) fscale = fmax(fscale, P.w[i]);
+    for (int i = 0; i < P.nv(); ++i) fscale = fmax(fscale, fmax(P.w[i], fabs(P.q[i])));
     double tau = 1.0 / fscale;
     for (int outer = 0; outer < 80; ++outer) {
       const bool last = 2.0 * P.K() / tau < tol;
@@ -251,6 +254,12 @@ using namespace bcbf;
 extern "C" int bcbf_socp_solve(int Q, int nv, int K, int pc, double rho, const double* w, int w_per_problem,
                                const double* r, const double* c, const double* d, const double* A, const double* b,
                                double tol, double* y, int* status, int* iters, void* stream_) {
+  return bcbf_socp_solve_lin(Q, nv, K, pc, rho, w, w_per_problem, r, nullptr, c, d, A, b, tol, y, status, iters, stream_);
+}
+
+extern "C" int bcbf_socp_solve_lin(int Q, int nv, int K, int pc, double rho, const double* w, int w_per_problem,
+                                   const double* r, const double* q, const double* c, const double* d, const double* A,
+                                   const double* b, double tol, double* y, int* status, int* iters, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BCBF_REQUIRE(w && c && d && A && b && y && status, "bcbf_socp_solve: null pointer");
   BCBF_REQUIRE(Q >= 1 && nv >= 1 && nv <= kSV && K >= 1 && K <= kSK && pc >= 1 && pc <= kSP && rho >= 0.0 && tol > 0.0,
@@ -259,7 +268,7 @@ extern "C" int bcbf_socp_solve(int Q, int nv, int K, int pc, double rho, const d
   const int ws = w_per_problem ? nv : 0;
   const dim3 grid(ceil_div(Q, 32)), block(32);
 #define BCBF_SOCP_LAUNCH(NV, KC, PC) \
-  socp_solve_kernel<NV, KC, PC><<<grid, block, 0, stream>>>(Q, nv, K, pc, rho, w, ws, r, c, d, A, b, tol, y, status, iters)
+  socp_solve_kernel<NV, KC, PC><<<grid, block, 0, stream>>>(Q, nv, K, pc, rho, w, ws, r, q, c, d, A, b, tol, y, status, iters)
   if (nv == 3 && K == 3 && pc == 3) BCBF_SOCP_LAUNCH(3, 3, 3);        // unicycle: [relax, v, omega], CLC + 2 CBCs
   else if (nv == 3 && K == 2 && pc == 3) BCBF_SOCP_LAUNCH(3, 2, 3);   // unicycle, one obstacle
   else if (nv == 3 && K == 1 && pc == 3) BCBF_SOCP_LAUNCH(3, 1, 3);   // unicycle, CLC only

@@ -377,17 +377,19 @@ def socp_factor(Asq, reg=0.0):
     return A_socp, bfb, status
 
 
-def socp_solve(w, c, d, A, b, rho, r=None, tol=1e-9):
-    """Batched tiny SOCPs (bcbf_socp_solve): minimise sum_i w_i (y_i - r_i)^2 s.t. c_k^T y + d_k >= rho ||A_k y + b_k||.
-    c (Q,K,nv), d (Q,K), A (Q,K,pc,nv), b (Q,K,pc); w (nv,) or (Q,nv); r (Q,nv) or None.
+def socp_solve(w, c, d, A, b, rho, r=None, tol=1e-9, q=None):
+    """Batched tiny SOCPs (bcbf_socp_solve[_lin]): minimise sum_i w_i (y_i - r_i)^2 + q^T y
+    s.t. c_k^T y + d_k >= rho ||A_k y + b_k||.
+    c (Q,K,nv), d (Q,K), A (Q,K,pc,nv), b (Q,K,pc); w (nv,) or (Q,nv); r, q (Q,nv) or None.
     Returns y (Q,nv) [NaN where infeasible], status (Q,) int32 [0 optimal, 1 infeasible], iters (Q,) int32."""
-    _req(w, c, d, A, b, r)
+    _req(w, c, d, A, b, r, q)
     Q, K, nv = c.shape
     pc = A.shape[2]
     dev = c.device
     y = torch.empty(Q, nv, dtype=torch.float64, device=dev)
     status = torch.empty(Q, dtype=torch.int32, device=dev)
     iters = torch.empty(Q, dtype=torch.int32, device=dev)
-    check(_lib.load().bcbf_socp_solve(Q, nv, K, pc, float(rho), _ptr(w), int(w.ndim == 2), _ptr(r), _ptr(c), _ptr(d), _ptr(A),
-                                      _ptr(b), float(tol), _ptr(y), _ptr(status), _ptr(iters), _stream()))
+    check(_lib.load().bcbf_socp_solve_lin(Q, nv, K, pc, float(rho), _ptr(w), int(w.ndim == 2), _ptr(r), _ptr(q), _ptr(c),
+                                          _ptr(d), _ptr(A), _ptr(b), float(tol), _ptr(y), _ptr(status), _ptr(iters),
+                                          _stream()))
     return y, status, iters

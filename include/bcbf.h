@@ -320,6 +320,13 @@ int bcbf_ens_posterior(const double* LinvT, const double* X, const double* G, co
 int bcbf_socp_solve(int Q, int nv, int K, int pc, double rho, const double* w, int w_per_problem, const double* r,
                     const double* c, const double* d, const double* A, const double* b, double tol, double* y,
                     int* status, int* iters /* may be NULL */, void* stream);
+/* The same with a linear term:  minimise sum_i w_i (y_i - r_i)^2 + q^T y  (q (Q,nv) or NULL; w may be all zero: a pure
+ * linear objective, the call shape of optimizers.py:6-116 — optimizer_socp_cvxopt / optimizer_socp_cvxpy(u0,
+ * linear_objective, [(name, (A, bfb, bfc, d)), ...]); cones of fewer than pc rows are padded with zero rows).  Pinned by
+ * the reference's own known answer, tests/test_optimizers.py:6-119 (the cvxopt documentation SOCP).                  */
+int bcbf_socp_solve_lin(int Q, int nv, int K, int pc, double rho, const double* w, int w_per_problem, const double* r,
+                        const double* q, const double* c, const double* d, const double* A, const double* b, double tol,
+                        double* y, int* status, int* iters /* may be NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Model handle: owns device memory for one fitted MVGP; HOST-pointer interface (pinned or pageable).

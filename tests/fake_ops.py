@@ -183,7 +183,7 @@ def installed(monkeypatch):
     yield
 
 
-def socp_solve(w, c, d, A, b, rho, r=None, tol=1e-9):
+def socp_solve(w, c, d, A, b, rho, r=None, tol=1e-9, q=None):
     from oracle import socp_oracle as S
     Q, K, nv = c.shape
     y = torch.empty(Q, nv, dtype=torch.float64)
@@ -192,7 +192,8 @@ def socp_solve(w, c, d, A, b, rho, r=None, tol=1e-9):
     for p in range(Q):
         wp = (w[p] if w.ndim == 2 else w).numpy()
         rp = r[p].numpy() if r is not None else [0.0] * nv
-        yo, st, it = S.solve(wp, rp, c[p].numpy(), d[p].numpy(), A[p].numpy(), b[p].numpy(), float(rho), tol)
+        yo, st, it = S.solve(wp, rp, c[p].numpy(), d[p].numpy(), A[p].numpy(), b[p].numpy(), float(rho), tol,
+                             q=None if q is None else q[p].numpy())
         y[p] = torch.from_numpy(yo)
         status[p], iters[p] = st, it
     return y, status, iters
