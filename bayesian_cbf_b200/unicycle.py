@@ -186,6 +186,7 @@ class BayesCBFController:
         d = torch.zeros(R, K, **f64)
         A = torch.zeros(R, K, 3, 3, **f64)
         b = torch.zeros(R, K, 3, **f64)
+        notpd = torch.zeros(R, dtype=torch.int32, device=dev)
         # CLC, negated (reference :880-899):  -(grad V^T F [1;u] + grad_g V^T xdot_plan + gamma V)
         gV = self.clf.grad_clf(X, goal)
         hval = -((self.clf.grad_clf_wrt_goal(X, goal) * dplan).sum(1) + self.clf_gamma * self.clf.clf(X, goal))
@@ -202,14 +203,19 @@ class BayesCBFController:
             d[:, k] = e
             A[:, k, :, 1:] = A_socp
             b[:, k] = bfb
+            notpd = torch.maximum(notpd, (status != 0).to(torch.int32))
         c[:, 0, 0] = 1.0   # the relaxation enters the CLC only
+        # a posterior covariance that is not positive definite (the reference's torch.linalg.cholesky raises there,
+        # :861) is reported apart from a genuinely infeasible program: `control` returns status 2 for it
+        self.last_notpd = notpd
         return c, d, A, b
 
     def control(self, X, t, goal=None, dplan=None):
-        """u (R,2), relax (R,), status (R,) [0 optimal, 1 infeasible]."""
+        """u (R,2), relax (R,), status (R,) [0 optimal, 1 infeasible, 2 posterior covariance not positive definite]."""
         c, d, A, b = self.constraint_terms(X, t, goal, dplan)
         w = self._constants(X.device)['w']
         y, status, _ = ops.socp_solve(w, c.contiguous(), d.contiguous(), A.contiguous(), b.contiguous(), self.rho)
+        status = torch.where(self.last_notpd != 0, torch.full_like(status, 2), status)
         return y[:, 1:], y[:, 0], status
 
 
@@ -240,15 +246,20 @@ def rollout(controller, X0, steps, dt, true_L=12.0, on_step=None):
 class EnsembleLearner:
     """LearnedShiftInvariantDynamics (reference :295-428) for R rollouts: every rollout records its own (x, u) pairs,
     and every `train_every_n_steps` steps all R per-rollout MVGPs are re-fitted in one batch on the residual
-    xdot - F_prior(x)[1;u] over shift-invariant states [0, 0, theta] (at most `max_train` most recent... the reference
-    subsamples at random, :374-384; here a seeded random subset).  With `adam_iters > 0` every refit first runs that
-    many Adam steps on each rollout's own log marginal likelihood (the reference: 100, :386), all rollouts in the
-    same launches (ensemble.fit_ensemble_hyperparameters, rank-one task covariances as in
-    ControlAffineRegressorExactRankOne :301); with 0 the given hyper-parameters are held fixed."""
+    xdot - F_prior(x)[1;u] over shift-invariant states [0, 0, theta] (:326-330, :340-386), subsampled at random to at most
+    `max_train` points (the reference shuffles with numpy's global generator, :374-384; here a seeded torch generator, or
+    explicit index arrays via `set_subsample_source` for parity tests).  With `adam_iters > 0` every refit first runs that
+    many Adam steps on each rollout's own log marginal likelihood (the reference: 100, :386), all rollouts in the same
+    launches (ensemble.fit_ensemble_hyperparameters, rank-one task covariances as in ControlAffineRegressorExactRankOne
+    :301); with 0 the given hyper-parameters are held fixed.
+
+    `query_raw_state` (default True, the reference's behaviour): the learned GP is trained on shift-invariant inputs but
+    QUERIED at the raw state — `fu_func_gp` (:388-397) hands x itself to `learned_dynamics.fu_func_gp`; only
+    f_func / g_func / custom_predict_fullmat wrap their argument.  False queries at [0, 0, theta], which is what the
+    training inputs look like (the choice the round-1 throughput runs made)."""
 
     def __init__(self, R, dt, model_L=12.0, max_train=200, train_every_n_steps=400, lengthscale=(1.0, 1.0, 1.0),
-                 outputscale=1.0, A=None, B=None, seed=0, device='cuda', adam_iters=0, lr=0.1):
-        from .ensemble import MVGPEnsemble
+                 outputscale=1.0, A=None, B=None, seed=0, device='cuda', adam_iters=0, lr=0.1, query_raw_state=True):
         self.R, self.dt, self.model_L = R, float(dt), float(model_L)
         self.max_train, self.every = int(max_train), int(train_every_n_steps)
         self.device = torch.device(device)
@@ -258,50 +269,81 @@ class EnsembleLearner:
         self.A = (torch.eye(3, **f64) if A is None else torch.as_tensor(A, **f64)).expand(R, 3, 3).contiguous()
         self.B = (torch.eye(3, **f64) if B is None else torch.as_tensor(B, **f64)).expand(R, 3, 3).contiguous()
         self.C = torch.zeros(R, 3, 3, **f64)
-        self.ens = MVGPEnsemble(3, 2, device=self.device)
+        self.ens = None                     # MVGPEnsemble, created at the first fit (CUDA only)
         self.fitted = False
         self.Xs, self.Us = [], []
         self.gen = torch.Generator().manual_seed(seed)
         self.refits = 0
         self.adam_iters, self.lr = int(adam_iters), float(lr)
         self.hp = None
+        self.query_raw_state = bool(query_raw_state)
+        self._subsample_source = None
+        self._jitter_source = None
+
+    def set_subsample_source(self, index_arrays):
+        """Explicit subsample index arrays (one per refit that needs subsampling, consumed in order; the first `max_train`
+        entries of each are used, like the reference's shuffled_indices[:max_train])."""
+        self._subsample_source = None if index_arrays is None else iter(index_arrays)
+
+    def set_jitter_source(self, draws):
+        """Explicit U(0,1) factor-jitter draws, one (R, N) array per Cholesky attempt, instead of the seeded generator."""
+        self._jitter_source = None if draws is None else iter(draws)
 
     @staticmethod
     def shift_invariant(X):
         Z = torch.zeros_like(X)
-        Z[:, 2] = X[:, 2]
+        Z[..., 2] = X[..., 2]
         return Z
 
     def record(self, t, X, U, xdot, ok):
-        """on_step hook of `rollout`: train every n steps on what has been recorded so far, then record (x, u)."""
-        if len(self.Xs) > 1 and len(self.Xs) % self.every == 0:
+        """on_step hook of `rollout` = LearnedShiftInvariantDynamics.train (:340-354): every n recorded steps train on
+        what has been recorded so far, then record (x, u)."""
+        if len(self.Xs) > 0 and len(self.Xs) % self.every == 0:
             self.fit()
         self.Xs.append(X.clone())
         self.Us.append(U.clone())
 
-    def fit(self):
-        Xall = torch.stack(self.Xs, dim=1)                    # (R, T, 3)
+    def training_set(self):
+        """(Xtr (R,T,3) shift-invariant, Utr (R,T,2), err (R,T,3)) from everything recorded so far (:343-348, :367-386):
+        finite-difference Xdot minus the prior model's F(x)[1;u], subsampled to max_train points."""
+        Xall = torch.stack(self.Xs, dim=1)                    # (R, T+1, 3)
         Uall = torch.stack(self.Us, dim=1)
         Xdot = (Xall[:, 1:] - Xall[:, :-1]) / self.dt         # finite differences (:348)
-        Xtr, Utr = self.shift_invariant(Xall[:, :-1].reshape(-1, 3)).reshape(self.R, -1, 3), Uall[:, :-1]
+        Xtr, Utr = self.shift_invariant(Xall[:, :-1]), Uall[:, :-1]
         T = Xtr.shape[1]
-        UH = torch.cat([torch.ones(self.R, T, 1, dtype=torch.float64, device=self.device), Utr], dim=2)
+        UH = torch.cat([torch.ones(self.R, T, 1, dtype=torch.float64, device=Xtr.device), Utr], dim=2)
         Fp = ackermann_F(Xtr.reshape(-1, 3), self.model_L).reshape(self.R, T, 3, 3)
         err = Xdot - torch.einsum('rtnp,rtp->rtn', Fp, UH)
         if T > self.max_train:
-            idx = torch.randperm(T, generator=self.gen)[:self.max_train].to(self.device)
+            if self._subsample_source is not None:
+                idx = torch.as_tensor(next(self._subsample_source)).long()[:self.max_train]
+            else:
+                idx = torch.randperm(T, generator=self.gen)[:self.max_train]
+            idx = idx.to(Xtr.device)
             Xtr, Utr, err = Xtr[:, idx], Utr[:, idx], err[:, idx]
+        return Xtr.contiguous(), Utr.contiguous(), err.contiguous()
+
+    def fit(self):
+        from .ensemble import MVGPEnsemble
+        if len(self.Xs) < 2:          # nothing to difference yet ("Nothing to fit", reference :357-359)
+            return
+        if self.ens is None:
+            self.ens = MVGPEnsemble(3, 2, device=self.device)
+        Xtr, Utr, err = self.training_set()
         if self.adam_iters > 0:
             from .ensemble import EnsembleHyperParameters, fit_ensemble_hyperparameters
             if self.hp is None:      # parameters persist across refits, like the reference's learned_dynamics object
                 self.hp = EnsembleHyperParameters(self.R, 3, 3, rank=1, device=self.device)
-            fit_ensemble_hyperparameters(self.hp, Xtr.contiguous(), Utr.contiguous(), err.contiguous(),
-                                         training_iter=self.adam_iters, lr=self.lr, generator=self.gen)
+            fit_ensemble_hyperparameters(self.hp, Xtr, Utr, err, training_iter=self.adam_iters, lr=self.lr,
+                                         generator=self.gen)
             with torch.no_grad():
                 ls, s, A, B, C = [t.detach().contiguous() for t in self.hp.constrained()]
             self.ls, self.s, self.A, self.B, self.C = ls, s, A, B, C
-        self.ens.fit(Xtr.contiguous(), Utr.contiguous(), err.contiguous(), self.ls, self.s, self.A, self.B, self.C,
-                     jitter=lambda t: torch.rand(self.R, Xtr.shape[1], dtype=torch.float64, generator=self.gen))
+        if self._jitter_source is not None:
+            draw = lambda t: torch.as_tensor(next(self._jitter_source), dtype=torch.float64).reshape(self.R, Xtr.shape[1])
+        else:
+            draw = lambda t: torch.rand(self.R, Xtr.shape[1], dtype=torch.float64, generator=self.gen)
+        self.ens.fit(Xtr, Utr, err, self.ls, self.s, self.A, self.B, self.C, jitter=draw)
         self.fitted = True
         self.refits += 1
 
@@ -310,7 +352,8 @@ class EnsembleLearner:
             f64 = dict(dtype=torch.float64, device=self.device)
             Bk = self.B * self.s.reshape(-1, 1, 1)            # prior: k(x,x) B
             return torch.zeros(self.R, 3, 3, **f64), Bk.contiguous(), self.A
-        Mk, Bk = self.ens.posterior(self.shift_invariant(X).contiguous())
+        Xq = X if self.query_raw_state else self.shift_invariant(X)
+        Mk, Bk = self.ens.posterior(Xq.contiguous())
         return Mk, Bk, self.A
 
 

@@ -103,3 +103,28 @@ def test_graphed_rollout_equals_eager_rollout():
     assert torch.equal(eager['feasible'], graphed['feasible'])
     assert torch.equal(eager['X'], graphed['X'])
     assert torch.equal(eager['U'], graphed['U'])
+
+
+@pytest.mark.gpu
+def test_full_2000_step_recipe_against_the_recorded_run():
+    """BASELINE configs[2], all 2000 steps of `unicycle_bayes_cbf_safe_obstacle`: the CUDA rollout (captured control
+    step: bcbf_cbc1_terms + bcbf_socp_solve) against the per-step record of the CPU restatements
+    (oracle/gen_rollout_record.py -> tests/golden/rollout_safe_obstacle_2000.npz): the same feasibility decision at
+    every step, states / controls / cone terms to 1e-7."""
+    from oracle import gen_rollout_record as G
+    d = load('rollout_safe_obstacle_2000')
+    steps = int(d['steps'])
+    rec = G.run('cuda', steps=steps)
+    feas = np.unpackbits(d['feasible'])[:steps].astype(bool)
+    assert np.array_equal(rec['feasible'], feas) and int(d['n_feasible']) == int(feas.sum())
+    keep = np.arange(0, steps + 1, int(d['sample_every']))
+    assert np.abs(rec['X'][keep] - d['X']).max() < 1e-7
+    assert np.abs(rec['U'][keep[:-1]] - d['U']).max() < 1e-6
+    assert np.abs(rec['X'][-1] - d['X_final']).max() < 1e-7
+    assert np.array_equal(rec['term_steps'], d['term_steps'])
+    assert np.abs(rec['terms'] - d['terms']).max() < 1e-7 * max(1.0, np.abs(d['terms']).max())
+    # and the CUDA-graph replay of the same 2000 steps is bit-identical to the eager CUDA rollout
+    U, ctrl, X0, dt, _ = G.build('cuda')
+    graphed = U.GraphedRollout(ctrl, X0, dt, true_L=12.0).capture().run(steps)
+    assert np.array_equal(graphed['X'][:, 0].cpu().numpy(), rec['X'])
+    assert np.array_equal(graphed['feasible'][:, 0].cpu().numpy(), rec['feasible'])
