@@ -432,10 +432,220 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------- rollouts (configs[4])
+def cpu_rollout_sample(R, N, steps, seed=0):
+    """Host restatement of ONE control step of a learning rollout, per rollout: posterior blocks of its own N-point MVGP
+    (oracle.posterior_blocks), closed-form CBC / CLC cone terms and the barrier SOCP (tests/fake_ops.py,
+    oracle/socp_oracle.py).  Returns rollout-steps per second over R rollouts x `steps` steps (refits excluded)."""
+    import math
+    from oracle import mvgp_oracle as O
+    from tests import fake_ops
+    from bayesian_cbf_b200 import unicycle as Un
+
+    class _P:
+        def setattr(self, o, n, v):
+            setattr(o, n, v)
+    fake_ops.installed(_P()).__enter__()
+    g = torch.Generator().manual_seed(seed)
+    f = dict(dtype=torch.float64, generator=g)
+    models = []
+    eye = torch.eye(3, dtype=torch.float64)
+    for r in range(R):
+        X = torch.zeros(N, 3, dtype=torch.float64)
+        X[:, 2] = 2 * torch.rand(N, **f) - 1
+        U = 2 * torch.rand(N, 2, **f) - 1
+        Xdot = 0.1 * torch.randn(N, 3, **f)
+        hyp = O.Hyper(torch.tensor([1.0, 1.0, 0.7], dtype=torch.float64), torch.tensor(1.0, dtype=torch.float64), eye, eye,
+                      torch.zeros(3, 3, dtype=torch.float64))
+        L = O.perturbed_cholesky(hyp, X, O.homogeneous(U), [torch.rand(N, **f)], direct=True)
+        models.append((hyp, X, U, Xdot, L))
+    x0, xg = [-3.0, -1.0, -math.pi / 4], [0.0, 0.0, math.pi / 4]
+    planner = Un.PiecewiseLinearPlanner(x0, xg, 2000, 0.001, frac_time_to_reach_goal=0.95)
+    cbfs = Un.obstacles_at_mid_from_start_and_goal(x0, xg, term_weights=(0.7, 0.3))
+
+    def posterior(Xs):
+        Mk, Bk = [], []
+        for r, (hyp, X, U, Xdot, L) in enumerate(models):
+            m, b = O.posterior_blocks(hyp, X, U, Xdot, L, Xs[r:r + 1], direct=True)
+            Mk.append(m[0]); Bk.append(b[0])
+        return torch.stack(Mk), torch.stack(Bk), eye
+    ctrl = Un.BayesCBFController(planner, Un.CLFCartesian(Kp=(0.9, 1.5, 0.0)), cbfs, [5.0, 5.0], model_L=12.0,
+                                 clf_gamma=10.0, max_risk=0.01, posterior=posterior)
+    X0 = torch.tensor(x0, dtype=torch.float64).repeat(R, 1) + 0.05 * (torch.rand(R, 3, **f) - 0.5)
+    Un.rollout(ctrl, X0, 2, 0.001, true_L=1.0)
+    t0 = time.perf_counter()
+    Un.rollout(ctrl, X0, steps, 0.001, true_L=1.0)
+    return R * steps / (time.perf_counter() - t0)
+
+
+def run_rollouts(args):
+    """BASELINE configs[4] shape on this rank's GPU: R independent `learning_helps_avoid_getting_stuck` rollouts (reference
+    unicycle_move_to_pose.py:1948-1969), each with its own MVGP refitted every `--train-every` steps on at most 200 of its
+    own samples with `--adam-iters` Adam steps; per control step and rollout: ensemble posterior -> CBC / CLC cone terms
+    -> batched SOCP, the control step replayed from a CUDA graph.  One "step" = one control step of all R rollouts."""
+    import math
+    import torch.distributed as dist
+    from bayesian_cbf_b200 import _lib, unicycle as Un
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        Rc, Sc = 4, max(10, min(args.steps, 40))
+        v = cpu_rollout_sample(Rc, 200, Sc)
+        sample = '%d rollouts x %d control steps, N=200 per-rollout models, host restatement (refits excluded)' % (Rc, Sc)
+        print(json.dumps(dict(impl='reference', metric='controlled rollout steps/sec (posterior + CBC terms + SOCP per step)',
+                              value=v, unit='rollout-steps/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=1e3 * Rc / v, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
+                              data='synthetic', config=dict(workload='ensemble of unicycle learning rollouts (BASELINE configs[4])'),
+                              cpu_baseline=dict(value=v, unit='rollout-steps/s', cores=cores, kind='port', sample=sample),
+                              e2e=dict(value=v, unit='rollout-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+    lib = _lib.load()
+    R, K, W, dt = args.rollouts, args.steps, args.warmup, 0.001
+    x0, xg = [-3.0, -1.0, -math.pi / 4], [0.0, 0.0, math.pi / 4]
+    planner = Un.PiecewiseLinearPlanner(x0, xg, 2000, dt, frac_time_to_reach_goal=0.95)
+    cbfs = Un.obstacles_at_mid_from_start_and_goal(x0, xg, term_weights=(0.7, 0.3))
+    learner = Un.EnsembleLearner(R, dt, model_L=12.0, max_train=200, train_every_n_steps=args.train_every,
+                                 lengthscale=(1.0, 1.0, 0.7), outputscale=1.0, adam_iters=args.adam_iters, seed=rank,
+                                 device=dev, query_raw_state=not args.query_shift_invariant)
+    ctrl = Un.BayesCBFController(planner, Un.CLFCartesian(Kp=(0.9, 1.5, 0.0)), cbfs, [5.0, 5.0], model_L=12.0,
+                                 clf_gamma=10.0, max_risk=0.01, posterior=learner.posterior)
+    g = torch.Generator().manual_seed(rank)
+    hX0 = (torch.tensor(x0, dtype=torch.float64).repeat(R, 1)
+           + 0.05 * (torch.rand(R, 3, generator=g, dtype=torch.float64) - 0.5)).pin_memory()
+    X0 = hX0.to(dev)
+    Un.rollout(ctrl, X0, max(W, 3), dt, true_L=1.0)          # warm-up steps (eager), nothing recorded
+    learner.Xs, learner.Us = [], []
+    gr = Un.GraphedRollout(ctrl, X0, dt, true_L=1.0).capture()
+    state = dict(refits=0)
+
+    def on_step(t, X, u, xdot, ok):
+        learner.record(t, X, u, xdot, ok)
+        if learner.refits != state['refits']:      # the posterior switched kernels / buffers: re-capture the step
+            state['refits'] = learner.refits
+            gr.capture()
+            gr._set_plan(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.bcbf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    X0.copy_(hX0, non_blocking=True)                           # e2e: start states come from pinned host memory ...
+    gr.X.copy_(X0)
+    out = gr.run(K, on_step=on_step, record=False)
+    hXf = gr.X.to('cpu', non_blocking=True)                    # ... and the final states / alive flags go back
+    halive = out['alive'].to('cpu', non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.bcbf_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+    al = torch.tensor([int(halive.sum())], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(al, op=dist.ReduceOp.SUM)
+    ms_max, wall_ms = float(t[0]), float(t[1])
+    # roofline of the HBM-bound kernel of the step: one rollout's own L^-1 streamed per rollout and step
+    roof = None
+    if learner.fitted:
+        Xq = gr.X.clone()
+        for _ in range(3):
+            learner.ens.posterior(Xq)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        tk = 0.0
+        for _ in range(5):
+            flush.zero_()                                      # > L2: every launch streams its factors from HBM
+            k0.record()
+            learner.ens.posterior(Xq)
+            k1.record()
+            torch.cuda.synchronize()
+            tk += k0.elapsed_time(k1) / 5
+        hbm = 6541.1
+        mp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        src = 'fallback'
+        if os.path.exists(mp):
+            try:
+                hbm, src = float(json.load(open(mp))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs, of measured'
+            except Exception:
+                pass
+        ach = learner.ens.posterior_bytes() / (tk * 1e-3) * 1e-9
+        roof = dict(bound='hbm', achieved=ach, peak=hbm, unit='GB/s', frac=ach / hbm, traffic=None,
+                    kernel='ens_posterior_kernel', kernel_ms=tk, peak_source=src,
+                    algorithmic_bytes_per_launch=learner.ens.posterior_bytes(),
+                    note='timed alone after an L2 flush; inside the captured step it is %.0f%% of the step by this time'
+                         % (100 * tk / (ms_max / K)))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        v = cpu_rollout_sample(4, 200, 25)
+        cpu = dict(value=v, unit='rollout-steps/s', cores=cores, kind='port',
+                   sample='4 rollouts x 25 control steps, N=200 per-rollout models, host restatement of posterior + cone '
+                          'terms + SOCP (refits excluded)')
+    Rt = R * world
+    line = dict(metric='controlled rollout steps/sec (posterior + CBC terms + SOCP per step)',
+                value=Rt * K / (ms_max * 1e-3), unit='rollout-steps/s', n_gpus=world, steps=K, warmup=max(W, 3),
+                ms_per_step=ms_max / K, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+                config=dict(workload='ensemble of %d unicycle learning rollouts per GPU (BASELINE configs[4]: '
+                                     'learning_helps_avoid_getting_stuck), refit every %d steps on <= 200 samples with %d '
+                                     'Adam steps' % (R, args.train_every, args.adam_iters),
+                            rollouts_per_gpu=R, parallelism='rollouts sharded, no collective' if world > 1 else 'single GPU',
+                            query_state='raw (reference)' if not args.query_shift_invariant else 'shift-invariant',
+                            l2='per-rollout factors: %d x %.0f KB per step, larger than L2' %
+                               (R, (learner.ens.posterior_bytes() / R / 1024) if learner.fitted else 0)),
+                refits=learner.refits, alive_at_end=int(al.item()), n_train_last=getattr(learner.ens, 'N', 0),
+                clocks=dict(sm_mhz=clocks.get('sm_mhz'), sm_max_mhz=clocks.get('sm_max_mhz'), reasons=clocks.get('reasons', []),
+                            samples=clocks.get('samples', 0)),
+                e2e=dict(value=Rt * K / (wall_ms * 1e-3), unit='rollout-steps/s', h2d_bytes_per_step=R * 3 * 8 / K,
+                         d2h_bytes_per_step=R * (3 * 8 + 1) / K, note='whole run by the host clock: start states from pinned '
+                         'host memory, final states and alive flags back; refits and graph re-captures included'),
+                gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=53)
+    ap.add_argument('--workload', default='posterior', choices=['posterior', 'rollouts'],
+                    help='posterior: BASELINE configs[3] (the metric headline); rollouts: configs[4] ensemble of learning rollouts')
+    ap.add_argument('--steps', type=int, default=None, help='default 53 (posterior) / 2000 (rollouts)')
+    ap.add_argument('--rollouts', type=int, default=512, help='rollouts per GPU (workload rollouts)')
+    ap.add_argument('--train-every', type=int, default=400)
+    ap.add_argument('--adam-iters', type=int, default=100)
+    ap.add_argument('--query-shift-invariant', action='store_true',
+                    help='query the learned GP at [0,0,theta] instead of the raw state (the reference queries raw)')
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n-train', type=int, default=16384)
@@ -451,6 +661,10 @@ def main():
     ap.add_argument('--no-parity-floor', action='store_true',
                     help='skip the exact-solution / floor measurement of the mean parity (about a minute of host time)')
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 53 if args.workload == 'posterior' else 2000
+    if args.workload == 'rollouts':
+        return run_rollouts(args)
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.queries_per_step is None:
         args.queries_per_step = 18648 if args.var_path == 'int8' else 18944
