@@ -36,6 +36,68 @@ def broadcast_state(tensors, src=0, group=None, order=STATE_ORDER):
     return nbytes
 
 
+def packed_lower_elems(Npad, block=128):
+    nb = Npad // block
+    return block * block * nb * (nb + 1) // 2
+
+
+def pack_lower(M, out=None, block=128):
+    """Lower-triangular 128-blocks of a factor-sized matrix (Npad, Npad), block row after block row, into one contiguous
+    vector: (nb (nb + 1) / 2) * 128 * 128 elements — what a receiving rank needs of L^-1 (the strictly-upper blocks are
+    zero).  One strided copy per block row."""
+    Npad = M.shape[0]
+    nb = Npad // block
+    out = torch.empty(packed_lower_elems(Npad, block), dtype=M.dtype, device=M.device) if out is None else out
+    off = 0
+    for i in range(nb):
+        w = (i + 1) * block
+        out[off:off + block * w].view(block, w).copy_(M[i * block:(i + 1) * block, :w])
+        off += block * w
+    return out
+
+
+def unpack_lower(buf, M, block=128):
+    """Inverse of pack_lower into a (Npad, Npad) buffer; the strictly-upper blocks are zeroed."""
+    Npad = M.shape[0]
+    nb = Npad // block
+    off = 0
+    for i in range(nb):
+        w = (i + 1) * block
+        M[i * block:(i + 1) * block, :w].copy_(buf[off:off + block * w].view(block, w))
+        if w < Npad:
+            M[i * block:(i + 1) * block, w:].zero_()
+        off += block * w
+    return M
+
+
+def broadcast_state_packed(tensors, src=0, group=None, order=STATE_ORDER):
+    """ONE collective for the whole fitted state: the packed lower triangle of L^-1 followed by alpha, G, W, X in a
+    single contiguous buffer (1.08 GB instead of 2.16 GB in five calls at N = 16384).  In place on the receivers.
+    Returns the number of bytes broadcast."""
+    rank, world = world_info(group)
+    if world == 1:
+        return 0
+    Linv = tensors['Linv']
+    rest = [tensors[k] for k in order if k != 'Linv']
+    nl = packed_lower_elems(Linv.shape[0])
+    total = nl + sum(t.numel() for t in rest)
+    buf = torch.empty(total, dtype=Linv.dtype, device=Linv.device)
+    if rank == src:
+        pack_lower(Linv, buf[:nl])
+        off = nl
+        for t in rest:
+            buf[off:off + t.numel()].copy_(t.reshape(-1))
+            off += t.numel()
+    dist.broadcast(buf, src=src, group=group)
+    if rank != src:
+        unpack_lower(buf[:nl], Linv)
+        off = nl
+        for t in rest:
+            t.copy_(buf[off:off + t.numel()].view(t.shape))
+            off += t.numel()
+    return total * buf.element_size()
+
+
 def gather_shards(local, total, group=None):
     """All-gather of per-rank result shards (leading dimension partitioned by shard_bounds) into the full result on
     every rank.  Optional: the bench keeps results sharded."""
@@ -69,7 +131,9 @@ class ShardedPosterior:
             self.model.fit(hyper, X, U, Xdot, jitter, jitter_scale)
         else:
             self.model.alloc_state(hyper, X.shape[0])
-        self.broadcast_bytes = broadcast_state(self.model.state_tensors(), self.src, self.group)
+        st = self.model.state_tensors()
+        packed = st['Linv'].ndim == 2 and st['Linv'].shape[0] == st['Linv'].shape[1] and st['Linv'].shape[0] % 128 == 0
+        self.broadcast_bytes = (broadcast_state_packed if packed else broadcast_state)(st, self.src, self.group)
         if self.rank != self.src and hasattr(self.model, 'adopt_state'):
             self.model.adopt_state()
         return self

@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bayesian_cbf_b200.sharding import ShardedPosterior, broadcast_state, gather_shards, shard_bounds
+from bayesian_cbf_b200.sharding import (ShardedPosterior, broadcast_state, broadcast_state_packed, gather_shards, pack_lower,
+                                        packed_lower_elems, shard_bounds, unpack_lower)
 from oracle import mvgp_oracle as O
 
 
@@ -21,6 +22,15 @@ def test_shard_bounds_cover_and_balance():
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_unpack_lower_round_trip():
+    g = torch.Generator().manual_seed(0)
+    M = torch.tril(torch.randn(384, 384, generator=g, dtype=torch.float64))
+    buf = pack_lower(M)
+    assert buf.numel() == packed_lower_elems(384) == 128 * 128 * 6
+    out = torch.full((384, 384), 7.0, dtype=torch.float64)            # stale contents must not survive
+    assert torch.equal(unpack_lower(buf, out), M)
 
 
 class _OracleModel:
@@ -103,6 +113,16 @@ def _worker(rank, world, port, q):
         t = dict(a=torch.full((3,), float(rank)), b=torch.full((2, 2), float(rank)))
         nb = broadcast_state(t, src=1, order=('a', 'b'))
         assert nb == (3 + 4) * 4 and float(t['a'][0]) == 1.0 and float(t['b'][1, 1]) == 1.0
+        # the packed one-collective form used for factor-sized states (Npad a multiple of 128)
+        g = torch.Generator().manual_seed(9)
+        Lref = torch.tril(torch.randn(256, 256, generator=g, dtype=torch.float64))
+        others = dict(alpha=torch.randn(256, 4, generator=g, dtype=torch.float64), G=torch.randn(256, 3, generator=g, dtype=torch.float64),
+                      W=torch.randn(256, 9, generator=g, dtype=torch.float64), X=torch.randn(200, 3, generator=g, dtype=torch.float64))
+        st = dict(Linv=Lref.clone() if rank == 1 else torch.full((256, 256), 3.0, dtype=torch.float64))
+        st.update({k: (v.clone() if rank == 1 else torch.zeros_like(v)) for k, v in others.items()})
+        nb = broadcast_state_packed(st, src=1)
+        assert nb == 8 * (packed_lower_elems(256) + sum(v.numel() for v in others.values()))
+        assert torch.equal(st['Linv'], Lref) and all(torch.equal(st[k], v) for k, v in others.items())
         local = torch.arange(*shard_bounds(5, world, rank), dtype=torch.float64).reshape(-1, 1)
         assert torch.equal(gather_shards(local, 5).reshape(-1), torch.arange(5, dtype=torch.float64))
         q.put((rank, 'ok'))
