@@ -104,6 +104,11 @@ _SIGNATURES = {
     'bcbf_posterior_var_i8': (c_int, [_P, _P, c_int, _P, c_int, _P, _P, c_double, c_int, c_int, _P, _P]),
     'bcbf_posterior_blocks_i8': (c_int, [_P, _P, c_int, _P, c_int, _P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, _P,
                                          _P]),
+    'bcbf_oz_factor_bytes_d': (c_longlong, [c_int, c_int]),
+    'bcbf_oz_split_factor_d': (c_int, [_P, c_int, c_int, _P, _P, c_int, _P]),
+    'bcbf_posterior_blocks_i8_d': (c_int, [_P, _P, c_int, _P, c_int, _P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, _P,
+                                           c_int, _P]),
+    'bcbf_model_set_oz_digits': (c_int, [c_void_p, c_int]),
     'bcbf_oz_debug_counters': (c_int, [c_int, POINTER(ctypes.c_ulonglong * 8)]),
     'bcbf_oz_gemm': (c_int, [c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
     'bcbf_oz_gemm_tn': (c_int, [c_int, c_int, c_int, c_double, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
@@ -113,6 +118,7 @@ _SIGNATURES = {
     'bcbf_set_trtri_i8': (c_int, [c_int]),
     'bcbf_set_potrf_i8': (c_int, [c_int]),
     'bcbf_oz_set_cluster': (c_int, [c_int]),
+    'bcbf_oz_set_group': (c_int, [c_int]),
     'bcbf_oz_profile_enable': (c_int, [c_int]),
     'bcbf_oz_profile_read': (c_int, [POINTER(c_double), POINTER(c_int)]),
     'bcbf_model_set_var_path': (c_int, [c_void_p, c_int]),

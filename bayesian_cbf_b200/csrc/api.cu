@@ -297,6 +297,7 @@ struct bcbf_model {
   double* oz_rowscale = nullptr;
   size_t cap_oz = 0;
   bool oz_ready = false;
+  int oz_sd = 7;            // digits per operand (7 default, 6 opt-in)
   double oz_split_ms = 0.0;
 };
 
@@ -327,7 +328,7 @@ static int ensure_oz_digits(bcbf_model* m, cudaStream_t s, bool timed) {
   if (m->oz_ready) return BCBF_OK;
   BCBF_REQUIRE(m->Npad <= bcbf_oz_max_npad(), "int8 covariance path supports Npad <= %d (got %d): use var_path 0",
                bcbf_oz_max_npad(), m->Npad);
-  const size_t bytes = (size_t)bcbf_oz_factor_bytes(m->Npad);
+  const size_t bytes = (size_t)bcbf_oz_factor_bytes_d(m->Npad, m->oz_sd);
   if (bytes > m->cap_oz) {
     if (m->oz_digits) { BCBF_CUDA(cudaFree(m->oz_digits)); m->oz_digits = nullptr; }
     if (m->oz_rowscale) { BCBF_CUDA(cudaFree(m->oz_rowscale)); m->oz_rowscale = nullptr; }
@@ -342,7 +343,7 @@ static int ensure_oz_digits(bcbf_model* m, cudaStream_t s, bool timed) {
     BCBF_CUDA(cudaEventCreate(&e1));
     BCBF_CUDA(cudaEventRecord(e0, s));
   }
-  int rc = bcbf_oz_split_factor(m->Linv, m->Npad, m->Npad, m->oz_digits, m->oz_rowscale, s);
+  int rc = bcbf_oz_split_factor_d(m->Linv, m->Npad, m->Npad, m->oz_digits, m->oz_rowscale, m->oz_sd, s);
   if (rc) {
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
@@ -367,6 +368,14 @@ extern "C" int bcbf_model_set_var_path(bcbf_model* m, int path) {
   return BCBF_OK;
 }
 extern "C" int bcbf_model_get_var_path(bcbf_model* m) { return m ? m->var_path : -1; }
+extern "C" int bcbf_model_set_oz_digits(bcbf_model* m, int digits) {
+  BCBF_REQUIRE(m && (digits == 6 || digits == 7), "bcbf_model_set_oz_digits: 6 or 7");
+  if (digits != m->oz_sd) {
+    m->oz_sd = digits;
+    m->oz_ready = false;      // re-split L^-1 at the next query
+  }
+  return BCBF_OK;
+}
 extern "C" double bcbf_model_oz_split_ms(bcbf_model* m) { return m ? m->oz_split_ms : 0.0; }
 
 extern "C" int bcbf_model_create(bcbf_model** out, int device) {
@@ -658,9 +667,9 @@ static int query_batch_device(bcbf_model* m, const double* dXq, const double* dU
   const bool i8 = m->var_path == 1 && Npad <= bcbf_oz_max_npad();
   if (i8) {
     if (need_var && (rc = ensure_oz_digits(m, s, false))) return rc;
-    rc = need_var ? bcbf_posterior_blocks_i8(m->oz_digits, m->oz_rowscale, Npad, m->Kstar, ldks, m->G, m->W,
-                                             m->hyp_dev + 8, m->hyp_dev + 56, m->hyp.outputscale, n, p, Qb,
-                                             need_mean ? Mk : nullptr, Bk, s)
+    rc = need_var ? bcbf_posterior_blocks_i8_d(m->oz_digits, m->oz_rowscale, Npad, m->Kstar, ldks, m->G, m->W,
+                                               m->hyp_dev + 8, m->hyp_dev + 56, m->hyp.outputscale, n, p, Qb,
+                                               need_mean ? Mk : nullptr, Bk, m->oz_sd, s)
                   : bcbf_posterior_blocks(m->Linv, Npad, Npad, m->Kstar, ldks, m->G, m->W, m->hyp_dev + 8,
                                           m->hyp_dev + 56, m->hyp.outputscale, n, p, Qb, Mk, nullptr, s);
   } else {

@@ -59,11 +59,12 @@ __device__ __forceinline__ double scale_of(double mx) {
   return ldexp(1.0, e);
 }
 
-// x (|x| <= 0.498) -> seven signed digits, x ~= sum_j d[j] 256^-(j+1)
-__device__ __forceinline__ void digits_of(double x, int (&d)[S]) {
-  long long I = __double2ll_rn(x * 72057594037927936.0);  // x 2^56
+// x (|x| <= 0.498) -> SD signed digits, x ~= sum_j d[j] 256^-(j+1)  (SD = 7: 56 bits; SD = 6: 48 bits)
+template <int SD>
+__device__ __forceinline__ void digits_of(double x, int (&d)[SD]) {
+  long long I = __double2ll_rn(x * __longlong_as_double((1023LL + 8 * SD) << 52));  // x 2^(8 SD), one rounding
 #pragma unroll
-  for (int j = S - 1; j >= 1; --j) {
+  for (int j = SD - 1; j >= 1; --j) {
     const int b = static_cast<int>(static_cast<signed char>(I & 0xFF));
     d[j] = b;
     I = (I - b) >> 8;
@@ -82,10 +83,12 @@ __global__ void rowscale_kernel(const double* __restrict__ Linv, int ld, int Npa
   if (lane == 0) rowscale[row] = scale_of(mx);
 }
 
-// blob of row block I, K step ks (ks < 4 (I+1)):  [slice 7][row group 16][k chunk 2][row 8][16 bytes]
+// blob of row block I, K step ks (ks < 4 (I+1)):  [slice SD][row group 16][k chunk 2][row 8][16 bytes]
+template <int SD>
 __global__ void __launch_bounds__(256) split_factor_kernel(const double* __restrict__ Linv, int ld,
                                                            const double* __restrict__ rowscale,
                                                            int8_t* __restrict__ blob) {
+  constexpr int S = SD, A_STEP = SD * TM * KSTEP;   // (shadow the 7-digit constants of the GEMM kernels)
   const int kc = blockIdx.x, I = blockIdx.y;
   if (kc > I) return;
   const int r = threadIdx.x % TM, half = threadIdx.x / TM;
@@ -186,12 +189,13 @@ __global__ void mean_finalize_kernel(const double* __restrict__ part, int Qpad, 
 
 // blob of column tile J, K step ks:  [slice 7][column group 8][k chunk 2][column 8][16 bytes]; column = P (q % QT) + t.
 // One thread per frakB COLUMN and 16 consecutive rows i: eight neighbouring threads store 128 contiguous bytes per slice.
-template <int P>
+template <int P, int SD>
 __global__ void __launch_bounds__(128) split_frakb_kernel(const double* __restrict__ Kstar, int ldks,
                                                           const double* __restrict__ G, int Npad, int Q, int nJ,
                                                           const unsigned long long* __restrict__ colmax,
                                                           int8_t* __restrict__ blob, double* __restrict__ colscale) {
   constexpr int QT = TN / P;
+  constexpr int S = SD, B_STEP = SD * TN * KSTEP;
   const int cg = blockIdx.x * blockDim.x + threadIdx.x;  // global column
   if (cg >= nJ * TN) return;
   const int i0 = blockIdx.y * 16;
@@ -234,7 +238,8 @@ struct VarArgs {
   int nb;         // row blocks of L^-1 (Npad / 128)
   int nJg;        // groups of CL column tiles (Qpad / (CL QT))
   int Qpad;
-  long long total_tiles;  // work items: 4 ceil(nb / 4) nJg
+  long long total_tiles;  // work items: group ceil(nb / group) nJg
+  int group;              // row blocks per scheduling group (see tile_of)
   unsigned long long* dbg;
 };
 
@@ -242,15 +247,18 @@ struct VarArgs {
 // blocks x consecutive column tiles, so CTAs running side by side share L^-1 digits ~37-fold and frakB digits 4-fold
 // through L2.  A work item is (row block I, group of CL column tiles); CTA `rank` of the cluster takes tile CL Jg + rank.
 __device__ __forceinline__ bool tile_of(const VarArgs& a, long long t, int& I, int& Jg) {
-  const int per_group = 4 * a.nJg;
+  const int G = a.group;
+  const int per_group = G * a.nJg;
   const int g = static_cast<int>(t / per_group), r = static_cast<int>(t % per_group);
-  Jg = r >> 2;
-  const int ii = ((r & 3) + static_cast<int>((t >> 2) & 3)) & 3;
-  I = a.nb - 1 - (4 * g + ii);
+  Jg = r / G;
+  const int ii = ((r % G) + static_cast<int>((t / G) % G)) % G;
+  I = a.nb - 1 - (G * g + ii);
   return I >= 0;
 }
 
+template <int SD = S>
 __device__ __forceinline__ void issue_kstep(uint32_t tmem, uint32_t a_base, uint32_t b_base, bool first) {
+  constexpr int S = SD;
 #pragma unroll
   for (int a = 0; a < S; ++a) {
     const uint64_t ad = smem_desc_kmajor(a_base + a * (TM * KSTEP), 128, 256);
@@ -271,9 +279,12 @@ __device__ __forceinline__ void issue_kstep(uint32_t tmem, uint32_t a_base, uint
 // 1050 cycles per K step with counters on) - the limiter is the shared-memory port, which carries the MMA operand reads
 // (96 KB per K step) AND the incoming copies (42 KB): 138 KB / 128 B/clk = 1080 cycles against the 920-cycle MMA pattern,
 // and multicast does not change what arrives in shared memory.  Kept as an option (bcbf_oz_set_cluster).
-template <int P, int CL>
+// SD = digits per operand: 7 (default; products with digit sum <= 6: 28 MMAs' worth per K step, 2^-56 truncation) or 6
+// (digit sum <= 5: 21 products, 2^-48 truncation: B_k to ~3e-11 of the prior scale, 25 % less tensor work; opt-in).
+template <int P, int CL, int SD>
 __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
   constexpr int QT = TN / P, NP = P * (P + 1) / 2;
+  constexpr int S = SD, A_STEP = SD * TM * KSTEP, B_STEP = SD * TN * KSTEP, STAGE = A_STEP + B_STEP;
   const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const long long worker = blockIdx.x / CL, nworkers = gridDim.x / CL;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
           }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE);
-          issue_kstep(tmem, sa, sa + A_STEP, ks == 0);
+          issue_kstep<SD>(tmem, sa, sa + A_STEP, ks == 0);
           if (CL == 1) mma_commit(&empty[stage]);  // frees the stage when these MMAs have read it
           else mma_commit_multicast(&empty[stage], 0x3);  // ... in both CTAs: the peer writes half of my stage
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
@@ -499,13 +510,15 @@ static Prof g_prof;
 static unsigned long long* g_dbg = nullptr;
 
 static int g_cluster = 1;  // CTAs per cluster of oz_var_kernel (1 or 2); bcbf_oz_set_cluster
+static int g_group = 4;    // row blocks per scheduling group of oz_var_kernel; bcbf_oz_set_group
 
-template <int P, int CL>
+template <int P, int CL, int SD>
 static int launch_var(VarArgs a, cudaStream_t stream) {
+  constexpr int kSmemBytes = NSTAGE * SD * (TM + TN) * KSTEP + 128 + TN * 8 + 4 * 160 * 8;
   int dev = 0, sms = 148;
   BCBF_CUDA(cudaGetDevice(&dev));
   BCBF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  BCBF_CUDA(cudaFuncSetAttribute(oz_var_kernel<P, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  BCBF_CUDA(cudaFuncSetAttribute(oz_var_kernel<P, CL, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
@@ -524,7 +537,7 @@ static int launch_var(VarArgs a, cudaStream_t stream) {
     if (max_clusters[dev & 63] == 0) {
       cfg.gridDim = dim3(sms - sms % CL);
       int n = 0;
-      BCBF_CUDA(cudaOccupancyMaxActiveClusters(&n, oz_var_kernel<P, CL>, &cfg));
+      BCBF_CUDA(cudaOccupancyMaxActiveClusters(&n, oz_var_kernel<P, CL, SD>, &cfg));
       max_clusters[dev & 63] = n > 0 ? n : 1;
     }
     if (workers > max_clusters[dev & 63]) workers = max_clusters[dev & 63];
@@ -537,7 +550,7 @@ static int launch_var(VarArgs a, cudaStream_t stream) {
     BCBF_CUDA(cudaEventCreate(&g_prof.e1[g_prof.n]));
     BCBF_CUDA(cudaEventRecord(g_prof.e0[g_prof.n], stream));
   }
-  BCBF_CUDA(cudaLaunchKernelEx(&cfg, oz_var_kernel<P, CL>, a));
+  BCBF_CUDA(cudaLaunchKernelEx(&cfg, oz_var_kernel<P, CL, SD>, a));
   BCBF_LAUNCH_CHECK();
   if (prof) {
     BCBF_CUDA(cudaEventRecord(g_prof.e1[g_prof.n], stream));
@@ -546,11 +559,12 @@ static int launch_var(VarArgs a, cudaStream_t stream) {
   return BCBF_OK;
 }
 
-template <int P>
+template <int P, int SD>
 static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, const double* Kstar, int ldks,
                       const double* G, const double* W, const double* Bmat, const double* Ct, double kss, int n, int Q,
                       double* Mk, double* Bk, cudaStream_t stream) {
   constexpr int QT = TN / P, NP = P * (P + 1) / 2;
+  constexpr int B_STEP = SD * TN * KSTEP;
   const int CL = g_cluster;
   const int nb = Npad / TM, nJg = ceil_div(Q, QT * CL), nJ = nJg * CL, Qpad = nJ * QT, nc = n * P;
   const int nsplit = ceil_div(Npad, kCmRows);
@@ -580,7 +594,7 @@ static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, con
   if ((rc = workspace(2, sizeof(double) * (size_t)nJ * TN, &colscale))) return rc;
   if ((rc = workspace(3, sizeof(double) * (size_t)nb * Qpad * NP, &spart))) return rc;
   // every column of every tile is written (dead columns and queries past Q: zero digits, zero scale)
-  split_frakb_kernel<P><<<dim3(ceil_div(nJ * TN, 128), Npad / 16), 128, 0, stream>>>(
+  split_frakb_kernel<P, SD><<<dim3(ceil_div(nJ * TN, 128), Npad / 16), 128, 0, stream>>>(
       Kstar, ldks, G, Npad, Q, nJ, static_cast<const unsigned long long*>(colmax), static_cast<int8_t*>(bblob),
       static_cast<double*>(colscale));
   BCBF_LAUNCH_CHECK();
@@ -593,9 +607,10 @@ static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, con
   a.nb = nb;
   a.nJg = nJg;
   a.Qpad = Qpad;
-  a.total_tiles = (long long)ceil_div(nb, 4) * 4 * nJg;
+  a.group = g_group;
+  a.total_tiles = (long long)ceil_div(nb, g_group) * g_group * nJg;
   a.dbg = g_dbg;
-  rc = CL == 2 ? launch_var<P, 2>(a, stream) : launch_var<P, 1>(a, stream);
+  rc = CL == 2 ? launch_var<P, 2, SD>(a, stream) : launch_var<P, 1, SD>(a, stream);
   if (rc) return rc;
   finalize_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(a.Spart, Qpad, nb, Q, P, Bmat, kss, Bk);
   BCBF_LAUNCH_CHECK();
@@ -1182,24 +1197,32 @@ static int run_update(int M, int N, int K, double alpha, const double* PA, int l
 
 using namespace bcbf;
 
-extern "C" long long bcbf_oz_factor_bytes(int Npad) {
-  if (Npad <= 0 || Npad % oz::TM != 0) return 0;
+extern "C" long long bcbf_oz_factor_bytes_d(int Npad, int digits) {
+  if (Npad <= 0 || Npad % oz::TM != 0 || (digits != 6 && digits != 7)) return 0;
   const long long nb = Npad / oz::TM;
-  return 2LL * nb * (nb + 1) * oz::A_STEP;
+  return 2LL * nb * (nb + 1) * digits * oz::TM * oz::KSTEP;
 }
+extern "C" long long bcbf_oz_factor_bytes(int Npad) { return bcbf_oz_factor_bytes_d(Npad, oz::S); }
 
 extern "C" int bcbf_oz_max_npad(void) { return oz::kMaxNpad; }
 
 extern "C" int bcbf_oz_split_factor(const double* Linv, int ld, int Npad, void* digits, double* rowscale,
                                     void* stream_) {
+  return bcbf_oz_split_factor_d(Linv, ld, Npad, digits, rowscale, oz::S, stream_);
+}
+
+extern "C" int bcbf_oz_split_factor_d(const double* Linv, int ld, int Npad, void* digits, double* rowscale, int ndigits,
+                                      void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BCBF_REQUIRE(Linv && digits && rowscale, "bcbf_oz_split_factor: null pointer");
+  BCBF_REQUIRE(ndigits == 6 || ndigits == 7, "bcbf_oz_split_factor: digits=%d (6 or 7)", ndigits);
   BCBF_REQUIRE(Npad > 0 && Npad % oz::TM == 0 && ld >= Npad && Npad <= oz::kMaxNpad,
                "bcbf_oz_split_factor: Npad=%d ld=%d (Npad must be a multiple of 128 and <= %d)", Npad, ld, oz::kMaxNpad);
   oz::rowscale_kernel<<<ceil_div(Npad, 8), 256, 0, stream>>>(Linv, ld, Npad, rowscale);
   BCBF_LAUNCH_CHECK();
   const int nb = Npad / oz::TM;
-  oz::split_factor_kernel<<<dim3(nb, nb), 256, 0, stream>>>(Linv, ld, rowscale, static_cast<int8_t*>(digits));
+  if (ndigits == 7) oz::split_factor_kernel<7><<<dim3(nb, nb), 256, 0, stream>>>(Linv, ld, rowscale, static_cast<int8_t*>(digits));
+  else oz::split_factor_kernel<6><<<dim3(nb, nb), 256, 0, stream>>>(Linv, ld, rowscale, static_cast<int8_t*>(digits));
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }
@@ -1208,20 +1231,31 @@ extern "C" int bcbf_posterior_blocks_i8(const void* digits, const double* rowsca
                                         int ldks, const double* G, const double* W, const double* Bmat,
                                         const double* Ct, double kss, int n, int p, int Q, double* Mk, double* Bk,
                                         void* stream_) {
+  return bcbf_posterior_blocks_i8_d(digits, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, p, Q, Mk, Bk, oz::S,
+                                    stream_);
+}
+
+extern "C" int bcbf_posterior_blocks_i8_d(const void* digits, const double* rowscale, int Npad, const double* Kstar,
+                                          int ldks, const double* G, const double* W, const double* Bmat,
+                                          const double* Ct, double kss, int n, int p, int Q, double* Mk, double* Bk,
+                                          int ndigits, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(ndigits == 6 || ndigits == 7, "bcbf_posterior_blocks_i8: digits=%d (6 or 7)", ndigits);
   BCBF_REQUIRE(digits && rowscale && Kstar && G && Bmat && (Mk || Bk), "bcbf_posterior_blocks_i8: null pointer");
   BCBF_REQUIRE(!Mk || (W && Ct), "bcbf_posterior_blocks_i8: Mk requested without W / Ct");
   BCBF_REQUIRE(n >= 1 && n <= BCBF_MAX_N_DIM, "bcbf_posterior_blocks_i8: n=%d", n);
   BCBF_REQUIRE(Npad > 0 && Npad % oz::TM == 0 && Npad <= oz::kMaxNpad && Q >= 1 && ldks >= Q,
                "bcbf_posterior_blocks_i8: Npad=%d Q=%d ldks=%d", Npad, Q, ldks);
   const int8_t* A = static_cast<const int8_t*>(digits);
+#define BCBF_OZ_RUN(P_, D_) oz::run_blocks<P_, D_>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream)
   switch (p) {
-    case 1: return oz::run_blocks<1>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream);
-    case 2: return oz::run_blocks<2>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream);
-    case 3: return oz::run_blocks<3>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream);
-    case 4: return oz::run_blocks<4>(A, rowscale, Npad, Kstar, ldks, G, W, Bmat, Ct, kss, n, Q, Mk, Bk, stream);
+    case 1: return ndigits == 7 ? BCBF_OZ_RUN(1, 7) : BCBF_OZ_RUN(1, 6);
+    case 2: return ndigits == 7 ? BCBF_OZ_RUN(2, 7) : BCBF_OZ_RUN(2, 6);
+    case 3: return ndigits == 7 ? BCBF_OZ_RUN(3, 7) : BCBF_OZ_RUN(3, 6);
+    case 4: return ndigits == 7 ? BCBF_OZ_RUN(4, 7) : BCBF_OZ_RUN(4, 6);
     default: break;
   }
+#undef BCBF_OZ_RUN
   set_last_error("bcbf_posterior_blocks_i8: p=%d unsupported", p);
   return BCBF_ERR_INVALID;
 }
@@ -1308,6 +1342,12 @@ extern "C" int bcbf_oz_gemm(int M, int N, int K, double alpha, const double* A, 
 }
 
 // CTAs per cluster of oz_var_kernel: 1 (default) or 2 (the pair multicasts the L^-1 digits to each other).
+extern "C" int bcbf_oz_set_group(int row_blocks) {
+  BCBF_REQUIRE(row_blocks >= 1 && row_blocks <= 32, "bcbf_oz_set_group: 1..32");
+  oz::g_group = row_blocks;
+  return BCBF_OK;
+}
+
 extern "C" int bcbf_oz_set_cluster(int ctas) {
   BCBF_REQUIRE(ctas == 1 || ctas == 2, "bcbf_oz_set_cluster: 1 or 2");
   oz::g_cluster = ctas;

@@ -91,6 +91,12 @@ class MVGPModel:
         check(self._lib.bcbf_model_set_var_path(self._h, self.VAR_PATHS[path] if isinstance(path, str) else int(path)))
         return self
 
+    def set_oz_digits(self, digits):
+        """Digits per operand of the int8 path: 7 (default, FP64 rounding level) or 6 (opt-in: 21 instead of 28 digit
+        products, B_k to ~3e-11 of the prior scale)."""
+        check(self._lib.bcbf_model_set_oz_digits(self._h, int(digits)))
+        return self
+
     @property
     def var_path(self):
         return {v: k for k, v in self.VAR_PATHS.items()}[self._lib.bcbf_model_get_var_path(self._h)]

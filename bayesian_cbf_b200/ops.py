@@ -233,14 +233,16 @@ def posterior_blocks(Linv, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, 
     return Mk, Bk
 
 
-def oz_split_factor(Linv):
-    """Digits of L^-1 for the int8 tensor-core covariance path (csrc/ozaki.cu): (digits uint8 blob, rowscale (Npad))."""
+def oz_split_factor(Linv, ndigits=7):
+    """Digits of L^-1 for the int8 tensor-core covariance path (csrc/ozaki.cu): (digits uint8 blob, rowscale (Npad)).
+    ndigits: 7 (default) or 6 (the opt-in 21-product mode; pass the same count to posterior_blocks_i8)."""
     _req(Linv)
     Npad = Linv.shape[0]
     lib = _lib.load()
-    digits = torch.empty(lib.bcbf_oz_factor_bytes(Npad), dtype=torch.int8, device=Linv.device)
+    digits = torch.empty(lib.bcbf_oz_factor_bytes_d(Npad, int(ndigits)), dtype=torch.int8, device=Linv.device)
     rowscale = torch.empty(Npad, dtype=torch.float64, device=Linv.device)
-    check(lib.bcbf_oz_split_factor(_ptr(Linv), Linv.stride(0), Npad, _ptr(digits), _ptr(rowscale), _stream()))
+    check(lib.bcbf_oz_split_factor_d(_ptr(Linv), Linv.stride(0), Npad, _ptr(digits), _ptr(rowscale), int(ndigits),
+                                     _stream()))
     return digits, rowscale
 
 
@@ -254,7 +256,7 @@ def posterior_var_i8(digits, rowscale, Kstar, G, Bmat, kss, p, Q):
     return Bk
 
 
-def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, want_cov=True):
+def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, want_cov=True, ndigits=7):
     """posterior_blocks with the covariance contraction on the int8 tensor cores and the mean fused into the pass over
     K* that finds the column scales (bcbf_posterior_blocks_i8)."""
     _req(rowscale, Kstar, G, W, Bmat, Ct)
@@ -262,9 +264,9 @@ def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, w
     dev = Kstar.device
     Mk = torch.empty(Q, n, p, dtype=torch.float64, device=dev) if want_mean else None
     Bk = torch.empty(Q, p, p, dtype=torch.float64, device=dev) if want_cov else None
-    check(_lib.load().bcbf_posterior_blocks_i8(_ptr(digits), _ptr(rowscale), Npad, _ptr(Kstar), Kstar.stride(0), _ptr(G),
-                                               _ptr(W), _ptr(Bmat), _ptr(Ct), float(kss), n, p, Q, _ptr(Mk), _ptr(Bk),
-                                               _stream()))
+    check(_lib.load().bcbf_posterior_blocks_i8_d(_ptr(digits), _ptr(rowscale), Npad, _ptr(Kstar), Kstar.stride(0), _ptr(G),
+                                                 _ptr(W), _ptr(Bmat), _ptr(Ct), float(kss), n, p, Q, _ptr(Mk), _ptr(Bk),
+                                                 int(ndigits), _stream()))
     return Mk, Bk
 
 

@@ -279,12 +279,13 @@ def run_ours(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     lib = _lib.load()
+    if args.oz_group:
+        _lib.check(lib.bcbf_oz_set_group(args.oz_group))
     N, QS, K, W = args.n_train, args.queries_per_step, args.steps, args.warmup
     X, U, Xdot, hyp, jitter = make_workload(N)
     hyper = make_hyper(N_DIM, P_DIM, hyp['lengthscale'].numpy(), float(hyp['outputscale']), hyp['A'].numpy(),
                        hyp['B'].numpy(), hyp['C'].numpy())
-    model = MVGPModel(local_rank).set_var_path(args.var_path)
-    i8 = args.var_path == 'int8'
+XX
     prof_enable = lib.bcbf_oz_profile_enable if i8 else lib.bcbf_profile_enable
     prof_read = lib.bcbf_oz_profile_read if i8 else lib.bcbf_profile_read
 
@@ -403,7 +404,7 @@ def run_ours(args):
     if i8:
         # oz_var_kernel runs the contraction on the int8 tensor pipe: 7 x 7 digit products with digit sum <= 6 = 28
         # int8 GEMMs of the same (triangular) shape, N^2/2 MACs per column each -> 28 N^2 p int8 ops per query
-        ops_per_launch = 28.0 * fp64_flops_per_launch
+        ops_per_launch = nprod * fp64_flops_per_launch
         achieved = ops_per_launch / (kernel_ms * 1e-3) * 1e-12
         # denominator: the int8 tensor pipe measured LIVE on this GPU (MEASURED_PEAKS.json has HBM and bf16 only).
         # The kernel runs inside a seconds-long step under the power cap, so `peak` is the sustained figure: what the bare
@@ -497,8 +498,9 @@ def run_ours(args):
                 config=dict(workload='synthetic unicycle MVGP fit N=%d + batched posterior query, %d queries/step/GPU '
                                      '(BASELINE configs[3]; 53 steps = 1.004M queries)' % (N, QS),
                             n_train=N, n=N_DIM, m=M_DIM, queries_per_step=QS, outputs='M_k(3x3), B_k(3x3), mean(3), svar',
-                            covariance_kernel=('oz_var_kernel: tcgen05 int8 tensor cores, 7x7 error-free digit splitting of '
-                                               'both FP64 operands, FP64 recombination' if i8 else
+                            covariance_kernel=('oz_var_kernel: tcgen05 int8 tensor cores, %dx%d error-free digit splitting of '
+                                               'both FP64 operands (%d digit products), FP64 recombination'
+                                               % (args.digits, args.digits, int(nprod)) if i8 else
                                                'post_var_kernel: FP64 tensor pipe (DMMA)'),
                             parallelism='queries sharded, factor broadcast once (NCCL)' if world > 1 else 'single GPU',
                             l2='inputs larger than L2: L^-1 is %.2f GB (lower triangle), streamed every step' % (4.0 * N * (N + 1) / 1e9)),
@@ -744,6 +746,10 @@ def main():
     ap.add_argument('--var-path', default='int8', choices=['dmma', 'int8'],
                     help='kernel of the N^2 p covariance contraction: FP64 tensor pipe, or int8 tensor cores (tcgen05) with '
                          'error-free digit splitting')
+    ap.add_argument('--digits', type=int, default=7, choices=[6, 7],
+                    help='digits per operand of the int8 covariance kernel: 7 (default, 28 digit products, FP64 rounding '
+                         'level) or 6 (opt-in: 21 products, B_k to ~3e-11 of the prior scale)')
+    ap.add_argument('--oz-group', type=int, default=None, help='row blocks per scheduling group of oz_var_kernel (tuning)')
     ap.add_argument('--e2e-steps', type=int, default=8)
     ap.add_argument('--cpu-sample-queries', type=int, default=2048)
     ap.add_argument('--ref-queries-per-step', type=int, default=1024)

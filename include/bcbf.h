@@ -225,9 +225,24 @@ int bcbf_posterior_var_i8(const void* digits, const double* rowscale, int Npad, 
 int bcbf_posterior_blocks_i8(const void* digits, const double* rowscale, int Npad, const double* Kstar, int ldks,
                              const double* G, const double* W, const double* Bmat, const double* Ct, double kss, int n,
                              int p, int Q, double* Mk, double* Bk, void* stream);
+/* The same with an explicit digit count (6 or 7; the entry points above use 7).  Seven digits keep the 28 digit products
+ * whose weights reach 2^-56 of row scale x column scale (FP64 rounding level: B_k to ~4e-13 of the prior scale at
+ * N = 16384).  Six digits keep 21 products (2^-48: B_k to ~3e-11 of the prior scale, still inside the 1e-9 parity
+ * tolerance) for 25 % less tensor work — an opt-in trade, never the default.  The digit array of L^-1 must have been split
+ * with the same count (bcbf_oz_factor_bytes_d bytes).                                                                   */
+long long bcbf_oz_factor_bytes_d(int Npad, int digits);
+int bcbf_oz_split_factor_d(const double* Linv, int ld, int Npad, void* digits_out, double* rowscale, int digits,
+                           void* stream);
+int bcbf_posterior_blocks_i8_d(const void* digits_in, const double* rowscale, int Npad, const double* Kstar, int ldks,
+                               const double* G, const double* W, const double* Bmat, const double* Ct, double kss, int n,
+                               int p, int Q, double* Mk, double* Bk, int digits, void* stream);
 /* oz_var_kernel runs as single CTAs (1, default) or as clusters of 2 CTAs that multicast the L^-1 digits to each other
  * (bit-identical results; measured no faster: the shared-memory port, not L2, is the limiter). */
 int bcbf_oz_set_cluster(int ctas);
+/* Work order of oz_var_kernel: consecutive work items sweep `row_blocks` row blocks of L^-1 x consecutive column tiles, so
+ * the 148 CTAs running side by side share row_blocks digit blobs of L^-1 and 148 / row_blocks of frakB through L2
+ * (28 row_blocks + 14 * 148 / row_blocks KB per K step: minimal near 8).  Results do not depend on it (bit-identical). */
+int bcbf_oz_set_group(int row_blocks);
 /* Development aid: pipeline counters of oz_var_kernel (see csrc/ozaki.cu). */
 int bcbf_oz_debug_counters(int enable, unsigned long long out[8]);
 /* General FP64-accurate GEMM on the int8 tensor cores (same digit splitting; csrc/ozaki.cu: oz_gemm_kernel):
@@ -372,6 +387,8 @@ int bcbf_model_fit_timing(bcbf_model* m, double out_ms[5]);
  * results).  With path 1 the fit also splits
  * L^-1 into digits (bcbf_model_oz_split_ms: device time of that step in the last fit; it is part of fit "total").  */
 int bcbf_model_set_var_path(bcbf_model* m, int path);
+/* Digits per operand of path 1: 7 (default) or 6 (see bcbf_posterior_blocks_i8_d); takes effect at the next query. */
+int bcbf_model_set_oz_digits(bcbf_model* m, int digits);
 int bcbf_model_get_var_path(bcbf_model* m);
 double bcbf_model_oz_split_ms(bcbf_model* m);
 

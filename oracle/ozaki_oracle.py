@@ -26,9 +26,10 @@ def scale_of(mx):
     return np.where(mx > 0.0, np.ldexp(1.0, e), 1.0)
 
 
-def digits_of(x):
-    """x (|x| <= 0.498) -> int64 array (..., 7) of digits in [-128, 127] (csrc/ozaki.cu: digits_of)."""
-    I = np.rint(np.asarray(x, dtype=np.float64) * 2.0 ** 56).astype(np.int64)   # exact: power-of-two scaling, one rint
+def digits_of(x, S=S):
+    """x (|x| <= 0.498) -> int64 array (..., S) of digits in [-128, 127] of round(x 2^(8 S)) (csrc/ozaki.cu: digits_of;
+    S = 7 everywhere except the opt-in 6-digit mode of the covariance kernel)."""
+    I = np.rint(np.asarray(x, dtype=np.float64) * 2.0 ** (8 * S)).astype(np.int64)   # exact: power-of-two scaling, one rint
     d = np.zeros(I.shape + (S,), dtype=np.int64)
     for j in range(S - 1, 0, -1):
         b = ((I & 0xFF) ^ 0x80) - 0x80         # low byte read as signed
@@ -103,7 +104,7 @@ def update(C, PA, PB, alpha=-1.0):
     return v * scale + np.asarray(C, dtype=np.float64)
 
 
-def posterior_bk(Linv, Kstar, G, Bmat, kss):
+def posterior_bk(Linv, Kstar, G, Bmat, kss, digits=S):
     """B_k (Q,p,p) = kss B - V^T V, V = L^-1 frakB, exactly as oz_var_kernel + finalize_kernel compute it:
     Linv (Npad,Npad) lower triangular, Kstar (Npad,Q), G (Npad,p).  Row scales from the lower triangle of L^-1, column
     scales from max_i |K*[i,q]| |G[i,t]|, digits of (K* G) / scale, recombination as in gemm(); per 128-row block the p(p+1)/2
@@ -118,9 +119,9 @@ def posterior_bk(Linv, Kstar, G, Bmat, kss):
     frak = (Kstar[:, :, None] * G[:, None, :]).reshape(Npad, Q * p)            # column = p q + t, one rounding per entry
     cmax = (np.abs(Kstar)[:, :, None] * np.abs(G)[:, None, :]).reshape(Npad, Q * p).max(axis=0)
     cs = scale_of(cmax)
-    da, db = digits_of(Linv / rs[:, None]), digits_of(frak / cs[None, :])
+    da, db = digits_of(Linv / rs[:, None], digits), digits_of(frak / cs[None, :], digits)
     v = np.zeros((Npad, Q * p))
-    for d in range(S - 1, -1, -1):
+    for d in range(digits - 1, -1, -1):                 # digits = 6: the 21 products with digit sum <= 5
         acc = np.zeros(v.shape, dtype=np.int64)
         for a in range(d + 1):
             acc += da[..., a] @ db[..., d - a]

@@ -204,11 +204,11 @@ def oz_max_npad():
     return 18432
 
 
-def oz_split_factor(Linv):
+def oz_split_factor(Linv, ndigits=7):
     return Linv, torch.ones(Linv.shape[0], dtype=torch.float64)
 
 
-def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, want_cov=True):
+def posterior_blocks_i8(digits, rowscale, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=True, want_cov=True, ndigits=7):
     return posterior_blocks(digits, Kstar, G, W, Bmat, Ct, kss, n, p, Q, want_mean=want_mean, want_cov=want_cov)
 
 

@@ -360,3 +360,52 @@ def test_oz_gemm_tn_lower_is_bit_identical_and_accurate():
     exact = (Lh.T.astype(np.longdouble) @ Lh.astype(np.longdouble)).astype(np.float64)
     bound = np.abs(Lh).max(0)[:, None] * np.abs(Lh).max(0)[None, :]
     assert (np.abs(P - exact) / bound).max() < Lh.shape[0] * 2.0 ** -50
+
+
+@pytest.mark.parametrize('N,n,m,Q', [(300, 3, 2, 50), (640, 2, 1, 200)])
+def test_six_digit_mode_is_bit_identical_to_its_restatement_and_inside_the_parity_tolerance(N, n, m, Q):
+    """The opt-in 6-digit mode of oz_var_kernel (21 digit products instead of 28): bit for bit the arithmetic of
+    oracle/ozaki_oracle.py:posterior_bk(digits=6); against the CPU oracle of the path its B_k stays inside the 1e-9
+    parity tolerance (measured ~1e-11 of the prior scale) but is, as designed, less exact than the 7-digit default."""
+    from bayesian_cbf_b200 import ops
+    from oracle import ozaki_oracle as Z
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(43, N, n, m, Q, box=2.0)
+    p = m + 1
+    L, Linv, G, alpha, W = _fit_on_gpu(X, U, Xdot, hyp, jit)
+    Ks = ops.cross_gram(_d(X), _d(Xq), _d(hyp.lengthscale), float(hyp.outputscale))
+    out = {}
+    for nd in (6, 7):
+        digits, rowscale = ops.oz_split_factor(Linv, ndigits=nd)
+        _, Bk = ops.posterior_blocks_i8(digits, rowscale, Ks, G, W, _d(hyp.B), _d(hyp.C.t()), float(hyp.outputscale), n, p, Q,
+                                        want_mean=False, ndigits=nd)
+        out[nd] = Bk.cpu().numpy()
+    ref6 = Z.posterior_bk(Linv.cpu().numpy(), Ks.cpu().numpy()[:, :Q], G.cpu().numpy(), hyp.B.numpy(),
+                          float(hyp.outputscale), digits=6)
+    assert np.array_equal(out[6], ref6)
+    Lref = O.perturbed_cholesky(hyp, X, O.homogeneous(U), [jit], direct=True)
+    _, Bk_o = O.posterior_blocks(hyp, X, U, Xdot, Lref, Xq, direct=True)
+    prior = (hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)).item()
+    e6 = np.abs(out[6] - Bk_o.numpy()).max() / prior
+    e7 = np.abs(out[7] - Bk_o.numpy()).max() / prior
+    print('B_k error / prior scale: 6 digits %.2e, 7 digits %.2e' % (e6, e7))
+    assert e6 < 1e-9 and e7 < 1e-9
+    assert np.abs(out[6] - out[7]).max() / prior < 1e-9 and not np.array_equal(out[6], out[7])
+
+
+def test_model_handle_six_digit_option():
+    from bayesian_cbf_b200.model import MVGPModel, make_hyper
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(12, 900, 3, 2, 3000, box=2.0)
+    h = make_hyper(3, 3, hyp.lengthscale.numpy(), float(hyp.outputscale), hyp.A.numpy(), hyp.B.numpy(), hyp.C.numpy())
+    model = MVGPModel(0).set_var_path('int8')
+    model.fit(h, X.numpy(), U.numpy(), Xdot.numpy(), jit.numpy(), 1e-5)
+    o7 = model.query(Xq.numpy(), Uq.numpy())
+    o6 = model.set_oz_digits(6).query(Xq.numpy(), Uq.numpy())        # re-splits L^-1 with six digits
+    o7b = model.set_oz_digits(7).query(Xq.numpy(), Uq.numpy())
+    model.close()
+    prior = (hyp.outputscale * torch.linalg.matrix_norm(hyp.B, 2)).item()
+    assert np.array_equal(o7['Bk'], o7b['Bk']) and np.array_equal(o7['mean'], o6['mean'])
+    d = np.abs(o6['Bk'] - o7['Bk']).max() / prior
+    assert 0 < d < 1e-9, d
+    with pytest.raises(Exception):
+        model2 = MVGPModel(0)
+        model2.set_oz_digits(5)
