@@ -285,7 +285,9 @@ def run_ours(args):
     X, U, Xdot, hyp, jitter = make_workload(N)
     hyper = make_hyper(N_DIM, P_DIM, hyp['lengthscale'].numpy(), float(hyp['outputscale']), hyp['A'].numpy(),
                        hyp['B'].numpy(), hyp['C'].numpy())
-XX
+    model = MVGPModel(local_rank).set_var_path(args.var_path).set_oz_digits(args.digits)
+    nprod = {7: 28.0, 6: 21.0}[args.digits]
+    i8 = args.var_path == 'int8'
     prof_enable = lib.bcbf_oz_profile_enable if i8 else lib.bcbf_profile_enable
     prof_read = lib.bcbf_oz_profile_read if i8 else lib.bcbf_profile_read
 
