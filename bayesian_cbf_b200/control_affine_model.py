@@ -32,10 +32,11 @@ from ._lib import NotPositiveDefiniteError
 from .gp_algebra import GaussianProcess
 from .gp_modules import (ConstantMean, GammaPrior, IndexKernel, LinearKernel, MultivariateNormalResult, RBFKernel,
                          ScaleKernel)
-from .matrix_variate_multitask_kernel import HetergeneousMatrixVariateKernel, MatrixVariateIndexKernel
+from .matrix_variate_multitask_kernel import (HetergeneousCoregionalizationKernel, HetergeneousMatrixVariateKernel,
+                                              MatrixVariateIndexKernel)
 from .matrix_variate_multitask_model import HetergeneousMatrixVariateMean
 from .misc import DynamicsModel, torch_kron
-from .mll import mvgp_log_marginal
+from .mll import dense_log_marginal, mvgp_log_marginal
 
 LOG = logging.getLogger(__name__)
 LOG.setLevel(logging.INFO)
@@ -874,8 +875,9 @@ ControlAffineRegMatrixDiag = partial(
 # instead of the Kronecker pair (A, B).  It exists in the reference as the baseline the MVGP is compared against
 # (control_affine_model.py:1106-1331; speed test pendulum.py:1316-1319).  The (N n) x (N n) factorisation and every
 # N-sized product run on the same CUDA kernels; the (u^T (x) I) Sigma (u (x) I) contraction that assembles the Gram
-# entries is small-index glue.  fit() with training_iter > 0 is not provided for this comparator (the fused log
-# marginal of mll.py is specific to the Kronecker model).
+# entries is small-index glue.  fit() runs Adam on the dense (N n)-dimensional log marginal (mll.dense_log_marginal:
+# CUDA Cholesky / inverse / K^-1, the covariance assembled differentiably by HetergeneousCoregionalizationKernel) —
+# the reference's speed test fits this comparator for 50 iterations before timing it (pendulum.py:1366).
 # =====================================================================================================================
 class ControlAffineVectorGP(ControlAffineExactGP):
     def __init__(self, x_dim, u_dim, likelihood, rank=None, gamma_length_scale_prior=None):
@@ -888,12 +890,12 @@ class ControlAffineVectorGP(ControlAffineExactGP):
         self.task_covar = IndexKernel(num_tasks=num_tasks, rank=(num_tasks if rank is None else rank))
         prior = None if gamma_length_scale_prior is None else GammaPrior(*gamma_length_scale_prior)
         self.input_covar = ScaleKernel(RBFKernel(lengthscale_prior=prior) + LinearKernel())
-        self.covar_module = None     # the lazy HetergeneousCoregionalizationKernel is only needed by gpytorch's fit
+        self.covar_module = HetergeneousCoregionalizationKernel(self.task_covar, self.input_covar, self.decoder)
         self.train_inputs = None
         self.train_targets = None
 
     def forward(self, mxu):
-        raise NotImplementedError("ControlAffineVectorGP.forward (gpytorch training path) is not provided")
+        return MultivariateNormalResult(self.mean_module(mxu), self.covar_module(mxu, mxu))
 
     def state_dict(self, *a, **k):
         return dict(matshape=self.matshape, decoder=self.decoder.state_dict(),
@@ -909,12 +911,35 @@ class ControlAffineRegressorVector(ControlAffineRegressor):
     def _fit_with_warnings(self, Xtrain_in, Utrain_in, XdotTrain_in, training_iter=50, lr=0.1):
         if Xtrain_in.shape[0] == 0:
             return self
-        if training_iter > 0:
-            raise NotImplementedError("hyper-parameter fitting of the CoGP comparator is not provided; set its "
-                                      "parameters and call fit(..., training_iter=0)")
+        _need_cuda(self.device)
+        model = self.model
         Xtrain, Utrain, XdotTrain = [self._ensure_device_dtype(X) for X in (Xtrain_in, Utrain_in, XdotTrain_in)]
         self.clear_cache()
-        self.model.set_train_data(Xtrain, Utrain, XdotTrain)
+        model.set_train_data(Xtrain, Utrain, XdotTrain)
+        model.train()
+        optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+        scheduler = torch.optim.lr_scheduler.MultiStepLR(
+            optimizer, milestones=(torch.tensor([0.3, 0.6, 0.8, 0.90]) * training_iter).tolist())
+        MXU = model.train_inputs[0]
+        prior = model.input_covar.base_kernel.kernels[0].lengthscale_prior
+        self.fit_losses = []
+        for i in range(training_iter):          # the loop of the base class (reference :310-334) on the dense density
+            optimizer.zero_grad()
+            if self._fit_noise_source is not None:
+                noise = torch.as_tensor(next(self._fit_noise_source)).reshape(-1).to(device=self.device, dtype=XdotTrain.dtype)
+            else:
+                noise = torch.rand(XdotTrain.numel(), dtype=XdotTrain.dtype).to(self.device)
+            y = (XdotTrain.reshape(-1) * (1 + 1e-6 * noise)).double()
+            out = model(MXU)
+            logp = dense_log_marginal(out.covariance_matrix.double(), y - out.mean.double())
+            if prior is not None:
+                logp = logp + prior.log_prob(model.input_covar.base_kernel.kernels[0].lengthscale.double())
+            loss = -logp / y.numel()
+            assert not torch.isnan(loss).any() and not torch.isinf(loss).any()
+            loss.backward()
+            self.fit_losses.append(loss.detach())
+            optimizer.step()
+            scheduler.step()
         return self
 
     def set_hyperparameters(self, lengthscale=None, outputscale=None, Sigma=None, C=None, linear_variance=None):

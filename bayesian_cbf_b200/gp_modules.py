@@ -111,7 +111,18 @@ class RBFKernel(Kernel):
         s = torch.ones((), dtype=torch.float64, device=x1.device) if outputscale is None else outputscale.double()
         ls = self.lengthscale.reshape(-1).double().expand(x1.shape[-1]).contiguous()
         a, c = x1.double(), x2.double()
-        if a.requires_grad or c.requires_grad:
+        if torch.is_grad_enabled() and self.training and (self.raw_lengthscale.requires_grad or s.requires_grad):
+            # hyper-parameter fit of a model that evaluates this module directly (the CoGP comparator): the squared
+            # distances come from the fused kernel (log of the unit-lengthscale Gram), the lengthscale / scale
+            # dependence is elementwise and differentiable
+            one = torch.ones(a.shape[-1], dtype=torch.float64, device=a.device)
+            if self.raw_lengthscale.numel() == 1:
+                D2 = -2.0 * torch.log(ops.gram_ca(a.contiguous(), c.contiguous(), one, 1.0).clamp_min(1e-300))
+                K = s * torch.exp(-0.5 * D2 / (self.lengthscale.double().reshape(()) ** 2))
+            else:
+                d = (a.unsqueeze(1) - c.unsqueeze(0)) / ls
+                K = s * torch.exp(-0.5 * (d * d).sum(-1))
+        elif a.requires_grad or c.requires_grad:
             K = autograd_ops.rbf_kernel(a, c, ls.detach(), s.detach())
         else:
             K = ops.gram_ca(a.contiguous(), c.contiguous(), ls.detach(), float(s.detach()))
@@ -205,6 +216,11 @@ class LinearKernel(Kernel):
 
     def forward(self, x1, x2, diag=False, outputscale=None, **params):
         _need_cuda(x1, 'LinearKernel')
+        if torch.is_grad_enabled() and self.training and self.raw_variance.requires_grad:
+            G = ops.gemm(x1.double(), x2.double(), transb=True)
+            sc = self.variance.double().reshape(()) * (1.0 if outputscale is None else outputscale.double())
+            K = (sc * G).to(x1.dtype)
+            return torch.diagonal(K) if diag else K
         s = 1.0 if outputscale is None else float(outputscale.detach())
         K = ops.gemm(x1.double(), x2.double(), transb=True, alpha=s * float(self.variance.detach()))
         K = K.to(x1.dtype)

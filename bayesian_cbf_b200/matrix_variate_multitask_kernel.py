@@ -183,3 +183,69 @@ class HetergeneousMatrixVariateKernel(MatrixVariateKernel):
                 assert not torch.isnan(value).any()
         res = self.mask_dependent_covar(M1[..., 0], U1, M2[..., 0], U2, X1, X2, covar_xx).to(mxu1.dtype)
         return torch.diagonal(res) if diag else res
+
+
+class HetergeneousCoregionalizationKernel(MatrixVariateKernel):
+    """The CoGP comparator's covariance (reference :207-316): vec F(x) ~ GP with ONE (p n) x (p n) coregionalisation matrix
+    Sigma = task_covar_module.covar_matrix instead of the Kronecker pair (A, B); rows sorted train-first as above:
+
+        [ (H1 (x) I_n)(K11 (x) Sigma)(H2^T (x) I_n)      (H1 (x) I_n)(K12 (x) Sigma) ]
+        [                (.)^T                                  K22 (x) Sigma         ]
+
+    H = blockdiag(uh_i^T).  Sigma's index is (q in p, r in n), r fastest.  The data kernel is whatever module was handed
+    in, evaluated densely; the contractions over the small (p, n) indices are einsum glue and stay differentiable (the
+    comparator's fit back-propagates through them)."""
+
+    def num_outputs_per_input(self, mxu1, mxu2):
+        M1, X1, _ = self.decoder.decode(mxu1)
+        M1s = M1[..., 0]
+        end = _train_end(M1s)
+        test_size = (M1s.size(-1) - end) * self.task_covar_module.covar_matrix.shape[-1]
+        return (end * X1.shape[-1] + test_size) / M1s.size(-1)
+
+    def _sigma4(self):
+        _, n, p = self.decoder.sizes
+        Sigma = _dense(self.task_covar_module.covar_matrix)
+        return Sigma, Sigma.reshape(p, n, p, n), n, p
+
+    def kernel1(self, Kxx, UH1, UH2):
+        """(H1 (x) I)(K (x) Sigma)(H2^T (x) I): entry [(i,r),(j,s)] = K_ij sum_qq' uh1_i[q] Sigma[(q,r),(q',s)] uh2_j[q']."""
+        _, S4, n, _ = self._sigma4()
+        uSu = torch.einsum('iq,qrts,jt->irjs', UH1.to(S4.dtype), S4, UH2.to(S4.dtype))
+        return (Kxx.unsqueeze(1).unsqueeze(-1) * uSu).reshape(UH1.shape[0] * n, UH2.shape[0] * n)
+
+    def kernel2(self, Kxx):
+        Sigma, _, _, _ = self._sigma4()
+        return torch_kron(Kxx, Sigma, batch_dims=0)
+
+    def correlation_kernel_12(self, Kxx, UH1):
+        """(H1 (x) I)(K12 (x) Sigma): entry [(i,r),(j,q',s)] = K_ij sum_q uh1_i[q] Sigma[(q,r),(q',s)]."""
+        _, S4, n, p = self._sigma4()
+        uS = torch.einsum('iq,qrts->irts', UH1.to(S4.dtype), S4)                       # (N1, n, p, n)
+        return (Kxx.reshape(Kxx.shape[0], 1, Kxx.shape[1], 1, 1) * uS.unsqueeze(2)).reshape(
+            UH1.shape[0] * n, Kxx.shape[1] * p * n)
+
+    def mask_dependent_covar(self, M1s, U1, M2s, U2, covar_xx):
+        e1, e2 = _train_end(M1s), _train_end(M2s)
+        assert (M1s[e1:] == 0).all() and (M2s[e2:] == 0).all(), "rows must be sorted train-first"
+        n11 = bool(e1 and e2)
+        n22 = bool((covar_xx.shape[0] - e1) and (covar_xx.shape[1] - e2))
+        k11 = self.kernel1(covar_xx[:e1, :e2], U1[:e1], U2[:e2]) if n11 else None
+        k22 = self.kernel2(covar_xx[e1:, e2:]) if n22 else None
+        if n11 and n22:
+            k12 = self.correlation_kernel_12(covar_xx[:e1, e2:], U1[:e1])
+            k21 = self.correlation_kernel_12(covar_xx[e1:, :e2].transpose(0, 1), U2[:e2]).transpose(0, 1)
+            return torch.cat([torch.cat([k11, k12], dim=1), torch.cat([k21, k22], dim=1)], dim=0)
+        return k22 if k11 is None else k11
+
+    def forward(self, mxu1, mxu2, diag=False, last_dim_is_batch=False, **params):
+        assert not torch.isnan(mxu1).any() and not torch.isnan(mxu2).any()
+        if last_dim_is_batch:
+            raise RuntimeError("HetergeneousCoregionalizationKernel does not accept the last_dim_is_batch argument.")
+        M1, X1, U1 = self.decoder.decode(mxu1)
+        M2, X2, U2 = self.decoder.decode(mxu2)
+        covar_x = _dense(self.data_covar_module.forward(X1, X2, **params)).to(mxu1.device)
+        for name, value in self.data_covar_module.named_parameters():
+            assert not torch.isnan(value).any()
+        res = self.mask_dependent_covar(M1[..., 0], U1, M2[..., 0], U2, covar_x)
+        return torch.diagonal(res) if diag else res

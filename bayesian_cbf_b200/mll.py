@@ -91,3 +91,54 @@ def mvgp_log_marginal(lengthscale, outputscale, A, B, C, X, UH, Xdot):
     _need_cuda(lengthscale, A, B, C, X, UH, Xdot)
     return _MVGPLogMarginal.apply(lengthscale.reshape(-1), outputscale.reshape(()), A, B, C, X.contiguous(),
                                   UH.contiguous(), Xdot.contiguous())
+
+
+class _DenseLogMarginal(torch.autograd.Function):
+    """log N(r; 0, K) for a dense SPD K (M x M) — the CoGP comparator's marginal likelihood, whose (N n) x (N n)
+    covariance has no Kronecker structure (reference control_affine_model.py:1106-1127 hands it to gpytorch's
+    ExactMarginalLogLikelihood).  Forward: blocked Cholesky (psd-safe jitter escalation 1e-8 * 10^t like gpytorch),
+    triangular inverse, alpha = K^-1 r, all on the CUDA kernels; backward: dK = 1/2 (alpha alpha^T - K^-1), dr = -alpha.
+    K itself is assembled by the caller with differentiable glue (HetergeneousCoregionalizationKernel)."""
+
+    @staticmethod
+    def forward(ctx, K, r):
+        M = K.shape[0]
+        Mpad = ops.padded(M)
+        dev = K.device
+        jitter = 0.0
+        ones = torch.ones(M, dtype=torch.float64, device=dev)
+        for attempt in range(7):
+            buf = torch.eye(Mpad, dtype=torch.float64, device=dev)
+            buf[:M, :M] = K.detach()
+            try:
+                L, dinv = ops.potrf_(buf, M, ones if jitter > 0 else None, jitter)
+                break
+            except NotPositiveDefiniteError:
+                if attempt == 6:
+                    raise
+                jitter = 1e-8 if jitter == 0.0 else jitter * 10
+        Linv = ops.trtri(L, dinv)
+        rp = torch.zeros(Mpad, 2, dtype=torch.float64, device=dev)
+        rp[:M, 0] = r.detach()
+        z = ops.trmm_lower(Linv, rp)
+        alpha = ops.trmm_lower(Linv, z.contiguous(), trans=True)[:M, 0].contiguous()
+        quad = (z[:M, 0] * z[:M, 0]).sum()
+        logdet = 2.0 * torch.log(torch.diagonal(L)[:M]).sum()
+        if Mpad >= 2048 and Mpad <= ops.oz_max_npad():
+            Kinv = ops.oz_gemm_tn(Linv, Linv, lower=True)
+        else:
+            Kinv = ops.gemm(Linv, Linv, transa=True)
+        ctx.save_for_backward(alpha, Kinv[:M, :M])
+        return -0.5 * (quad + logdet + M * math.log(2 * math.pi))
+
+    @staticmethod
+    def backward(ctx, g):
+        alpha, Kinv = ctx.saved_tensors
+        gK = 0.5 * g * (torch.outer(alpha, alpha) - Kinv)
+        return gK, -g * alpha
+
+
+def dense_log_marginal(K, r):
+    """log N(r; 0, K), float64 CUDA tensors, differentiable w.r.t. K and r."""
+    _need_cuda(K, r)
+    return _DenseLogMarginal.apply(K, r)

@@ -32,14 +32,15 @@ from oracle import gpytorch_shim  # noqa: E402
 
 gpytorch_shim.install()
 
-from bayes_cbf.control_affine_model import ControlAffineRegressor, ControlAffineExactGP  # noqa: E402
+from bayes_cbf.control_affine_model import (ControlAffineRegressor, ControlAffineExactGP,  # noqa: E402
+                                            ControlAffineRegressorVector)
 import gpytorch  # noqa: E402  (the shim)
 
 OUT = os.path.join(ROOT, 'tests', 'golden')
 np64 = lambda t: t.detach().cpu().double().numpy().copy()      # copy: .numpy() aliases the (later updated) parameter
 
 
-def case_fit(name, n, m, N, seed, iters, rank=None, prior=None, lr=0.1):
+def case_fit(name, n, m, N, seed, iters, rank=None, prior=None, lr=0.1, vector=False):
     torch.set_default_dtype(torch.float64)
     gen = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
@@ -49,7 +50,7 @@ def case_fit(name, n, m, N, seed, iters, rank=None, prior=None, lr=0.1):
     Xdot = torch.sin(X @ Wt) + (torch.cos(X) * U[:, :1]) + 0.05 * torch.randn(N, n, generator=gen)
     mc = partial(ControlAffineExactGP, rank=rank, gamma_length_scale_prior=prior) if (rank is not None or prior) \
         else ControlAffineExactGP
-    reg = ControlAffineRegressor(n, m, device='cpu', model_class=mc)
+    reg = ControlAffineRegressorVector(n, m, device='cpu') if vector else ControlAffineRegressor(n, m, device='cpu', model_class=mc)
     reg.model.double()
     with torch.no_grad():                                  # non-trivial, reproducible start
         for _, prm in reg.model.named_parameters():
@@ -86,10 +87,15 @@ def case_fit(name, n, m, N, seed, iters, rank=None, prior=None, lr=0.1):
         out['final/' + pname] = np64(prm)
     mdl = reg.model
     p_, n_ = mdl.matshape
-    out['final_lengthscale'] = np64(mdl.input_covar.base_kernel.lengthscale.reshape(-1))
     out['final_outputscale'] = np64(mdl.input_covar.outputscale.reshape(()))
-    out['final_A'] = np64(mdl.task_covar.U.covar_matrix.evaluate())
-    out['final_B'] = np64(mdl.task_covar.V.covar_matrix.evaluate())
+    if vector:                                             # CoGP comparator: scalar RBF lengthscale + linear kernel, one Sigma
+        out['final_lengthscale'] = np64(mdl.input_covar.base_kernel.kernels[0].lengthscale.reshape(-1))
+        out['final_linear_variance'] = np64(mdl.input_covar.base_kernel.kernels[1].variance.reshape(()))
+        out['final_Sigma'] = np64(mdl.task_covar.covar_matrix.evaluate())
+    else:
+        out['final_lengthscale'] = np64(mdl.input_covar.base_kernel.lengthscale.reshape(-1))
+        out['final_A'] = np64(mdl.task_covar.U.covar_matrix.evaluate())
+        out['final_B'] = np64(mdl.task_covar.V.covar_matrix.evaluate())
     out['final_C'] = np64(torch.stack([bm.constant.reshape(()) for bm in mdl.mean_module.base_means]).reshape(p_, n_))
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
     print('wrote', name, 'loss %.6f -> %.6f' % (losses[0], losses[-1]))
@@ -98,3 +104,4 @@ def case_fit(name, n, m, N, seed, iters, rank=None, prior=None, lr=0.1):
 if __name__ == '__main__':
     case_fit('ref_fit_unicycle_f64', n=3, m=2, N=40, seed=41, iters=20)
     case_fit('ref_fit_pendulum_rank1_prior_f64', n=2, m=1, N=36, seed=42, iters=50, rank=1, prior=(1e-3, 1e-3))
+    case_fit('ref_fit_pendulum_cogp_vector_f64', n=2, m=1, N=30, seed=43, iters=25, vector=True)

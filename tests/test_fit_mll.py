@@ -109,6 +109,39 @@ def test_fit_trajectory_against_the_reference(case, dev):
     assert abs(s - float(d['final_outputscale'])) < 1e-6
 
 
+def test_cogp_fit_trajectory_against_the_reference(dev):
+    """ControlAffineRegressorVector.fit (the CoGP comparator the reference's speed test fits for 50 iterations before
+    timing, pendulum.py:1366): dense (N n)-dimensional log marginal on the CUDA Cholesky / inverse, covariance from
+    HetergeneousCoregionalizationKernel — against the reference's own fit of the same class over the dense stand-in."""
+    from bayesian_cbf_b200.control_affine_model import ControlAffineRegressorVector
+    from tests.golden_util import T, load
+    d = load('ref_fit_pendulum_cogp_vector_f64')
+    n, m, iters = int(d['n']), int(d['m']), int(d['iters'])
+    reg = ControlAffineRegressorVector(n, m, device=dev)
+    reg.model.double()
+    names = dict(reg.model.named_parameters())
+    assert set(names) == {k[len('init/'):] for k in d.files if k.startswith('init/')}
+    with torch.no_grad():
+        for k, prm in names.items():
+            prm.copy_(T(d['init/' + k]).reshape(prm.shape).to(dev))
+    reg.set_fit_noise_source(list(d['noise']))
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        reg.fit(T(d['X']), T(d['U']), T(d['Xdot']), training_iter=iters, lr=float(d['lr']))
+    finally:
+        torch.set_default_dtype(old)
+    losses = torch.stack(reg.fit_losses).cpu().numpy()
+    assert np.abs(losses - d['loss']).max() < 1e-7 * max(1.0, np.abs(d['loss']).max()), np.abs(losses - d['loss'])
+    for k, prm in names.items():
+        want = d['final/' + k].reshape(prm.shape)
+        assert np.abs(prm.detach().cpu().numpy() - want).max() < 1e-6 * max(1.0, np.abs(want).max()), k
+    assert np.abs(reg._sigma64().cpu().numpy() - d['final_Sigma']).max() < 1e-6 * np.abs(d['final_Sigma']).max()
+    # the fitted comparator predicts through the same class API as before
+    mean, var = reg.custom_predict(T(d['X'])[:3].to(dev), T(d['U'])[:3].to(dev))
+    assert mean.shape == (3, n) and torch.isfinite(mean).all() and torch.isfinite(var).all()
+
+
 def test_fit_lowers_the_loss_and_predicts(dev):
     from bayesian_cbf_b200.control_affine_model import ControlAffineRegressorExact
     torch.manual_seed(0)
