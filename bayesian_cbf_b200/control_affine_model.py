@@ -286,14 +286,20 @@ class ControlAffineRegressor(DynamicsModel):
         return self.model.covar_module.task_covar_module.V.covar_matrix.evaluate()
 
     def _hyper64(self):
-        """(lengthscale (n,), outputscale float, A, B, C (p,n)) detached, float64, on the device."""
+        """(lengthscale (n,), outputscale float, A, B, C (p,n)) detached, float64, on the device.  Cached until a
+        parameter changes (in-place updates bump `_version`; re-assignment changes the object): the constrained values
+        cost ~15 tiny launches and one device->host read (the outputscale), which used to be paid on every predict."""
         m = self.model
-        ls = m.input_covar.base_kernel.lengthscale.detach().reshape(-1).double().expand(self.x_dim).contiguous()
-        s = float(m.input_covar.outputscale.detach())
-        A = self._A_mat().detach().double().contiguous()
-        B = self._B_mat().detach().double().contiguous()
-        C = m.mean_module.constants().detach().double().contiguous()
-        return ls, s, A, B, C
+        key = tuple((id(p), p._version, p.dtype, p.device) for p in m.parameters())
+        hc = getattr(self, '_hyper_cache', None)
+        if hc is None or hc[0] != key:
+            ls = m.input_covar.base_kernel.lengthscale.detach().reshape(-1).double().expand(self.x_dim).contiguous()
+            s = float(m.input_covar.outputscale.detach())
+            A = self._A_mat().detach().double().contiguous()
+            B = self._B_mat().detach().double().contiguous()
+            C = m.mean_module.constants().detach().double().contiguous()
+            self._hyper_cache = hc = (key, (ls, s, A, B, C))
+        return hc[1]
 
     def set_hyperparameters(self, lengthscale=None, outputscale=None, A=None, B=None, C=None):
         """Set the constrained hyper-parameters directly (lengthscale (n,), outputscale, A (n,n), B (p,p), C (p,n)).

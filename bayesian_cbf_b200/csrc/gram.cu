@@ -19,8 +19,10 @@ struct GramParams {
   const double* X2;  // cols (c, n)
   const double* UH;   // rows: (a, p) or null
   const double* UH2;  // cols: (c, p) or null (train mode: == UH)
-  double inv_ls[kMaxN];
-  double Bm[kMaxP * kMaxP];
+  double inv_ls[kMaxN];       // 1 / lengthscale, filled on the host when the caller's lengthscale lives in host memory
+  double Bm[kMaxP * kMaxP];   // B, likewise
+  const double* ls_dev;       // non-null: lengthscale (n) in DEVICE memory, read by the kernel itself (no host fetch,
+  const double* B_dev;        // no stream synchronisation: the torch-tensor call path); same for B (p, p)
   double scale;
   int a, c, n, p;
   double* out;
@@ -29,6 +31,20 @@ struct GramParams {
   int pad_identity;        // train mode: identity on the pad diagonal
   int vec_ok;              // 16-byte stores allowed (even ld, aligned base)
 };
+
+// Every kernel starts by staging 1 / lengthscale and B in shared memory, from the parameter block or from device memory.
+__device__ __forceinline__ void load_hyper(const GramParams& P, double* inv_ls, double* Bm) {
+  const int t = threadIdx.x;
+  if (t < kMaxN) inv_ls[t] = t < P.n ? (P.ls_dev ? 1.0 / P.ls_dev[t] : P.inv_ls[t]) : 0.0;
+  if (t >= 32 && t < 32 + kMaxP * kMaxP) {
+    const int e = t - 32;
+    Bm[e] = e < P.p * P.p ? (P.B_dev ? P.B_dev[e] : P.Bm[e]) : 0.0;
+  }
+  __syncthreads();
+}
+#define BCBF_LOAD_HYPER(P)                                   \
+  __shared__ double h_inv_ls[kMaxN], h_Bm[kMaxP * kMaxP];    \
+  load_hyper(P, h_inv_ls, h_Bm)
 
 // ---- one Gram entry; the ONE definition every kernel that needs Kb[i,j] uses, so that the train Gram, the compensated
 // residual (gram_resid_kernel) and the ensembles see bit-identical values.  Every operation is spelled out (no
@@ -59,6 +75,7 @@ __device__ __forceinline__ double ub_entry(const double* __restrict__ g, const d
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(256) gram_kernel(GramParams P) {
+  BCBF_LOAD_HYPER(P);
   __shared__ double xr[kGT][kMaxN + 1], xc[kGT][kMaxN + 1];
   __shared__ double gr[kGT][kMaxP], uc[kGT][kMaxP];
   const int tid = threadIdx.x;
@@ -66,13 +83,13 @@ __global__ void __launch_bounds__(256) gram_kernel(GramParams P) {
   const int n = P.n, p = P.p;
   for (int idx = tid; idx < kGT * n; idx += 256) {
     int r = idx / n, d = idx % n;
-    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], P.inv_ls[d]) : 0.0;
-    xc[r][d] = (c0 + r < P.c) ? __dmul_rn(P.X2[(long long)(c0 + r) * n + d], P.inv_ls[d]) : 0.0;
+    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], h_inv_ls[d]) : 0.0;
+    xc[r][d] = (c0 + r < P.c) ? __dmul_rn(P.X2[(long long)(c0 + r) * n + d], h_inv_ls[d]) : 0.0;
   }
   if (TRAIN) {
     for (int idx = tid; idx < kGT * p; idx += 256) {
       int r = idx / p, q = idx % p;
-      gr[r][q] = (r0 + r < P.a) ? g_entry(P.UH + (long long)(r0 + r) * p, P.Bm, p, q) : 0.0;
+      gr[r][q] = (r0 + r < P.a) ? g_entry(P.UH + (long long)(r0 + r) * p, h_Bm, p, q) : 0.0;
       uc[r][q] = (c0 + r < P.c) ? P.UH2[(long long)(c0 + r) * p + q] : 0.0;
     }
   }
@@ -122,6 +139,7 @@ __device__ __forceinline__ void lower_tile(int t, int& bi, int& bj) {
 // part of a full matrix mirrors it (entry(j, i) evaluated as rbf(j,i) * (g_j . uh_i), the same bits as its mirror image).
 template <int NN, int PP, bool LOWER>
 __global__ void __launch_bounds__(256) gram_train_kernel(GramParams P) {
+  BCBF_LOAD_HYPER(P);
   __shared__ double xr[kGT][kMaxN + 1], xc[kGT][kMaxN + 1];
   __shared__ double gr[kGT][kMaxP + 1], ur[kGT][kMaxP + 1], gc[kGT][kMaxP + 1], uc[kGT][kMaxP + 1];
   const int tid = threadIdx.x;
@@ -132,15 +150,15 @@ __global__ void __launch_bounds__(256) gram_train_kernel(GramParams P) {
   const int n = NN > 0 ? NN : P.n, p = PP > 0 ? PP : P.p;
   for (int idx = tid; idx < kGT * n; idx += 256) {
     int r = idx / n, d = idx % n;
-    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], P.inv_ls[d]) : 0.0;
-    xc[r][d] = (c0 + r < P.a) ? __dmul_rn(P.X1[(long long)(c0 + r) * n + d], P.inv_ls[d]) : 0.0;
+    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], h_inv_ls[d]) : 0.0;
+    xc[r][d] = (c0 + r < P.a) ? __dmul_rn(P.X1[(long long)(c0 + r) * n + d], h_inv_ls[d]) : 0.0;
   }
   for (int idx = tid; idx < kGT * p; idx += 256) {
     int r = idx / p, q = idx % p;
     const bool vr = r0 + r < P.a, vc = c0 + r < P.a;
-    gr[r][q] = vr ? g_entry(P.UH + (long long)(r0 + r) * p, P.Bm, p, q) : 0.0;
+    gr[r][q] = vr ? g_entry(P.UH + (long long)(r0 + r) * p, h_Bm, p, q) : 0.0;
     ur[r][q] = vr ? P.UH[(long long)(r0 + r) * p + q] : 0.0;
-    gc[r][q] = vc ? g_entry(P.UH + (long long)(c0 + r) * p, P.Bm, p, q) : 0.0;
+    gc[r][q] = vc ? g_entry(P.UH + (long long)(c0 + r) * p, h_Bm, p, q) : 0.0;
     uc[r][q] = vc ? P.UH[(long long)(c0 + r) * p + q] : 0.0;
   }
   __syncthreads();
@@ -219,6 +237,7 @@ template <int NN, int PP>
 __global__ void __launch_bounds__(256) gram_resid_kernel(GramParams P, const double* __restrict__ jitter, double jscale,
                                                          const double* __restrict__ alpha, int lda, int cfirst, int nc,
                                                          int tiles_per_split, double* __restrict__ partial) {
+  BCBF_LOAD_HYPER(P);
   __shared__ double xr[kGT][kMaxN + 1], xc[kGT][kMaxN + 1];
   __shared__ double gr[kGT][kMaxP + 1], ur[kGT][kMaxP + 1], gc[kGT][kMaxP + 1], uc[kGT][kMaxP + 1];
   __shared__ double al[kGT][kResMaxC];
@@ -229,12 +248,12 @@ __global__ void __launch_bounds__(256) gram_resid_kernel(GramParams P, const dou
   const int t0 = blockIdx.y * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
   for (int idx = tid; idx < kGT * n; idx += 256) {
     int r = idx / n, d = idx % n;
-    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], P.inv_ls[d]) : 0.0;
+    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], h_inv_ls[d]) : 0.0;
   }
   for (int idx = tid; idx < kGT * p; idx += 256) {
     int r = idx / p, q = idx % p;
     const bool vr = r0 + r < P.a;
-    gr[r][q] = vr ? g_entry(P.UH + (long long)(r0 + r) * p, P.Bm, p, q) : 0.0;
+    gr[r][q] = vr ? g_entry(P.UH + (long long)(r0 + r) * p, h_Bm, p, q) : 0.0;
     ur[r][q] = vr ? P.UH[(long long)(r0 + r) * p + q] : 0.0;
   }
   double hi[4][kResMaxC], lo[4][kResMaxC];
@@ -247,12 +266,12 @@ __global__ void __launch_bounds__(256) gram_resid_kernel(GramParams P, const dou
     __syncthreads();
     for (int idx = tid; idx < kGT * n; idx += 256) {
       int r = idx / n, d = idx % n;
-      xc[r][d] = (c0 + r < P.a) ? __dmul_rn(P.X1[(long long)(c0 + r) * n + d], P.inv_ls[d]) : 0.0;
+      xc[r][d] = (c0 + r < P.a) ? __dmul_rn(P.X1[(long long)(c0 + r) * n + d], h_inv_ls[d]) : 0.0;
     }
     for (int idx = tid; idx < kGT * p; idx += 256) {
       int r = idx / p, q = idx % p;
       const bool vc = c0 + r < P.a;
-      gc[r][q] = vc ? g_entry(P.UH + (long long)(c0 + r) * p, P.Bm, p, q) : 0.0;
+      gc[r][q] = vc ? g_entry(P.UH + (long long)(c0 + r) * p, h_Bm, p, q) : 0.0;
       uc[r][q] = vc ? P.UH[(long long)(c0 + r) * p + q] : 0.0;
     }
     for (int idx = tid; idx < kGT * kResMaxC; idx += 256) {
@@ -337,25 +356,27 @@ __global__ void gram_resid_finalize_kernel(const double* __restrict__ partial, i
 // evaluated (the plug-in contract of HetergeneousMatrixVariateKernel: any data_covar_module).  One thread per entry.
 __global__ void ca_weight_kernel(const double* __restrict__ K, int ldk, const double* __restrict__ UH1,
                                  const double* __restrict__ UH2, GramParams P, double* __restrict__ out, int ldo) {
+  BCBF_LOAD_HYPER(P);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)P.a * P.c) return;
   const int i = (int)(idx / P.c), j = (int)(idx % P.c), p = P.p;
   double s = 0.0;
-  for (int q = 0; q < p; ++q) s = __fma_rn(g_entry(UH1 + (long long)i * p, P.Bm, p, q), UH2[(long long)j * p + q], s);
+  for (int q = 0; q < p; ++q) s = __fma_rn(g_entry(UH1 + (long long)i * p, h_Bm, p, q), UH2[(long long)j * p + q], s);
   out[(long long)i * ldo + j] = __dmul_rn(K[(long long)i * ldk + j], s);
 }
 
 // k, dk/dx1 (a,c,n), d2k/dx1dx2 (a,c,n,n); one thread per (i,j) pair — small-b API path only.
 __global__ void rbf_blocks_kernel(GramParams P, double* K, double* dK, double* d2K) {
+  BCBF_LOAD_HYPER(P);
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)P.a * P.c) return;
   const int i = (int)(idx / P.c), j = (int)(idx % P.c), n = P.n;
   double w[kMaxN];  // (x1 - x2) / l^2
   double d2 = 0.0;
   for (int d = 0; d < n; ++d) {
-    double df = (P.X1[(long long)i * n + d] - P.X2[(long long)j * n + d]) * P.inv_ls[d];
+    double df = (P.X1[(long long)i * n + d] - P.X2[(long long)j * n + d]) * h_inv_ls[d];
     d2 = fma(df, df, d2);
-    w[d] = df * P.inv_ls[d];
+    w[d] = df * h_inv_ls[d];
   }
   const double k = P.scale * exp(-0.5 * d2);
   if (K) K[idx] = k;
@@ -364,7 +385,7 @@ __global__ void rbf_blocks_kernel(GramParams P, double* K, double* dK, double* d
   if (d2K)
     for (int d = 0; d < n; ++d)
       for (int e = 0; e < n; ++e)
-        d2K[(idx * n + d) * n + e] = ((d == e ? P.inv_ls[d] * P.inv_ls[d] : 0.0) - w[d] * w[e]) * k;
+        d2K[(idx * n + d) * n + e] = ((d == e ? h_inv_ls[d] * h_inv_ls[d] : 0.0) - w[d] * w[e]) * k;
 }
 
 
@@ -381,6 +402,7 @@ __global__ void __launch_bounds__(256) gram_backward_kernel(GramParams P, const 
                                                             const double* __restrict__ alphaAi,
                                                             const double* __restrict__ alpha, int lda, int nout_dim,
                                                             double* __restrict__ partial) {
+  BCBF_LOAD_HYPER(P);
   __shared__ double xr[kGT][kMaxN + 1], xc[kGT][kMaxN + 1];
   __shared__ double ur[kGT][kMaxP], uc[kGT][kMaxP], gr[kGT][kMaxP];
   __shared__ double ar[kGT][kMaxN], ac[kGT][kMaxN];
@@ -390,8 +412,8 @@ __global__ void __launch_bounds__(256) gram_backward_kernel(GramParams P, const 
   const int n = P.n, p = P.p, nd = nout_dim;
   for (int idx = tid; idx < kGT * n; idx += 256) {
     int r = idx / n, d = idx % n;
-    xr[r][d] = (r0 + r < P.a) ? P.X1[(long long)(r0 + r) * n + d] * P.inv_ls[d] : 0.0;
-    xc[r][d] = (c0 + r < P.c) ? P.X1[(long long)(c0 + r) * n + d] * P.inv_ls[d] : 0.0;
+    xr[r][d] = (r0 + r < P.a) ? P.X1[(long long)(r0 + r) * n + d] * h_inv_ls[d] : 0.0;
+    xc[r][d] = (c0 + r < P.c) ? P.X1[(long long)(c0 + r) * n + d] * h_inv_ls[d] : 0.0;
   }
   for (int idx = tid; idx < kGT * nd; idx += 256) {
     int r = idx / nd, d = idx % nd;
@@ -403,7 +425,7 @@ __global__ void __launch_bounds__(256) gram_backward_kernel(GramParams P, const 
     double g = 0.0, u = 0.0;
     if (r0 + r < P.a) {
       u = P.UH[(long long)(r0 + r) * p + q];
-      for (int t = 0; t < p; ++t) g += P.UH[(long long)(r0 + r) * p + t] * P.Bm[t * p + q];
+      for (int t = 0; t < p; ++t) g += P.UH[(long long)(r0 + r) * p + t] * h_Bm[t * p + q];
     }
     ur[r][q] = u;
     gr[r][q] = g;
@@ -435,7 +457,7 @@ __global__ void __launch_bounds__(256) gram_backward_kernel(GramParams P, const 
       const double ge = gbar * e;
       acc[0] += ge * S;                                       // d/d outputscale
       const double gk = ge * S * P.scale;                     // Gbar * Kb
-      for (int d = 0; d < n; ++d) acc[1 + d] += gk * dd[d] * P.inv_ls[d];   // (dx/l)^2 / l
+      for (int d = 0; d < n; ++d) acc[1 + d] += gk * dd[d] * h_inv_ls[d];   // (dx/l)^2 / l
       const double gs = ge * P.scale;
       for (int a = 0; a < p; ++a)
         for (int b = 0; b < p; ++b) acc[1 + kMaxN + a * kMaxP + b] += gs * ur[rl][a] * uc[cl][b];
@@ -465,26 +487,27 @@ __global__ void gram_backward_finalize_kernel(const double* __restrict__ partial
   if (lane == 0) out[t] = v;
 }
 
-// Small parameter blocks (lengthscale, B) may live on the host or on the device.  Host pointers are read directly;
-// device pointers are fetched on the stream (one short synchronisation — the torch-tensor call path).
-static int fetch_small(double* dst, const double* src, int count, cudaStream_t stream) {
+// Small parameter blocks (lengthscale, B) may live on the host or on the device.  Host pointers are copied into the
+// kernel's parameter block; device pointers are handed to the kernel, which reads them itself — no copy back, no stream
+// synchronisation on the torch-tensor call path (round 1 fetched them with a D2H copy + sync per call: the dominant cost of
+// the small-N regimes).
+static int resolve_small(double* dst, const double** dev_out, const double* src, int count) {
   cudaPointerAttributes attr{};
   cudaError_t e = cudaPointerGetAttributes(&attr, src);
   if (e != cudaSuccess) { cudaGetLastError(); attr.type = cudaMemoryTypeUnregistered; }
   if (attr.type == cudaMemoryTypeUnregistered || attr.type == cudaMemoryTypeHost) {
     for (int i = 0; i < count; ++i) dst[i] = src[i];
-    return BCBF_OK;
+    *dev_out = nullptr;
+  } else {
+    *dev_out = src;
   }
-  e = cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyDeviceToHost, stream);
-  if (e != cudaSuccess) return cuda_fail(e, "copy hyper-parameters", __FILE__, __LINE__);
-  e = cudaStreamSynchronize(stream);
-  if (e != cudaSuccess) return cuda_fail(e, "sync hyper-parameters", __FILE__, __LINE__);
   return BCBF_OK;
 }
 
 static int fill_common(GramParams& P, const double* lengthscale, double outputscale, int n, cudaStream_t stream) {
-  double ls[kMaxN];
-  int rc = fetch_small(ls, lengthscale, n, stream);
+  (void)stream;
+  double ls[kMaxN] = {1, 1, 1, 1, 1, 1, 1, 1};
+  int rc = resolve_small(ls, &P.ls_dev, lengthscale, n);
   if (rc != BCBF_OK) return rc;
   for (int d = 0; d < n; ++d) P.inv_ls[d] = 1.0 / ls[d];
   P.scale = outputscale;
@@ -517,7 +540,7 @@ static int gram_train_impl(const double* X, const double* UH, const double* Bmat
   GramParams P{};
   int rc = fill_common(P, lengthscale, outputscale, n, stream);
   if (rc != BCBF_OK) return rc;
-  if ((rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
+  if ((rc = resolve_small(P.Bm, &P.B_dev, Bmat, p * p)) != BCBF_OK) return rc;
   P.X1 = X; P.X2 = X; P.UH = UH; P.UH2 = UH; P.a = N; P.c = N; P.p = p;
   P.out = Kb; P.ld = ld; P.rows_out = Npad; P.cols_out = Npad; P.pad_identity = 1; P.vec_ok = 1;
   const int nt = Npad / kGT;
@@ -573,7 +596,7 @@ extern "C" int bcbf_gram_resid(const double* X, const double* UH, const double* 
   GramParams P{};
   int rc = fill_common(P, lengthscale, outputscale, n, stream);
   if (rc != BCBF_OK) return rc;
-  if ((rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
+  if ((rc = resolve_small(P.Bm, &P.B_dev, Bmat, p * p)) != BCBF_OK) return rc;
   P.X1 = X; P.X2 = X; P.UH = UH; P.UH2 = UH; P.a = N; P.c = N; P.p = p;
   int S, tps;
   resid_splits(N, &S, &tps);
@@ -621,7 +644,7 @@ extern "C" int bcbf_gram_ca(const double* X1, const double* UH1, int a, const do
   GramParams P{};
   int rc = fill_common(P, lengthscale, outputscale, n, stream);
   if (rc != BCBF_OK) return rc;
-  if (UH1 && (rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
+  if (UH1 && (rc = resolve_small(P.Bm, &P.B_dev, Bmat, p * p)) != BCBF_OK) return rc;
   P.X1 = X1; P.X2 = X2; P.UH = UH1; P.UH2 = UH2; P.a = a; P.c = c; P.p = UH1 ? p : 0;
   P.out = out; P.ld = ld; P.rows_out = a; P.cols_out = c; P.pad_identity = 0;
   dim3 grid(ceil_div(c, kGT), ceil_div(a, kGT));
@@ -640,7 +663,7 @@ extern "C" int bcbf_ca_weight(const double* K, int ldk, const double* UH1, int a
   BCBF_REQUIRE(a >= 1 && c >= 1 && p >= 1 && p <= kMaxP && ldk >= c && ldo >= c, "bcbf_ca_weight: a=%d c=%d p=%d ldk=%d ldo=%d",
                a, c, p, ldk, ldo);
   GramParams P{};
-  int rc = fetch_small(P.Bm, Bmat, p * p, stream);
+  int rc = resolve_small(P.Bm, &P.B_dev, Bmat, p * p);
   if (rc != BCBF_OK) return rc;
   P.a = a; P.c = c; P.p = p;
   ca_weight_kernel<<<ceil_div((long long)a * c, 256), 256, 0, stream>>>(K, ldk, UH1, UH2, P, out, ldo);
@@ -676,7 +699,7 @@ extern "C" int bcbf_gram_train_backward(const double* X, const double* UH, const
   GramParams P{};
   int rc = fill_common(P, lengthscale, outputscale, n, stream);
   if (rc != BCBF_OK) return rc;
-  if ((rc = fetch_small(P.Bm, Bmat, p * p, stream)) != BCBF_OK) return rc;
+  if ((rc = resolve_small(P.Bm, &P.B_dev, Bmat, p * p)) != BCBF_OK) return rc;
   P.X1 = X; P.X2 = X; P.UH = UH; P.UH2 = UH; P.a = N; P.c = N; P.p = p;
   dim3 grid(ceil_div(N, kGT), ceil_div(N, kGT));
   const long long nblocks = (long long)grid.x * grid.y;

@@ -30,8 +30,12 @@ class _MVGPLogMarginal(torch.autograd.Function):
         p = UH.shape[1]
         nout = Xdot.shape[1]
         dev = X.device
-        ls_d, B_d = ls.detach().contiguous(), B.detach().contiguous()
-        s_f = float(s)
+        # the outputscale is folded into B (Kb = k1 o (UH (s B) UH^T) with a unit-scale kernel k1): every hyper-parameter
+        # stays on the device and the Gram kernels read them there — no device->host read in the iteration
+        ls_d = ls.detach().contiguous()
+        s_d = s.detach().reshape(())
+        B_d = (s_d * B.detach()).contiguous()
+        s_f = 1.0
         Y = (Xdot - UH @ C.detach()).contiguous()
         ones = torch.ones(N, dtype=torch.float64, device=dev)
         jitter = 0.0
@@ -52,14 +56,16 @@ class _MVGPLogMarginal(torch.autograd.Function):
         z = ops.trmm_lower(Linv, Ypad)                              # L^-1 Y
         alpha = ops.trmm_lower(Linv, z.contiguous(), trans=True)    # Kb^-1 Y
         alpha = alpha[:N].contiguous()
-        # n x n glue: factor A on the host (a 2x2 / 3x3 matrix; avoids dragging a dense-solver library into the loop)
-        A_h = A.detach().cpu()
-        La_h = torch.linalg.cholesky(A_h)
-        Ai = torch.cholesky_inverse(La_h).to(dev)
-        YtA = z[:N].transpose(0, 1) @ z[:N]                          # Y^T Kb^-1 Y  (n x n)
+        # n x n glue on the device (2x2 / 3x3 matrices, elementwise column-by-column factorisation: no library solver, no
+        # host round trip)
+        from .ensemble import _small_cholesky, _small_lower_inverse
+        La = _small_cholesky(A.detach().unsqueeze(0))
+        Lai = _small_lower_inverse(La)[0]
+        Ai = Lai.transpose(0, 1) @ Lai
+        YtA = ops.gemm(z[:N].contiguous(), z[:N].contiguous(), transa=True)   # Y^T Kb^-1 Y  (n x n)
         quad = torch.trace(Ai @ YtA)
         logdetK = 2.0 * torch.log(torch.diagonal(L)[:N]).sum()
-        logdetA = (2.0 * torch.log(torch.diagonal(La_h)).sum()).to(dev)
+        logdetA = 2.0 * torch.log(torch.diagonal(La[0])).sum()
         value = -0.5 * (quad + nout * logdetK + N * logdetA + N * nout * math.log(2 * math.pi))
         # ---- gradients (always needed by fit; computed eagerly) -----------------------------------------------
         if Linv.shape[0] >= 2048 and Linv.shape[0] <= ops.oz_max_npad():
@@ -67,9 +73,13 @@ class _MVGPLogMarginal(torch.autograd.Function):
         else:
             Pinv = ops.gemm(Linv, Linv, transa=True)                 # Kb^-1 = L^-T L^-1  (Npad, Npad)
         alphaAi = (alpha @ Ai).contiguous()
-        g_s, g_ls, g_B = ops.gram_train_backward(X, UH, B_d, ls_d, s_f, Pinv.contiguous(), alphaAi, alpha)
+        g_s1, g_ls, g_Beff = ops.gram_train_backward(X, UH, B_d, ls_d, s_f, Pinv.contiguous(), alphaAi, alpha)
+        # chain rule of the folding B_eff = s B, s_kernel = 1:  d/ds = (d/ds_kernel) / s  (Kb is linear in both),
+        # d/dB = s d/dB_eff
+        g_s = g_s1 / s_d
+        g_B = g_Beff * s_d
         g_A = 0.5 * (Ai @ YtA @ Ai - N * Ai)
-        g_C = UH.transpose(0, 1) @ alphaAi
+        g_C = ops.gemm(UH, alphaAi, transa=True)
         ctx.save_for_backward(g_ls.clone(), g_s.clone(), g_A, g_B.clone(), g_C)
         ctx.jitter = jitter
         return value
