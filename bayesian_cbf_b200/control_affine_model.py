@@ -926,7 +926,8 @@ class ControlAffineRegressorVector(ControlAffineRegressor):
         optimizer = torch.optim.Adam(model.parameters(), lr=lr)
         scheduler = torch.optim.lr_scheduler.MultiStepLR(
             optimizer, milestones=(torch.tensor([0.3, 0.6, 0.8, 0.90]) * training_iter).tolist())
-        MXU = model.train_inputs[0]
+        MXU = model.train_inputs[0].double()     # the covariance is assembled in float64 whatever the model dtype (the
+        # kernels factorise in float64; float32 round-off of a (N n)^2 matrix would need jitter at the 1e-2 level)
         prior = model.input_covar.base_kernel.kernels[0].lengthscale_prior
         self.fit_losses = []
         for i in range(training_iter):          # the loop of the base class (reference :310-334) on the dense density
@@ -937,7 +938,7 @@ class ControlAffineRegressorVector(ControlAffineRegressor):
                 noise = torch.rand(XdotTrain.numel(), dtype=XdotTrain.dtype).to(self.device)
             y = (XdotTrain.reshape(-1) * (1 + 1e-6 * noise)).double()
             out = model(MXU)
-            logp = dense_log_marginal(out.covariance_matrix.double(), y - out.mean.double())
+            logp = dense_log_marginal(out.covariance_matrix, y - out.mean.double())
             if prior is not None:
                 logp = logp + prior.log_prob(model.input_covar.base_kernel.kernels[0].lengthscale.double())
             loss = -logp / y.numel()

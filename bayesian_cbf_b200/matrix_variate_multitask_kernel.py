@@ -203,24 +203,26 @@ class HetergeneousCoregionalizationKernel(MatrixVariateKernel):
         test_size = (M1s.size(-1) - end) * self.task_covar_module.covar_matrix.shape[-1]
         return (end * X1.shape[-1] + test_size) / M1s.size(-1)
 
-    def _sigma4(self):
+    def _sigma4(self, dtype):
+        """Sigma in the dtype the covariance is assembled in (the inputs' dtype: a float32 model evaluated on float64
+        inputs — what the comparator's fit does — gets a float64 covariance of its float32 parameters)."""
         _, n, p = self.decoder.sizes
-        Sigma = _dense(self.task_covar_module.covar_matrix)
+        Sigma = _dense(self.task_covar_module.covar_matrix).to(dtype)
         return Sigma, Sigma.reshape(p, n, p, n), n, p
 
     def kernel1(self, Kxx, UH1, UH2):
         """(H1 (x) I)(K (x) Sigma)(H2^T (x) I): entry [(i,r),(j,s)] = K_ij sum_qq' uh1_i[q] Sigma[(q,r),(q',s)] uh2_j[q']."""
-        _, S4, n, _ = self._sigma4()
+        _, S4, n, _ = self._sigma4(Kxx.dtype)
         uSu = torch.einsum('iq,qrts,jt->irjs', UH1.to(S4.dtype), S4, UH2.to(S4.dtype))
         return (Kxx.unsqueeze(1).unsqueeze(-1) * uSu).reshape(UH1.shape[0] * n, UH2.shape[0] * n)
 
     def kernel2(self, Kxx):
-        Sigma, _, _, _ = self._sigma4()
+        Sigma, _, _, _ = self._sigma4(Kxx.dtype)
         return torch_kron(Kxx, Sigma, batch_dims=0)
 
     def correlation_kernel_12(self, Kxx, UH1):
         """(H1 (x) I)(K12 (x) Sigma): entry [(i,r),(j,q',s)] = K_ij sum_q uh1_i[q] Sigma[(q,r),(q',s)]."""
-        _, S4, n, p = self._sigma4()
+        _, S4, n, p = self._sigma4(Kxx.dtype)
         uS = torch.einsum('iq,qrts->irts', UH1.to(S4.dtype), S4)                       # (N1, n, p, n)
         return (Kxx.reshape(Kxx.shape[0], 1, Kxx.shape[1], 1, 1) * uS.unsqueeze(2)).reshape(
             UH1.shape[0] * n, Kxx.shape[1] * p * n)
@@ -244,7 +246,7 @@ class HetergeneousCoregionalizationKernel(MatrixVariateKernel):
             raise RuntimeError("HetergeneousCoregionalizationKernel does not accept the last_dim_is_batch argument.")
         M1, X1, U1 = self.decoder.decode(mxu1)
         M2, X2, U2 = self.decoder.decode(mxu2)
-        covar_x = _dense(self.data_covar_module.forward(X1, X2, **params)).to(mxu1.device)
+        covar_x = _dense(self.data_covar_module.forward(X1, X2, **params)).to(device=mxu1.device, dtype=mxu1.dtype)
         for name, value in self.data_covar_module.named_parameters():
             assert not torch.isnan(value).any()
         res = self.mask_dependent_covar(M1[..., 0], U1, M2[..., 0], U2, covar_x)
