@@ -97,6 +97,9 @@ _SIGNATURES = {
     'bcbf_model_state': (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)] + [POINTER(c_void_p)] * 6),
     'bcbf_model_alloc_state': (c_int, [c_void_p, POINTER(Hyper), c_int]),
     'bcbf_model_adopt': (c_int, [c_void_p]),
+    'bcbf_packed_lower_elems': (c_longlong, [c_int]),
+    'bcbf_pack_lower': (c_int, [_P, c_int, c_int, _P, _P]),
+    'bcbf_unpack_lower': (c_int, [_P, c_int, _P, c_int, _P]),
     'bcbf_model_fit_timing': (c_int, [c_void_p, POINTER(c_double * 5)]),
     'bcbf_oz_factor_bytes': (c_longlong, [c_int]),
     'bcbf_oz_max_npad': (c_int, []),

@@ -233,6 +233,26 @@ __global__ void tri_mv_t_finalize_kernel(const double* __restrict__ partial, int
   y[(long long)j * ldx + c] = (y0 ? beta * y0[(long long)j * ldx + c] : 0.0) + alpha * s;
 }
 
+// ---- packed lower triangle of a factor-sized matrix (multi-GPU broadcast of L^-1) -----------------------------------------
+// packed layout: block row after block row, block row i = a (128, 128 (i+1)) row-major matrix.  One CTA per 128x128 block
+// of the full matrix: lower blocks are copied, strictly-upper blocks are zeroed on unpack.
+__global__ void __launch_bounds__(256) pack_lower_kernel(const double* __restrict__ M, int ld, double* __restrict__ buf,
+                                                         int unpack, double* __restrict__ Mout) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  const long long off = (long long)kBlk * kBlk * bi * (bi + 1) / 2;      // start of block row bi in the packed buffer
+  const int w = (bi + 1) * kBlk;
+  for (int idx = threadIdx.x; idx < kBlk * kBlk / 2; idx += blockDim.x) {
+    const int r = idx >> 6, c = (idx & 63) * 2;
+    const long long m = (long long)(bi * kBlk + r) * ld + bj * kBlk + c;
+    const long long b = off + (long long)r * w + bj * kBlk + c;
+    if (!unpack) {
+      if (bj <= bi) *reinterpret_cast<double2*>(buf + b) = *reinterpret_cast<const double2*>(M + m);
+    } else {
+      *reinterpret_cast<double2*>(Mout + m) = bj <= bi ? *reinterpret_cast<const double2*>(buf + b) : make_double2(0.0, 0.0);
+    }
+  }
+}
+
 __global__ void build_uh_kernel(const double* __restrict__ U, int Q, int p, double* __restrict__ UH) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Q) return;
@@ -248,6 +268,27 @@ extern "C" const char* bcbf_last_error(void) { return g_err; }
 extern "C" int bcbf_version(void) { return 100; }
 extern "C" unsigned long long bcbf_launch_count(void) { return g_launch_count; }
 extern "C" int bcbf_padded(int N) { return ((N + kBlk - 1) / kBlk) * kBlk; }
+
+extern "C" long long bcbf_packed_lower_elems(int Npad) {
+  const long long nb = Npad / kBlk;
+  return (long long)kBlk * kBlk * nb * (nb + 1) / 2;
+}
+
+extern "C" int bcbf_pack_lower(const double* M, int ld, int Npad, double* buf, void* stream_) {
+  BCBF_REQUIRE(M && buf && Npad > 0 && Npad % kBlk == 0 && ld >= Npad && ld % 2 == 0, "bcbf_pack_lower: Npad=%d ld=%d", Npad, ld);
+  const int nb = Npad / kBlk;
+  pack_lower_kernel<<<dim3(nb, nb), 256, 0, static_cast<cudaStream_t>(stream_)>>>(M, ld, buf, 0, nullptr);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_unpack_lower(const double* buf, int Npad, double* M, int ld, void* stream_) {
+  BCBF_REQUIRE(M && buf && Npad > 0 && Npad % kBlk == 0 && ld >= Npad && ld % 2 == 0, "bcbf_unpack_lower: Npad=%d ld=%d", Npad, ld);
+  const int nb = Npad / kBlk;
+  pack_lower_kernel<<<dim3(nb, nb), 256, 0, static_cast<cudaStream_t>(stream_)>>>(nullptr, ld, const_cast<double*>(buf), 1, M);
+  BCBF_LAUNCH_CHECK();
+  return BCBF_OK;
+}
 
 extern "C" int bcbf_cbc1_terms(const double* Mk, const double* Bk, const double* Amat, const double* grad_h,
                                const double* h, const double* Fbar, double gamma, int n, int p, int Q, double* bfe,

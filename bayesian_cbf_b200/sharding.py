@@ -48,6 +48,11 @@ def pack_lower(M, out=None, block=128):
     Npad = M.shape[0]
     nb = Npad // block
     out = torch.empty(packed_lower_elems(Npad, block), dtype=M.dtype, device=M.device) if out is None else out
+    if M.is_cuda and M.dtype is torch.float64 and block == 128 and M.stride(1) == 1:      # one launch (bcbf_pack_lower)
+        from . import _lib
+        _lib.check(_lib.load().bcbf_pack_lower(M.data_ptr(), M.stride(0), Npad, out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+        return out
     off = 0
     for i in range(nb):
         w = (i + 1) * block
@@ -60,6 +65,11 @@ def unpack_lower(buf, M, block=128):
     """Inverse of pack_lower into a (Npad, Npad) buffer; the strictly-upper blocks are zeroed."""
     Npad = M.shape[0]
     nb = Npad // block
+    if M.is_cuda and M.dtype is torch.float64 and block == 128 and M.stride(1) == 1:
+        from . import _lib
+        _lib.check(_lib.load().bcbf_unpack_lower(buf.data_ptr(), Npad, M.data_ptr(), M.stride(0),
+                                                 torch.cuda.current_stream().cuda_stream))
+        return M
     off = 0
     for i in range(nb):
         w = (i + 1) * block

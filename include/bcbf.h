@@ -380,6 +380,12 @@ int bcbf_model_state(bcbf_model* m, int* N, int* Npad, double** L, double** Linv
                      double** W, double** Xtrain);
 int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int N);
 int bcbf_model_adopt(bcbf_model* m);
+/* The lower-triangular 128-blocks of a factor-sized matrix as one contiguous vector (block row after block row, row i =
+ * a (128, 128 (i+1)) row-major matrix): what is broadcast of L^-1, 4 Npad (Npad + 128) bytes instead of 8 Npad^2.
+ * bcbf_unpack_lower also zeroes the strictly-upper blocks of the destination.                                      */
+long long bcbf_packed_lower_elems(int Npad);
+int bcbf_pack_lower(const double* M, int ld, int Npad, double* buf, void* stream);
+int bcbf_unpack_lower(const double* buf, int Npad, double* M, int ld, void* stream);
 /* Milliseconds spent in the stages of the last bcbf_model_fit (gram, potrf, trtri, alpha, total). */
 int bcbf_model_fit_timing(bcbf_model* m, double out_ms[5]);
 /* Which kernel computes B_k in bcbf_model_query*: 0 = FP64 tensor pipe (DMMA, post_var_kernel), 1 = int8 tensor cores

@@ -369,3 +369,15 @@ def test_ops_reject_wrong_inputs():
     with pytest.raises(RuntimeError, match="libbcbf error -1"):     # bcbf_potrf: Npad must be a multiple of 128
         A = torch.eye(100, dtype=torch.float64, device='cuda')
         ops.potrf_(A, 100, None, 0.0)
+
+
+def test_pack_unpack_lower_on_the_device():
+    """bcbf_pack_lower / bcbf_unpack_lower (the one-collective factor broadcast) against the torch indexing form."""
+    from bayesian_cbf_b200.sharding import pack_lower, packed_lower_elems, unpack_lower
+    g = torch.Generator().manual_seed(0)
+    M = torch.tril(torch.randn(640, 640, generator=g, dtype=torch.float64))
+    buf = pack_lower(M.cuda())
+    assert buf.numel() == packed_lower_elems(640)
+    assert torch.equal(buf.cpu(), pack_lower(M))                       # CPU path: per-block-row strided copies
+    out = torch.full((640, 640), 7.0, dtype=torch.float64, device='cuda')
+    assert torch.equal(unpack_lower(buf, out).cpu(), M)                # strictly-upper blocks zeroed, lower restored
