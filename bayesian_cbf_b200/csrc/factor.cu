@@ -281,6 +281,285 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
   }
 }
 
+// ======================================================================================================================
+// potf2_inv2_kernel (round 2): the same 128x128 factor + inverse, re-organised around what the ncu source view of the kernel
+// above showed (profiles/r02f_potf2_ncu_summary.json): 46 % of its 172 us went to a column-oriented inverse whose k-loops
+// grow to 112 steps while 16..112 of 256 threads have work, 18 % to 7 warps waiting behind the single-warp 16x16 factor +
+// inverse of every panel.
+//   A  factor, 16-wide panels.  Warp 0 owns the diagonal blocks: it applies the pending rank-16 update to the NEXT
+//      diagonal block itself and factorises it (registers, shuffles) WHILE warps 1..7 run the trailing update of the
+//      current panel — the 16-pivot chain is off the other warps' path.  The panel solve is a forward substitution per
+//      row (no inverse of the diagonal block needed), so the 16x16 inverses leave the serial chain:
+//   A' all eight 16x16 diagonal inverses at once, one warp each.
+//   B  inverse by recursive doubling, X21 = -X22 (L21 X11) for blocks of 16, 32, 64: three levels of two register-tiled
+//      products with every thread busy (critical path 224 k-steps instead of 560); column tiles are strided so that the
+//      shared-memory reads of a half-warp fall into distinct banks.
+// Same storage convention (L in the lower triangle of `a`, strictly-lower X transposed into the upper triangle, diagonal of
+// X in xd), same outputs, same failure protocol.
+constexpr int kTS = 65;                      // row stride of the 64 x 64 scratch of phase B
+constexpr int kT2Elems = 64 * kTS;
+
+template <int H>
+__device__ __forceinline__ void inv_level(double* __restrict__ a, const double* __restrict__ xd, double* __restrict__ T,
+                                          int tid) {
+  constexpr int NPR = kBlk / (2 * H);        // pairs at this level
+  constexpr int TT = H / 4;                  // 4x4 tiles per edge; thread tile = rows 4 ti + e, columns tj + TT f
+  for (int t = tid; t < NPR * TT * TT; t += 256) {      // T_p = L21_p X11_p
+    const int pr = t / (TT * TT), tt = t % (TT * TT), ti = tt / TT, tj = tt % TT;
+    const int base = pr * 2 * H;
+    double acc[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+    for (int k = tj; k < H; ++k) {           // X11 is lower triangular: X11[k][c] = 0 for k < c, smallest column is tj
+      double va[4], vb[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) va[e] = a[(base + H + 4 * ti + e) * kPad + base + k];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) vb[f] = inv_get(a, xd, base + k, base + tj + TT * f);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vb[f], acc[e][f]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) T[(pr * H + 4 * ti + e) * kTS + tj + TT * f] = acc[e][f];
+  }
+  __syncthreads();
+  for (int t = tid; t < NPR * TT * TT; t += 256) {      // X21_p = -X22_p T_p
+    const int pr = t / (TT * TT), tt = t % (TT * TT), ti = tt / TT, tj = tt % TT;
+    const int base = pr * 2 * H;
+    double acc[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+    for (int k = 0; k <= 4 * ti + 3; ++k) {  // X22 is lower triangular: X22[r][k] = 0 for k > r
+      double va[4], vb[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) va[e] = inv_get(a, xd, base + H + 4 * ti + e, base + H + k);
+#pragma unroll
+      for (int f = 0; f < 4; ++f) vb[f] = T[(pr * H + k) * kTS + tj + TT * f];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vb[f], acc[e][f]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f < 4; ++f)        // X[r][c], r > c, lives at a[c][r]
+        a[(base + tj + TT * f) * kPad + base + H + 4 * ti + e] = -acc[e][f];
+  }
+  __syncthreads();
+}
+
+// warp 0: (optionally) subtract the rank-16 update of the previous panel from the 16x16 diagonal block at c0, factorise it
+// in registers (lane = row; pivots and multipliers by shuffle; one rsqrt per pivot, no division) and leave L_D in the
+// lower triangle of the block and 1 / diag in invd[c0 ..].  Returns 0 or the 1-based index of a non-positive pivot.
+__device__ __forceinline__ int factor_diag16(double* __restrict__ a, double* __restrict__ invd, int c0, int lane,
+                                             bool apply_update) {
+  const int rl = lane & (kSB - 1);
+  double r[kSB];
+#pragma unroll
+  for (int k = 0; k < kSB; ++k) r[k] = (k <= rl) ? a[(c0 + rl) * kPad + c0 + k] : 0.0;
+  if (apply_update) {      // a[c0+rl][c0+k] -= sum_t P[c0+rl][t] P[c0+k][t],  P = panel columns c0-16 .. c0-1
+    double prow[kSB];
+#pragma unroll
+    for (int t = 0; t < kSB; ++t) prow[t] = a[(c0 + rl) * kPad + c0 - kSB + t];
+#pragma unroll
+    for (int k = 0; k < kSB; ++k) {
+      double s = 0.0;
+#pragma unroll
+      for (int t = 0; t < kSB; ++t) s = fma(prow[t], a[(c0 + k) * kPad + c0 - kSB + t], s);
+      if (k <= rl) r[k] -= s;
+    }
+  }
+  int bad = 0;
+  double myinv = 0.0;
+#pragma unroll
+  for (int j = 0; j < kSB; ++j) {
+    double djj = __shfl_sync(0xffffffffu, r[j], j);
+    if (!(djj > 0.0)) {
+      if (bad == 0) bad = c0 + j + 1;
+      djj = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    const double inv = rsqrt(djj);
+    if (rl == j) { r[j] = djj * inv; myinv = inv; }
+    else if (rl > j) r[j] = r[j] * inv;
+#pragma unroll
+    for (int k = 0; k < kSB; ++k) {
+      if (k > j) {
+        const double lkj = __shfl_sync(0xffffffffu, r[j], k);
+        if (rl >= k) r[k] = fma(-r[j], lkj, r[k]);
+      }
+    }
+  }
+  if (lane < kSB) {
+#pragma unroll
+    for (int k = 0; k < kSB; ++k)
+      if (k <= lane) a[(c0 + lane) * kPad + c0 + k] = r[k];
+    invd[c0 + lane] = myinv;
+  }
+  return bad;
+}
+
+__global__ void __launch_bounds__(256, 1)
+potf2_inv2_kernel(double* __restrict__ A_, int ld, int k0, const double* __restrict__ jitter_, int N, double jscale,
+                  double* __restrict__ dinv_, int* __restrict__ info_, long long sA, long long sD, long long sJ) {
+  extern __shared__ __align__(16) double sm[];
+  double* a = sm;                    // [128][129]
+  double* xd = sm + kBlk * kPad;     // [128] diagonal of the inverse
+  double* invd = xd + kBlk;          // [128] 1 / diag(L)
+  double* T = invd + kBlk;           // [64][65] scratch of phase B
+  __shared__ int failed;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* A = A_ + (long long)blockIdx.x * sA;
+  double* dinv = dinv_ + (long long)blockIdx.x * sD;
+  const double* jitter = jitter_ ? jitter_ + (long long)blockIdx.x * sJ : nullptr;
+  int* info = info_ + blockIdx.x;
+  if (tid == 0) failed = 0;
+#pragma unroll 8
+  for (int it = 0; it < kBlk * kBlk / 2 / 256; ++it) {
+    const int idx2 = it * 256 + tid, r = idx2 >> 6, c = (idx2 & 63) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(A + (long long)(k0 + r) * ld + (k0 + c));
+    a[r * kPad + c] = (c <= r) ? v.x : 0.0;
+    a[r * kPad + c + 1] = (c + 1 <= r) ? v.y : 0.0;
+  }
+  __syncthreads();
+  if (tid < kBlk && jitter != nullptr && (k0 + tid) < N)
+    a[tid * kPad + tid] = __fma_rn(jscale, jitter[k0 + tid], a[tid * kPad + tid]);
+  __syncthreads();
+
+  // ======================= Phase A ===============================================================================
+  if (warp == 0) {
+    const int bad = factor_diag16(a, invd, 0, lane, false);
+    if (lane == 0 && bad != 0) { atomicCAS(info, 0, k0 + bad); failed = 1; }
+  }
+  __syncthreads();
+  for (int pnl = 0; pnl < kBlk / kSB; ++pnl) {
+    if (failed) break;
+    const int c0 = pnl * kSB, r0 = c0 + kSB, Tn = kBlk - r0;
+    if (Tn == 0) break;
+    // A2: forward substitution of every row below against L_D (thread = row; L_D and 1 / diag are broadcast reads)
+    if (tid < Tn) {
+      double* row = a + (r0 + tid) * kPad + c0;
+      double v[kSB];
+#pragma unroll
+      for (int j = 0; j < kSB; ++j) v[j] = row[j];
+#pragma unroll
+      for (int j = 0; j < kSB; ++j) {
+        const double pj = v[j] * invd[c0 + j];
+        v[j] = pj;
+#pragma unroll
+        for (int jj = j + 1; jj < kSB; ++jj) v[jj] = fma(-pj, a[(c0 + jj) * kPad + c0 + j], v[jj]);
+      }
+#pragma unroll
+      for (int j = 0; j < kSB; ++j) row[j] = v[j];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // next diagonal block: its share of the trailing update, then its factorisation — concurrently with A3 below
+      const int bad = factor_diag16(a, invd, r0, lane, true);
+      if (lane == 0 && bad != 0) { atomicCAS(info, 0, k0 + bad); failed = 1; }
+    } else {
+      // A3: trailing (lower) -= P P^T with 4x4 register tiles, minus the 16x16 diagonal block warp 0 owns (tiles t < 10)
+      const int nt = Tn / 4, ntiles = nt * (nt + 1) / 2;
+      for (int t = 10 + (tid - 32); t < ntiles; t += 224) {
+        int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        const double* pa = a + (r0 + 4 * ti) * kPad + c0;
+        const double* pb = a + (r0 + 4 * tj) * kPad + c0;
+        double acc[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < kSB; ++k) {
+          double va[4], vb[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            va[e] = pa[e * kPad + k];
+            vb[e] = pb[e * kPad + k];
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vb[f], acc[e][f]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const int i = r0 + 4 * ti + e, j = r0 + 4 * tj + f;
+            if (j <= i) a[i * kPad + j] -= acc[e][f];
+          }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (failed) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
+      int r = idx >> 7, c = idx & 127;
+      A[(long long)(k0 + r) * ld + (k0 + c)] = nan;
+      dinv[idx] = nan;
+    }
+    return;
+  }
+
+  // ======================= Phase A': the eight 16x16 diagonal inverses, one warp each (lane = column of X) =============
+  {
+    const int c0 = warp * kSB, rl = lane & (kSB - 1);
+    double r[kSB], x[kSB];
+#pragma unroll
+    for (int k = 0; k < kSB; ++k) r[k] = (k <= rl) ? a[(c0 + rl) * kPad + c0 + k] : 0.0;
+    const double myinv = invd[c0 + rl];
+#pragma unroll
+    for (int i = 0; i < kSB; ++i) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k < kSB; ++k) {
+        if (k < i) {
+          const double lik = __shfl_sync(0xffffffffu, r[k], i);   // L[i][k]
+          if (k >= rl) sacc = fma(lik, x[k], sacc);
+        }
+      }
+      const double dii = __shfl_sync(0xffffffffu, myinv, i);
+      x[i] = (i == rl) ? dii : (i > rl ? -sacc * dii : 0.0);
+    }
+    __syncwarp();
+    if (lane < kSB) {
+#pragma unroll
+      for (int i = 0; i < kSB; ++i) {
+        if (i == lane) xd[c0 + lane] = x[i];
+        else if (i > lane) a[(c0 + lane) * kPad + c0 + i] = x[i];   // X[i][j] (i > j) kept at a[j][i]
+      }
+    }
+  }
+  __syncthreads();
+
+  // ======================= Phase B: recursive doubling ============================================================
+  inv_level<16>(a, xd, T, tid);
+  inv_level<32>(a, xd, T, tid);
+  inv_level<64>(a, xd, T, tid);
+
+  for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
+    int r = idx >> 7, c = idx & 127;
+    double l = (c <= r) ? a[r * kPad + c] : 0.0;
+    double x = (c < r) ? a[c * kPad + r] : (c == r ? xd[r] : 0.0);
+    A[(long long)(k0 + r) * ld + (k0 + c)] = l;
+    dinv[idx] = x;
+  }
+}
+
 __global__ void zero_upper_blocks_kernel(double* __restrict__ A, int ld, int nb, long long sA) {
   // one CTA per strictly-upper 128x128 block (bi < bj); blockIdx.y = batch
   A += (long long)blockIdx.y * sA;
@@ -347,8 +626,13 @@ static LookAhead* get_lookahead() {
 
 // Trailing updates of bcbf_potrf with at least kPotrfI8MinRows rows run on the int8 tensor cores (csrc/ozaki.cu);
 // bcbf_set_potrf_i8(0) keeps everything on the FP64 pipe.
+static int g_potf2_variant = 1;   // 1: potf2_inv2_kernel (round 2), 0: potf2_inv_kernel (round 1); bcbf_set_potf2_variant
 static int g_potrf_i8 = 1;
 constexpr int kPotrfI8MinRows = 1024;
+extern "C" int bcbf_set_potf2_variant(int v) {
+  g_potf2_variant = v ? 1 : 0;
+  return BCBF_OK;
+}
 extern "C" int bcbf_set_potrf_i8(int on) {
   g_potrf_i8 = on ? 1 : 0;
   return BCBF_OK;
@@ -364,7 +648,9 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
                kBlk, ld, N);
   const int nb = Npad / kBlk;
   const int smem = (kBlk * kPad + kBlk + kTElems) * (int)sizeof(double);
+  const int smem2 = (kBlk * kPad + 2 * kBlk + kT2Elems) * (int)sizeof(double);
   BCBF_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  BCBF_CUDA(cudaFuncSetAttribute(potf2_inv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   BCBF_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * (size_t)R, stream));  // before the look-ahead fork below
   // Two-level blocking: outer block columns of kOuter = 512; inside one, a right-looking sweep over 128-wide panels
   // whose updates stay within the block column (K = 128, small); the bulk of the N^3/3 flops runs in ONE trailing
@@ -386,7 +672,10 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
     for (int k = J; k < jend; ++k) {
       const int k0 = k * kBlk;
       double* dk = dinv + (long long)k * kBlk * kBlk;
-      potf2_inv_kernel<<<R, 256, smem, cs>>>(A, ld, k0, jitter, N, jitter_scale, dk, info, sA, sD, sJ);
+      if (g_potf2_variant == 1)
+        potf2_inv2_kernel<<<R, 256, smem2, cs>>>(A, ld, k0, jitter, N, jitter_scale, dk, info, sA, sD, sJ);
+      else
+        potf2_inv_kernel<<<R, 256, smem, cs>>>(A, ld, k0, jitter, N, jitter_scale, dk, info, sA, sD, sJ);
       BCBF_LAUNCH_CHECK();
       const int rows = Npad - (k0 + kBlk);
       if (rows <= 0) break;

@@ -140,6 +140,9 @@ int bcbf_check_info(const int* info, void* stream);
 /* The large trailing updates of bcbf_potrf (single matrix, >= 1024 rows left) run on the int8 tensor cores
  * (bcbf_oz_update) by default; 0 keeps them on the FP64 pipe. */
 int bcbf_set_potrf_i8(int on);
+/* Diagonal-block kernel of bcbf_potrf[_batched]: 1 = potf2_inv2_kernel (default: diagonal factorisations overlapped with
+ * the trailing update inside the CTA, inverse by recursive doubling), 0 = round 1's potf2_inv_kernel (kept for A/B runs). */
+int bcbf_set_potf2_variant(int v);
 
 /* Linv = L^{-1} (lower; strictly-upper blocks are zero) from L and the diagonal-block inverses of bcbf_potrf.
  * scratch: Npad*Npad doubles.  Everything downstream (alpha, v = L \ kb*, posterior covariance) multiplies by
