@@ -447,11 +447,11 @@ class ControlAffineRegressor(DynamicsModel):
             Y = targets.double() - UH64 @ C                           # Y = Xdot - UH C  (:525-532)
             Ypad = torch.zeros(Npad, Y.shape[1], dtype=torch.float64, device=Y.device)
             Ypad[:N] = Y
-            # Kb^-1 Y (:545, cholesky_solve there): explicit-inverse product + two refinement steps whose residual is taken
+            # Kb^-1 Y (:545, cholesky_solve there): explicit-inverse product + three refinement steps whose residual is taken
             # against the factorised matrix itself in compensated arithmetic (bcbf_alpha_refine)
             eps, factor = self._cache['_jitter']
             self._cache['_alpha'] = ops.alpha_refine(Xtrain.double().contiguous(), UH64.contiguous(), B, ls, s, Linv, Ypad,
-                                                     eps, factor, iters=2).contiguous()
+                                                     eps, factor, iters=3).contiguous()
             G = torch.zeros(Npad, B.shape[0], dtype=torch.float64, device=Y.device)
             G[:N] = UH64 @ B
             self._cache['_G'] = G

@@ -76,7 +76,7 @@ def gram_resid(X, UH, B, lengthscale, outputscale, alpha, Y, jitter=None, jitter
     return R
 
 
-def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, jitter_scale=0.0, iters=2):
+def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, jitter_scale=0.0, iters=3):
     """alpha (Npad, nc) = (Kb + jitter)^-1 Y: explicit-inverse product + `iters` compensated refinement steps
     (bcbf_alpha_refine; reference cholesky_solve, control_affine_model.py:545).  Ypad (Npad, nc), pad rows zero."""
     _req(X, UH, B, lengthscale, Linv, jitter)

@@ -164,8 +164,9 @@ int bcbf_trmm_lower(const double* A, int lda, int Npad, int trans, const double*
  * alpha0 = Linv^T (Linv Y) followed by `iters` steps of iterative refinement  alpha += Linv^T Linv (Y - Kb' alpha)  with
  * the residual of bcbf_gram_resid.  Linv (Npad,Npad; ld) from bcbf_trtri; Y and alpha (Npad, ldy) with zero pad rows,
  * nc <= ldy <= 8 columns in use (ldy even); jitter (N) / jitter_scale as given to bcbf_potrf (jitter may be NULL);
- * scratch >= bcbf_alpha_refine_scratch_elems(N, Npad, ldy) doubles.  iters = 2 reaches the FP64 rounding of the exact
- * solution at the bench shapes (each step gains ~8 digits); iters = 0 is the plain explicit-inverse product.         */
+ * scratch >= bcbf_alpha_refine_scratch_elems(N, Npad, ldy) doubles.  Each step gains 1.5-2 digits in the posterior mean
+ * at the bench shapes (cond(Kb) ~ 1e11); iters = 3 (what bcbf_model_fit and the host class run) is converged at
+ * N = 16384 (a fourth step moves the mean by < 1e-12); iters = 0 is the plain explicit-inverse product.              */
 long long bcbf_alpha_refine_scratch_elems(int N, int Npad, int ldy);
 int bcbf_alpha_refine(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
                       double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,

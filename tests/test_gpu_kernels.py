@@ -227,7 +227,7 @@ def _fit_on_gpu(X, U, Xdot, hyp, jit):
     G[:N] = UH @ hyp.B
     Y = torch.zeros(Npad, hyp.n, dtype=torch.float64)
     Y[:N] = O.residual_targets(hyp, UH, Xdot)
-    alpha = ops.alpha_refine(*args, Linv, _d(Y), _d(jit), 1e-5, iters=2).contiguous()
+    alpha = ops.alpha_refine(*args, Linv, _d(Y), _d(jit), 1e-5, iters=3).contiguous()
     W = (alpha.unsqueeze(-1) * _d(G).unsqueeze(1)).reshape(Npad, -1).contiguous()
     return L, Linv, _d(G), alpha, W
 
