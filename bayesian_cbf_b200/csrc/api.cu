@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 namespace bcbf {
@@ -16,6 +17,39 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+namespace {
+struct ScratchState {
+  std::recursive_mutex mu;
+  int depth = 0;
+  cudaEvent_t ev = nullptr;
+  bool recorded = false;
+  cudaStream_t last = nullptr;
+};
+ScratchState g_scratch[64];
+}  // namespace
+
+ScratchScope::ScratchScope(cudaStream_t s) : stream(s), dev(0) {
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  ScratchState& st = g_scratch[dev & 63];
+  st.mu.lock();
+  if (st.depth++ == 0) {
+    if (st.ev == nullptr) cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming);
+    // the previous user of the scratch ran on another stream: order this call behind it on the device
+    if (st.recorded && st.last != s && st.ev != nullptr) cudaStreamWaitEvent(s, st.ev, 0);
+  }
+}
+
+ScratchScope::~ScratchScope() {
+  ScratchState& st = g_scratch[dev & 63];
+  if (--st.depth == 0 && st.ev != nullptr) {
+    if (cudaEventRecord(st.ev, stream) == cudaSuccess) {
+      st.recorded = true;
+      st.last = stream;
+    }
+  }
+  st.mu.unlock();
 }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {

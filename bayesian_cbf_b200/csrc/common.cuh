@@ -73,6 +73,21 @@ __device__ __forceinline__ double g_entry(const double* __restrict__ uh_row, con
   return g;
 }
 
+// ---- per-device scratch ordering ------------------------------------------------------------------------------------
+// Several entry points (posterior_*, oz_*, potrf, trtri) use library-owned per-device scratch buffers and, for potrf, a set
+// of look-ahead streams and events.  A ScratchScope at the top of such an entry point makes that safe for callers on
+// different streams / host threads of one device: a per-device host mutex is held while the call enqueues its work, the
+// caller's stream first waits (on the GPU) for the previous scratch user if that ran on another stream, and an event is
+// recorded when the call has enqueued everything.  Nested entry points (potrf -> oz_update) join the outer scope.
+struct ScratchScope {
+  explicit ScratchScope(cudaStream_t s);
+  ~ScratchScope();
+  ScratchScope(const ScratchScope&) = delete;
+  ScratchScope& operator=(const ScratchScope&) = delete;
+  cudaStream_t stream;
+  int dev;
+};
+
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace bcbf

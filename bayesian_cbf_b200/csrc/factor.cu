@@ -790,11 +790,13 @@ static int potrf_impl(double* A, int ld, int Npad, int N, const double* jitter, 
 
 extern "C" int bcbf_potrf(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale,
                           double* dinv, int* info, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   return potrf_impl(A, ld, Npad, N, jitter, jitter_scale, dinv, info, 1, 0, 0, 0, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int bcbf_potrf_batched(double* A, int ld, int Npad, int N, const double* jitter, double jitter_scale,
                                   double* dinv, int* info, int R, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   BCBF_REQUIRE(R >= 1, "bcbf_potrf_batched: R=%d", R);
   return potrf_impl(A, ld, Npad, N, jitter, jitter_scale, dinv, info, R, (long long)ld * Npad,
                     bcbf_dinv_elems(Npad), N, static_cast<cudaStream_t>(stream_));
@@ -889,11 +891,13 @@ static int trtri_impl(const double* L, const double* dinv, double* Linv, double*
 
 extern "C" int bcbf_trtri(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad,
                           void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   return trtri_impl(L, dinv, Linv, scratch, ld, Npad, 1, 0, 0, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int bcbf_trtri_batched(const double* L, const double* dinv, double* Linv, double* scratch, int ld, int Npad,
                                   int R, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   BCBF_REQUIRE(R >= 1, "bcbf_trtri_batched: R=%d", R);
   return trtri_impl(L, dinv, Linv, scratch, ld, Npad, R, (long long)ld * Npad, bcbf_dinv_elems(Npad),
                     static_cast<cudaStream_t>(stream_));

@@ -1239,6 +1239,7 @@ extern "C" int bcbf_posterior_blocks_i8_d(const void* digits, const double* rows
                                           int ldks, const double* G, const double* W, const double* Bmat,
                                           const double* Ct, double kss, int n, int p, int Q, double* Mk, double* Bk,
                                           int ndigits, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BCBF_REQUIRE(ndigits == 6 || ndigits == 7, "bcbf_posterior_blocks_i8: digits=%d (6 or 7)", ndigits);
   BCBF_REQUIRE(digits && rowscale && Kstar && G && Bmat && (Mk || Bk), "bcbf_posterior_blocks_i8: null pointer");
@@ -1287,6 +1288,7 @@ extern "C" int bcbf_oz_debug_counters(int enable, unsigned long long out[8]) {
 
 extern "C" int bcbf_oz_gemm_tn(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
                                double* C, int ldc, int lower, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BCBF_REQUIRE(A && B && C, "bcbf_oz_gemm_tn: null pointer");
   BCBF_REQUIRE(M > 0 && N > 0 && K > 0 && M % oz::TM == 0 && N % oz::TN == 0 && K % oz::KSTEP == 0 && K <= oz::kMaxNpad,
@@ -1299,6 +1301,7 @@ extern "C" int bcbf_oz_gemm_tn(int M, int N, int K, double alpha, const double* 
 
 extern "C" int bcbf_oz_update(int M, int N, int K, double alpha, const double* PA, int lda, const double* PB, int ldb,
                               double* C, int ldc, int lower, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BCBF_REQUIRE(PA && PB && C, "bcbf_oz_update: null pointer");
   BCBF_REQUIRE(M > 0 && N > 0 && K > 0 && M % oz::TM == 0 && N % oz::TN == 0 && K % oz::KSTEP == 0 && K <= oz::kMaxNpad,
@@ -1330,6 +1333,7 @@ extern "C" int bcbf_oz_gemm_reserve(int M, int N, int K) {
 
 extern "C" int bcbf_oz_gemm(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
                             double* C, int ldc, int tri, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BCBF_REQUIRE(A && B && C, "bcbf_oz_gemm: null pointer");
   BCBF_REQUIRE(M > 0 && N > 0 && K > 0 && M % oz::TM == 0 && N % oz::TN == 0 && K % oz::KSTEP == 0 && K <= oz::kMaxNpad,

@@ -528,6 +528,7 @@ static int run_mean(const double* Kstar, int ldks, const double* W, const double
 extern "C" int bcbf_posterior_blocks(const double* Linv, int ld, int Npad, const double* Kstar, int ldks,
                                      const double* G, const double* W, const double* Bmat, const double* Ct,
                                      double kss, int n, int p, int Q, double* Mk, double* Bk, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BCBF_REQUIRE(Linv && Kstar && G && Bmat, "bcbf_posterior_blocks: null pointer");
   BCBF_REQUIRE(n >= 1 && n <= BCBF_MAX_N_DIM && p >= 1 && p <= BCBF_MAX_P_DIM, "bcbf_posterior_blocks: n=%d p=%d", n, p);
@@ -553,6 +554,7 @@ extern "C" int bcbf_posterior_blocks(const double* Linv, int ld, int Npad, const
 extern "C" int bcbf_posterior_fu(const double* Linv, int ld, int Npad, const double* Kstar, int ldks, const double* G,
                                  const double* alpha, const double* Bmat, const double* C, const double* UHq, double kss,
                                  int n, int p, int Q, double* mean, double* svar, void* stream_) {
+  ::bcbf::ScratchScope scratch_scope(static_cast<cudaStream_t>(stream_));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   (void)alpha; (void)C; (void)mean;
   BCBF_REQUIRE(Linv && Kstar && G && Bmat && UHq && svar, "bcbf_posterior_fu: null pointer");

@@ -14,9 +14,12 @@
  *   - N  = number of training points, Npad = N rounded up to a multiple of 128 (bcbf_padded()); factor-sized
  *     buffers are Npad x Npad with leading dimension ld >= Npad, the pad region holds the identity;
  *   - n  = state dim, m = control dim, p = 1 + m (homogeneous control [1;u]);
- *   - the library keeps per-device scratch buffers (posterior partial sums, operand digits of the int8 kernels): entry
- *     points that use them (posterior_*, oz_*, potrf, trtri, model_*) must not run concurrently on different streams of the
- *     same device; one caller thread per device, as in the reference (single-threaded Python);
+ *   - the library keeps per-device scratch buffers (posterior partial sums, operand digits of the int8 kernels) and, for
+ *     bcbf_potrf, a set of look-ahead streams.  Entry points that use them (posterior_*, oz_*, potrf, trtri, model_*) may
+ *     be called on different streams and from different host threads of one device: a per-device lock is held while a call
+ *     enqueues its work, and a call on another stream than its predecessor first waits, on the GPU, for that predecessor
+ *     (calls that share scratch execute in call order; they do not overlap each other).  Calls on ONE stream are ordered by
+ *     the stream as usual.  A bcbf_model handle is used by one thread at a time;
  *   - return value: BCBF_OK (0) or a negative error code; bcbf_last_error() describes the last failure
  *     of the calling thread.  There is NO CPU fallback anywhere: without a CUDA device every compute
  *     entry point returns BCBF_ERR_CUDA.
