@@ -409,3 +409,32 @@ def test_model_handle_six_digit_option():
     with pytest.raises(Exception):
         model2 = MVGPModel(0)
         model2.set_oz_digits(5)
+
+
+def test_scratch_using_entry_points_are_safe_across_streams():
+    """Two torch streams call the int8 posterior (which shares per-device scratch: frakB digits, partial sums) back to back
+    without any host synchronisation between the calls; every result must equal the one computed alone (bit for bit: the
+    kernels are deterministic).  Round 1 documented this as a trap; ScratchScope (csrc/common.cuh) orders the calls."""
+    from bayesian_cbf_b200 import ops
+    X, U, Xdot, hyp, jit, Xq, Uq = _mk(51, 900, 3, 2, 3000, box=2.0)
+    L, Linv, G, alpha, W = _fit_on_gpu(X, U, Xdot, hyp, jit)
+    digits, rowscale = ops.oz_split_factor(Linv)
+    Bd, Ct = _d(hyp.B), _d(hyp.C.t())
+    Xd = _d(X)
+    ls = _d(hyp.lengthscale)
+    chunks = [(0, 1100), (1100, 2300), (2300, 3000), (500, 2900)]
+    Ks = [ops.cross_gram(Xd, _d(Xq[a:b]), ls, float(hyp.outputscale)) for a, b in chunks]
+    alone = []
+    for K, (a, b) in zip(Ks, chunks):
+        alone.append(ops.posterior_blocks_i8(digits, rowscale, K, G, W, Bd, Ct, float(hyp.outputscale), 3, 3, b - a))
+        torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    got = [None] * len(chunks)
+    for rep in range(3):
+        for i, (K, (a, b)) in enumerate(zip(Ks, chunks)):
+            with torch.cuda.stream(streams[i % 2]):
+                got[i] = ops.posterior_blocks_i8(digits, rowscale, K, G, W, Bd, Ct, float(hyp.outputscale), 3, 3, b - a)
+        torch.cuda.synchronize()
+        for i in range(len(chunks)):
+            assert torch.equal(got[i][1], alone[i][1]) and torch.equal(got[i][0], alone[i][0]), (rep, i)
