@@ -48,3 +48,34 @@ def test_nologger_is_silent():
     lg.add_scalars('a', dict(b=1.0), 0)
     lg.add_tensors('a', dict(b=np.zeros(2)), 0)
     assert lg.experiment_logs_dir == '/tmp'
+
+
+@pytest.mark.skipif(not __import__('os').path.isdir('/root/reference/bayes_cbf'), reason="needs the reference checkout")
+def test_reference_reader_reads_our_logs(tmp_path):
+    """SURVEY 8f-4 from the consumer side: the reference's OWN `misc.load_tensorboard_scalars` (misc.py:342-359, imported
+    unmodified in a subprocess; matplotlib stubbed) reads a run written by `tb_log.TBLogger` and recovers every array."""
+    import subprocess
+    import sys
+    logger = tb_log.TBLogger(['pendulum', 'speed'], runs_dir=str(tmp_path))
+    x = np.arange(6, dtype=np.float64).reshape(2, 3) / 4.0
+    for t in range(4):
+        logger.add_tensors('traj', dict(x=x * (t + 1), u=np.array([0.25 * t])), t)
+        logger.add_scalars('opt', dict(loss=1.0 / (t + 1)), t)
+    logger.close()
+    path = logger.summary_writer.event_files()[0]
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import gpytorch_shim; gpytorch_shim.install()\n"
+        "from bayes_cbf.misc import load_tensorboard_scalars\n"
+        "d = load_tensorboard_scalars(%r)\n"
+        "assert set(d) == {'traj/x', 'traj/u', 'opt/loss'}, set(d)\n"
+        "x = np.arange(6, dtype=np.float64).reshape(2, 3) / 4.0\n"
+        "for t in range(4):\n"
+        "    step, val = d['traj/x'][t]\n"
+        "    assert step == t and np.asarray(val).shape == (2, 3) and np.allclose(val, x * (t + 1))\n"
+        "    assert np.allclose(d['traj/u'][t][1], [0.25 * t])\n"
+        "    assert abs(float(np.asarray(d['opt/loss'][t][1]).reshape(-1)[0]) - 1.0 / (t + 1)) < 1e-6\n"
+        "print('REF_READER_OK')\n" % (__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))), path))
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and 'REF_READER_OK' in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
