@@ -348,7 +348,10 @@ class ControlAffineRegressor(DynamicsModel):
             warnings.simplefilter("ignore")
             return self._fit_with_warnings(*args, **kwargs)
 
-    def _fit_with_warnings(self, Xtrain_in, Utrain_in, XdotTrain_in, training_iter=50, lr=0.1):
+    def _fit_with_warnings(self, Xtrain_in, Utrain_in, XdotTrain_in, training_iter=50, lr=0.1, cuda_graph=None):
+        """Adam + MultiStepLR on -(log marginal + lengthscale prior) / (N n) with a fresh 1e-6 multiplicative target noise
+        per iteration (reference :274-335).  cuda_graph: None = capture value + gradients of one iteration in a CUDA graph
+        when the problem is small enough to be launch-bound (Npad <= 1024, >= 8 iterations), True / False to force."""
         if Xtrain_in.shape[0] == 0:
             return self
         _need_cuda(self.device)
@@ -364,17 +367,13 @@ class ControlAffineRegressor(DynamicsModel):
         X64 = Xtrain.double().contiguous()
         UH64 = torch.cat([Xtrain.new_ones(N, 1), Utrain], dim=1).double().contiguous()
         prior = model.input_covar.base_kernel.lengthscale_prior
-        self.fit_losses = []
         params = list(model.parameters(recurse=True))
-        for i in range(training_iter):
-            optimizer.zero_grad()
-            # fresh multiplicative target noise every iteration (reference :318-321), drawn on the CPU generator
-            if self._fit_noise_source is not None:
-                noise = torch.as_tensor(next(self._fit_noise_source)).reshape(XdotTrain.shape).to(
-                    device=self.device, dtype=XdotTrain.dtype)
-            else:
-                noise = torch.rand(XdotTrain.shape, dtype=XdotTrain.dtype).to(self.device)
-            Y = (XdotTrain * (1 + 1e-6 * noise)).double()
+        self.fit_losses = []
+        noise_buf = torch.zeros_like(XdotTrain)          # static input of the captured iteration
+
+        def value_and_grads():
+            """loss (0-d) and the fused finiteness flag of loss and gradients; gradients land in p.grad."""
+            Y = (XdotTrain * (1 + 1e-6 * noise_buf)).double()
             ls = model.input_covar.base_kernel.lengthscale
             logp = mvgp_log_marginal(ls.double().reshape(-1).expand(n), model.input_covar.outputscale.double(),
                                      self._A_mat().double(), self._B_mat().double(),
@@ -388,13 +387,64 @@ class ControlAffineRegressor(DynamicsModel):
             # the same with ONE read per iteration.
             grads = [p.grad for p in params if p.grad is not None]
             ok = torch.isfinite(loss) & torch.isfinite(torch.stack(torch._foreach_norm(grads)).sum())
-            assert bool(ok), "NaN / inf in the loss or a gradient of the log marginal likelihood"
-            self.fit_losses.append(loss.detach())
+            return loss.detach(), ok
+
+        graph = static = None
+        want_graph = cuda_graph if cuda_graph is not None else (ops.padded(N) <= 1024 and training_iter >= 8)
+        if want_graph and torch.device(self.device).type == 'cuda' and hasattr(torch.cuda, 'CUDAGraph'):
+            graph, static = self._capture_fit_iteration(value_and_grads, optimizer)
+        for i in range(training_iter):
+            # fresh multiplicative target noise every iteration (reference :318-321), drawn on the CPU generator
+            if self._fit_noise_source is not None:
+                noise = torch.as_tensor(next(self._fit_noise_source)).reshape(XdotTrain.shape).to(dtype=XdotTrain.dtype)
+            else:
+                noise = torch.rand(XdotTrain.shape, dtype=XdotTrain.dtype)
+            noise_buf.copy_(noise)
+            replayed = False
+            if graph is not None:
+                graph.replay()
+                loss, status = static
+                bad_pivot, not_finite = status.tolist()   # the one device->host read of the iteration
+                replayed = bad_pivot == 0
+            if not replayed:                              # eager iteration (with the psd-safe jitter escalation)
+                optimizer.zero_grad(set_to_none=False)    # keep the gradient tensors: the graph writes to these
+                loss, ok = value_and_grads()
+                not_finite = not bool(ok)
+            assert not not_finite, "NaN / inf in the loss or a gradient of the log marginal likelihood"
+            self.fit_losses.append(loss.clone())
             if LOG.isEnabledFor(logging.DEBUG):
                 LOG.debug('Iter %d/%d - Loss: %.3f' % (i + 1, training_iter, loss.item()))
             optimizer.step()
             scheduler.step()
         return self
+
+    def _capture_fit_iteration(self, value_and_grads, optimizer):
+        """One iteration's value + gradients as a CUDA graph (the small-N regime is launch- and Python-bound: ~150 tiny
+        launches per iteration).  Returns (graph, (loss, status)) with static output tensors — status = [Cholesky info,
+        not-finite flag] — or (None, None) when the capture is not possible: the caller then iterates eagerly.  The
+        optimiser step stays outside the graph."""
+        from .mll import capturable
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), capturable(info):
+                for _ in range(2):                        # warm-up: lazy initialisations, allocator, function attributes
+                    optimizer.zero_grad(set_to_none=True)
+                    value_and_grads()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            optimizer.zero_grad(set_to_none=True)
+            with capturable(info), torch.cuda.graph(graph):
+                loss, ok = value_and_grads()
+                status = torch.stack([info[0].to(torch.int64), (~ok).to(torch.int64)])
+            return graph, (loss, status)
+        except Exception as e:                            # e.g. an allocation inside the capture: stay eager
+            LOG.warning("fit: CUDA-graph capture of the iteration failed (%s); iterating eagerly" % (e,))
+            optimizer.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+            return None, None
 
     # ------------------------------------------------------------------------------------------ factor
     def _train_data(self):

@@ -30,11 +30,19 @@ struct ScratchState {
 ScratchState g_scratch[64];
 }  // namespace
 
+// A stream that is being captured into a CUDA graph may neither wait for an event recorded outside the capture nor
+// publish one: captured calls are ordered by whoever replays the graph.
+static bool stream_is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+
 ScratchScope::ScratchScope(cudaStream_t s) : stream(s), dev(0) {
   if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   ScratchState& st = g_scratch[dev & 63];
   st.mu.lock();
-  if (st.depth++ == 0) {
+  if (st.depth++ == 0 && !stream_is_capturing(s)) {
     if (st.ev == nullptr) cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming);
     // the previous user of the scratch ran on another stream: order this call behind it on the device
     if (st.recorded && st.last != s && st.ev != nullptr) cudaStreamWaitEvent(s, st.ev, 0);
@@ -43,7 +51,7 @@ ScratchScope::ScratchScope(cudaStream_t s) : stream(s), dev(0) {
 
 ScratchScope::~ScratchScope() {
   ScratchState& st = g_scratch[dev & 63];
-  if (--st.depth == 0 && st.ev != nullptr) {
+  if (--st.depth == 0 && st.ev != nullptr && !stream_is_capturing(stream)) {
     if (cudaEventRecord(st.ev, stream) == cudaSuccess) {
       st.recorded = true;
       st.last = stream;

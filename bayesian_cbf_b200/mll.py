@@ -24,6 +24,10 @@ from ._lib import NotPositiveDefiniteError
 
 
 class _MVGPLogMarginal(torch.autograd.Function):
+    # set by `capturable(info)` around a CUDA-graph capture: the Cholesky status goes to this tensor instead of being read
+    # back (a read synchronises, which a capture forbids); the caller checks it after the replay
+    deferred_info = None
+
     @staticmethod
     def forward(ctx, ls, s, A, B, C, X, UH, Xdot):
         N, n = X.shape
@@ -42,6 +46,9 @@ class _MVGPLogMarginal(torch.autograd.Function):
         L = dinv = None
         for attempt in range(7):          # psd-safe escalation like gpytorch's psd_safe_cholesky (1e-8 * 10^t)
             Kb = ops.gram_train_lower(X, UH, B_d, ls_d, s_f)
+            if _MVGPLogMarginal.deferred_info is not None:      # no read-back: a failed factor leaves NaNs and a status
+                L, dinv = ops.potrf_(Kb, N, None, 0.0, check_pd=False, info_out=_MVGPLogMarginal.deferred_info)
+                break
             try:
                 L, dinv = ops.potrf_(Kb, N, ones if jitter > 0 else None, jitter)
                 break
@@ -88,6 +95,22 @@ class _MVGPLogMarginal(torch.autograd.Function):
     def backward(ctx, g):
         g_ls, g_s, g_A, g_B, g_C = ctx.saved_tensors
         return g * g_ls, g * g_s, g * g_A, g * g_B, g * g_C, None, None, None
+
+
+class capturable:
+    """Context manager: inside it `mvgp_log_marginal` makes no device->host read (the Cholesky status is written to `info`,
+    a 1-element int32 CUDA tensor), so that value + gradients can be captured in a CUDA graph."""
+
+    def __init__(self, info):
+        self.info = info
+
+    def __enter__(self):
+        _MVGPLogMarginal.deferred_info = self.info
+        return self
+
+    def __exit__(self, *a):
+        _MVGPLogMarginal.deferred_info = None
+        return False
 
 
 def _need_cuda(*tensors):

@@ -179,14 +179,16 @@ def rbf_blocks(X1, X2, lengthscale, outputscale, grad=False, hess=False):
     return K, dK, d2K
 
 
-def potrf_(A, N, jitter=None, jitter_scale=1e-5, check_pd=True):
+def potrf_(A, N, jitter=None, jitter_scale=1e-5, check_pd=True, info_out=None):
     """In-place lower Cholesky of the padded matrix A (Npad,Npad) + jitter_scale*diag(jitter).
-    Returns (A, dinv).  Raises NotPositiveDefiniteError (a RuntimeError) when a pivot is not positive."""
+    Returns (A, dinv).  Raises NotPositiveDefiniteError (a RuntimeError) when a pivot is not positive.
+    check_pd=False skips the (synchronising) status read: the caller reads `info_out` (a 1-element int32 CUDA tensor that
+    receives 0 or 1 + the index of the failing pivot) when it chooses — what a CUDA-graph capture needs."""
     _req(A, jitter)
     Npad = A.shape[0]
     lib = _lib.load()
     dinv = torch.empty(lib.bcbf_dinv_elems(Npad), dtype=torch.float64, device=A.device)
-    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    info = torch.zeros(1, dtype=torch.int32, device=A.device) if info_out is None else info_out
     check(lib.bcbf_potrf(_ptr(A), A.stride(0), Npad, N, _ptr(jitter), float(jitter_scale), _ptr(dinv), _ptr(info),
                          _stream()))
     if check_pd:

@@ -83,7 +83,7 @@ def rbf_blocks(X1, X2, lengthscale, outputscale, grad=False, hess=False):
     return K, dK, d2K
 
 
-def potrf_(A, N, jitter=None, jitter_scale=1e-5, check_pd=True):
+def potrf_(A, N, jitter=None, jitter_scale=1e-5, check_pd=True, info_out=None):
     M = torch.tril(A)           # like bcbf_potrf, only the lower triangle is read
     M = M + torch.tril(M, -1).T
     if jitter is not None:
