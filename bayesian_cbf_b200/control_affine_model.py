@@ -403,7 +403,7 @@ class ControlAffineRegressor(DynamicsModel):
             replayed = False
             if graph is not None:
                 graph.replay()
-                loss, status = static
+                loss, status, _ = static
                 bad_pivot, not_finite = status.tolist()   # the one device->host read of the iteration
                 replayed = bad_pivot == 0
             if not replayed:                              # eager iteration (with the psd-safe jitter escalation)
@@ -420,26 +420,31 @@ class ControlAffineRegressor(DynamicsModel):
 
     def _capture_fit_iteration(self, value_and_grads, optimizer):
         """One iteration's value + gradients as a CUDA graph (the small-N regime is launch- and Python-bound: ~150 tiny
-        launches per iteration).  Returns (graph, (loss, status)) with static output tensors — status = [Cholesky info,
-        not-finite flag] — or (None, None) when the capture is not possible: the caller then iterates eagerly.  The
-        optimiser step stays outside the graph."""
+        launches per iteration).  Returns (graph, (loss, status, info)) with static tensors — status = [Cholesky info,
+        not-finite flag], info the status word the factor kernels write — or (None, None) when the capture is not possible:
+        the caller then iterates eagerly.  The optimiser step stays outside the graph."""
         from .mll import capturable
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side), capturable(info):
-                for _ in range(2):                        # warm-up: lazy initialisations, allocator, function attributes
-                    optimizer.zero_grad(set_to_none=True)
-                    value_and_grads()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            optimizer.zero_grad(set_to_none=True)
-            with capturable(info), torch.cuda.graph(graph):
-                loss, ok = value_and_grads()
-                status = torch.stack([info[0].to(torch.int64), (~ok).to(torch.int64)])
-            return graph, (loss, status)
+            with torch.cuda.stream(side), capturable(info):
+                optimizer.zero_grad(set_to_none=True)     # warm-up: lazy initialisations, scratch growth, cuBLAS handles
+                value_and_grads()
+                optimizer.zero_grad(set_to_none=True)
+                side.synchronize()
+                # capture_begin / capture_end directly: torch.cuda.graph() would also run the garbage collector and empty
+                # the caching allocator, which costs more than the iterations a short fit saves
+                graph.capture_begin()
+                try:
+                    loss, ok = value_and_grads()
+                    status = torch.stack([info[0].to(torch.int64), (~ok).to(torch.int64)])
+                finally:
+                    graph.capture_end()
+            torch.cuda.current_stream().wait_stream(side)
+            # `info` is written by the graph on every replay (a memset + the factor kernels): it must outlive this call
+            return graph, (loss, status, info)
         except Exception as e:                            # e.g. an allocation inside the capture: stay eager
             LOG.warning("fit: CUDA-graph capture of the iteration failed (%s); iterating eagerly" % (e,))
             optimizer.zero_grad(set_to_none=True)
