@@ -340,9 +340,11 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
           mbar_arrive_expect_tx(&full[stage], STAGE);
           if (CL == 1) {
             bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
-          } else {  // my half of the L^-1 digits goes to both CTAs; the peer sends the other half
-            constexpr int HALF = A_STEP / 2;
-            bulk_g2s_multicast(dst + rank * HALF, ap + (long long)ks * A_STEP + rank * HALF, HALF, &full[stage], 0x3);
+          } else {  // my 1/CL of the L^-1 digits goes to every CTA of the cluster; the peers send the rest
+            constexpr int PART = A_STEP / CL;
+            static_assert(PART % 16 == 0, "bulk copies move multiples of 16 bytes");
+            bulk_g2s_multicast(dst + rank * PART, ap + (long long)ks * A_STEP + rank * PART, PART, &full[stage],
+                               (1u << CL) - 1u);
           }
           bulk_g2s(dst + A_STEP, bp + (long long)ks * B_STEP, B_STEP, &full[stage]);
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
           const uint32_t sa = smem_u32(smem + stage * STAGE);
           issue_kstep<SD>(tmem, sa, sa + A_STEP, ks == 0);
           if (CL == 1) mma_commit(&empty[stage]);  // frees the stage when these MMAs have read it
-          else mma_commit_multicast(&empty[stage], 0x3);  // ... in both CTAs: the peer writes half of my stage
+          else mma_commit_multicast(&empty[stage], (1u << CL) - 1u);  // ... in every CTA: the peers write into my stage
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
         mma_commit(tmem_full);
@@ -509,7 +511,7 @@ static Prof g_prof;
 
 static unsigned long long* g_dbg = nullptr;
 
-static int g_cluster = 1;  // CTAs per cluster of oz_var_kernel (1 or 2); bcbf_oz_set_cluster
+static int g_cluster = 1;  // CTAs per cluster of oz_var_kernel (1, 2 or 4); bcbf_oz_set_cluster
 static int g_group = 4;    // row blocks per scheduling group of oz_var_kernel; bcbf_oz_set_group
 
 template <int P, int CL, int SD>
@@ -610,7 +612,9 @@ static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, con
   a.group = g_group;
   a.total_tiles = (long long)ceil_div(nb, g_group) * g_group * nJg;
   a.dbg = g_dbg;
-  rc = CL == 2 ? launch_var<P, 2, SD>(a, stream) : launch_var<P, 1, SD>(a, stream);
+  rc = CL == 4   ? launch_var<P, 4, SD>(a, stream)
+       : CL == 2 ? launch_var<P, 2, SD>(a, stream)
+                 : launch_var<P, 1, SD>(a, stream);
   if (rc) return rc;
   finalize_kernel<<<ceil_div(Q, 128), 128, 0, stream>>>(a.Spart, Qpad, nb, Q, P, Bmat, kss, Bk);
   BCBF_LAUNCH_CHECK();
@@ -1353,7 +1357,7 @@ extern "C" int bcbf_oz_set_group(int row_blocks) {
 }
 
 extern "C" int bcbf_oz_set_cluster(int ctas) {
-  BCBF_REQUIRE(ctas == 1 || ctas == 2, "bcbf_oz_set_cluster: 1 or 2");
+  BCBF_REQUIRE(ctas == 1 || ctas == 2 || ctas == 4, "bcbf_oz_set_cluster: 1, 2 or 4");
   oz::g_cluster = ctas;
   return BCBF_OK;
 }
