@@ -51,6 +51,10 @@ _SIGNATURES = {
     'bcbf_gram_resid_scratch_elems': (c_longlong, [c_int]),
     'bcbf_gram_resid': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_double, _P, c_int, _P, c_int, c_int,
                                 _P, c_int, _P, c_longlong, _P]),
+    'bcbf_gram_resid_stored': (c_int, [_P, c_int, c_int, _P, c_double, _P, c_int, _P, c_int, c_int, _P, c_int, _P,
+                                       c_longlong, _P]),
+    'bcbf_alpha_refine_ws': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_double, _P, c_int, c_int, _P,
+                                     c_int, c_int, c_int, _P, _P, c_longlong, _P, c_int, _P]),
     'bcbf_alpha_refine_scratch_elems': (c_longlong, [c_int, c_int, c_int]),
     'bcbf_alpha_refine': (c_int, [_P, _P, _P, _P, c_double, c_int, c_int, c_int, _P, c_double, _P, c_int, c_int, _P, c_int,
                                   c_int, c_int, _P, _P, c_longlong, _P]),

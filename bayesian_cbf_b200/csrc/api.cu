@@ -564,16 +564,18 @@ extern "C" long long bcbf_alpha_refine_scratch_elems(int N, int Npad, int ldy) {
 // digits in the posterior mean (the explicit inverse of a cond ~1e11 matrix is that good and no better): measured at
 // N = 16384, mean error 7e-7 -> ~2e-8 -> 2.5e-10 -> below 1e-12, so THREE steps are run (kRefineIters); the third is what
 // makes the result independent of last-bit differences in the factor.
-extern "C" int bcbf_alpha_refine(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
-                                 double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
-                                 const double* Linv, int ld, int Npad, const double* Y, int ldy, int nc, int iters,
-                                 double* alpha, double* scratch, long long scratch_elems, void* stream_) {
+extern "C" int bcbf_alpha_refine_ws(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                                    double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
+                                    const double* Linv, int ld, int Npad, const double* Y, int ldy, int nc, int iters,
+                                    double* alpha, double* scratch, long long scratch_elems, double* kb_ws, int ldk,
+                                    void* stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   BCBF_REQUIRE(X && UH && Bmat && lengthscale && Linv && Y && alpha && scratch, "bcbf_alpha_refine: null pointer");
   BCBF_REQUIRE(Npad > 0 && Npad % kBlk == 0 && N >= 1 && N <= Npad && ld >= Npad && nc >= 1 && nc <= ldy &&
                    ldy <= kMvMaxC && iters >= 0,
                "bcbf_alpha_refine: N=%d Npad=%d ld=%d nc=%d ldy=%d (<= %d) iters=%d", N, Npad, ld, nc, ldy, kMvMaxC, iters);
   BCBF_REQUIRE(scratch_elems >= bcbf_alpha_refine_scratch_elems(N, Npad, ldy), "bcbf_alpha_refine: scratch too small");
+  BCBF_REQUIRE(!kb_ws || ldk >= Npad, "bcbf_alpha_refine_ws: ldk=%d < Npad=%d", ldk, Npad);
   double* t = scratch;
   double* r = t + (size_t)Npad * ldy;
   double* part = r + (size_t)Npad * ldy;
@@ -582,15 +584,31 @@ extern "C" int bcbf_alpha_refine(const double* X, const double* UH, const double
   int rc;
   if ((rc = tri_mv(Linv, ld, Npad, 0, Y, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;
   if ((rc = tri_mv(Linv, ld, Npad, 1, t, ldy, ldy, 1.0, 0.0, nullptr, alpha, part, s))) return rc;
+  // With a workspace the factorised matrix is written out once more (the same kernel as for the factorisation: the same
+  // bits) and every residual streams it from HBM; without one every residual re-evaluates its N^2 entries.
+  if (kb_ws && iters > 0 &&
+      (rc = bcbf_gram_train_lower(X, UH, Bmat, lengthscale, outputscale, N, n, p, kb_ws, ldk, Npad, s)))
+    return rc;
   for (int it = 0; it < iters; ++it) {
     BCBF_CUDA(cudaMemsetAsync(r, 0, sizeof(double) * (size_t)Npad * ldy, s));
-    if ((rc = bcbf_gram_resid(X, UH, Bmat, lengthscale, outputscale, N, n, p, jitter, jitter_scale, alpha, ldy, Y, ldy, nc,
-                              r, ldy, rs, rs_elems, s)))
-      return rc;
+    if (kb_ws)
+      rc = bcbf_gram_resid_stored(kb_ws, ldk, N, jitter, jitter_scale, alpha, ldy, Y, ldy, nc, r, ldy, rs, rs_elems, s);
+    else
+      rc = bcbf_gram_resid(X, UH, Bmat, lengthscale, outputscale, N, n, p, jitter, jitter_scale, alpha, ldy, Y, ldy, nc,
+                           r, ldy, rs, rs_elems, s);
+    if (rc) return rc;
     if ((rc = tri_mv(Linv, ld, Npad, 0, r, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;
     if ((rc = tri_mv(Linv, ld, Npad, 1, t, ldy, ldy, 1.0, 1.0, alpha, alpha, part, s))) return rc;
   }
   return BCBF_OK;
+}
+
+extern "C" int bcbf_alpha_refine(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                                 double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
+                                 const double* Linv, int ld, int Npad, const double* Y, int ldy, int nc, int iters,
+                                 double* alpha, double* scratch, long long scratch_elems, void* stream_) {
+  return bcbf_alpha_refine_ws(X, UH, Bmat, lengthscale, outputscale, N, n, p, jitter, jitter_scale, Linv, ld, Npad, Y, ldy,
+                              nc, iters, alpha, scratch, scratch_elems, nullptr, 0, stream_);
 }
 
 constexpr int kRefineIters = 3;
@@ -601,9 +619,11 @@ static int finish_fit_from_factor(bcbf_model* m, const double* djit, double jitt
   // W = alpha (.) G.
   const int n = m->hyp.n, p = m->hyp.p, Npad = m->Npad, ldy = ld_y(n);
   cudaStream_t s = m->stream;
-  int rc = bcbf_alpha_refine(m->X, m->UH, m->hyp.B, m->hyp.lengthscale, m->hyp.outputscale, m->N, n, p, djit, jitter_scale,
-                             m->Linv, Npad, Npad, m->Y, ldy, n, kRefineIters, m->alpha, m->Y + (size_t)Npad * ldy,
-                             bcbf_alpha_refine_scratch_elems(m->N, Npad, ldy), s);
+  // the query buffer K* (>= Npad^2 doubles after a fit, idle until the first query) holds the copy of Kb the residuals read
+  double* kb_ws = (m->Kstar && m->cap_K >= (size_t)Npad * Npad && Npad >= 1024) ? m->Kstar : nullptr;
+  int rc = bcbf_alpha_refine_ws(m->X, m->UH, m->hyp.B, m->hyp.lengthscale, m->hyp.outputscale, m->N, n, p, djit,
+                                jitter_scale, m->Linv, Npad, Npad, m->Y, ldy, n, kRefineIters, m->alpha,
+                                m->Y + (size_t)Npad * ldy, bcbf_alpha_refine_scratch_elems(m->N, Npad, ldy), kb_ws, Npad, s);
   if (rc) return rc;
   build_w_kernel<<<ceil_div(Npad, 128), 128, 0, s>>>(m->alpha, ldy, m->G, Npad, n, p, m->W);
   BCBF_LAUNCH_CHECK();

@@ -233,7 +233,10 @@ __device__ __forceinline__ void dd_add(double& hi, double& lo, double h2, double
 
 constexpr int kResMaxC = 4;   // columns of alpha handled per pass (n <= 4 in one pass; larger n loops)
 
-template <int NN, int PP>
+// STORED: Kb is read from P.out (lower triangle valid, leading dimension P.ld: what bcbf_gram_train_lower wrote, so the
+// same bits as the on-the-fly evaluation) instead of being re-evaluated — the residual is then bound by the 2 N^2 x 8 B of
+// the two triangle passes and the Dot2 arithmetic, not by N^2 exponentials.  Same accumulation order: same result bits.
+template <int NN, int PP, bool STORED = false>
 __global__ void __launch_bounds__(256) gram_resid_kernel(GramParams P, const double* __restrict__ jitter, double jscale,
                                                          const double* __restrict__ alpha, int lda, int cfirst, int nc,
                                                          int tiles_per_split, double* __restrict__ partial) {
@@ -246,15 +249,17 @@ __global__ void __launch_bounds__(256) gram_resid_kernel(GramParams P, const dou
   const int n = NN > 0 ? NN : P.n, p = PP > 0 ? PP : P.p;
   const int ntiles = (P.a + kGT - 1) / kGT;
   const int t0 = blockIdx.y * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
-  for (int idx = tid; idx < kGT * n; idx += 256) {
-    int r = idx / n, d = idx % n;
-    xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], h_inv_ls[d]) : 0.0;
-  }
-  for (int idx = tid; idx < kGT * p; idx += 256) {
-    int r = idx / p, q = idx % p;
-    const bool vr = r0 + r < P.a;
-    gr[r][q] = vr ? g_entry(P.UH + (long long)(r0 + r) * p, h_Bm, p, q) : 0.0;
-    ur[r][q] = vr ? P.UH[(long long)(r0 + r) * p + q] : 0.0;
+  if (!STORED) {
+    for (int idx = tid; idx < kGT * n; idx += 256) {
+      int r = idx / n, d = idx % n;
+      xr[r][d] = (r0 + r < P.a) ? __dmul_rn(P.X1[(long long)(r0 + r) * n + d], h_inv_ls[d]) : 0.0;
+    }
+    for (int idx = tid; idx < kGT * p; idx += 256) {
+      int r = idx / p, q = idx % p;
+      const bool vr = r0 + r < P.a;
+      gr[r][q] = vr ? g_entry(P.UH + (long long)(r0 + r) * p, h_Bm, p, q) : 0.0;
+      ur[r][q] = vr ? P.UH[(long long)(r0 + r) * p + q] : 0.0;
+    }
   }
   double hi[4][kResMaxC], lo[4][kResMaxC];
 #pragma unroll
@@ -264,15 +269,17 @@ __global__ void __launch_bounds__(256) gram_resid_kernel(GramParams P, const dou
   for (int bj = t0; bj < t1; ++bj) {
     const int c0 = bj * kGT;
     __syncthreads();
-    for (int idx = tid; idx < kGT * n; idx += 256) {
-      int r = idx / n, d = idx % n;
-      xc[r][d] = (c0 + r < P.a) ? __dmul_rn(P.X1[(long long)(c0 + r) * n + d], h_inv_ls[d]) : 0.0;
-    }
-    for (int idx = tid; idx < kGT * p; idx += 256) {
-      int r = idx / p, q = idx % p;
-      const bool vc = c0 + r < P.a;
-      gc[r][q] = vc ? g_entry(P.UH + (long long)(c0 + r) * p, h_Bm, p, q) : 0.0;
-      uc[r][q] = vc ? P.UH[(long long)(c0 + r) * p + q] : 0.0;
+    if (!STORED) {
+      for (int idx = tid; idx < kGT * n; idx += 256) {
+        int r = idx / n, d = idx % n;
+        xc[r][d] = (c0 + r < P.a) ? __dmul_rn(P.X1[(long long)(c0 + r) * n + d], h_inv_ls[d]) : 0.0;
+      }
+      for (int idx = tid; idx < kGT * p; idx += 256) {
+        int r = idx / p, q = idx % p;
+        const bool vc = c0 + r < P.a;
+        gc[r][q] = vc ? g_entry(P.UH + (long long)(c0 + r) * p, h_Bm, p, q) : 0.0;
+        uc[r][q] = vc ? P.UH[(long long)(c0 + r) * p + q] : 0.0;
+      }
     }
     for (int idx = tid; idx < kGT * kResMaxC; idx += 256) {
       int r = idx / kResMaxC, c = idx % kResMaxC;
@@ -280,6 +287,40 @@ __global__ void __launch_bounds__(256) gram_resid_kernel(GramParams P, const dou
     }
     __syncthreads();
     const bool upper = bi < bj, diag = bi == bj;
+    if (STORED) {
+      // entry (row, col) of the symmetric matrix from its stored lower triangle; the 4 x 4 block of a thread is fetched
+      // before the arithmetic so that the 16 loads are in flight together
+      double kv[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = r0 + ty * 4 + i, col = c0 + tx * 4 + j;
+          double k = 0.0;
+          if (row < P.a && col < P.a)
+            k = (col <= row) ? __ldg(P.out + (long long)row * P.ld + col) : __ldg(P.out + (long long)col * P.ld + row);
+          kv[i][j] = k;
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cl = tx * 4 + j, col = c0 + cl;
+        double av[kResMaxC];
+#pragma unroll
+        for (int c = 0; c < kResMaxC; ++c) av[c] = al[cl][c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = r0 + ty * 4 + i;
+          if (row < P.a && col < P.a) {
+            double k = kv[i][j];
+            if (diag && col == row && jitter != nullptr) k = __fma_rn(jscale, jitter[row], k);
+#pragma unroll
+            for (int c = 0; c < kResMaxC; ++c)
+              if (c < nc) dd_add_prod(hi[i][c], lo[i][c], k, av[c]);
+          }
+        }
+      }
+      continue;
+    }
     double xa[4][kMaxN], xb[4][kMaxN], ga[4][kMaxP], ub[4][kMaxP];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -607,6 +648,34 @@ extern "C" int bcbf_gram_resid(const double* X, const double* UH, const double* 
     if (n == 3 && p == 3) gram_resid_kernel<3, 3><<<grid, 256, 0, stream>>>(P, jitter, jitter_scale, alpha, lda, cfirst, ncp, tps, scratch);
     else if (n == 2 && p == 2) gram_resid_kernel<2, 2><<<grid, 256, 0, stream>>>(P, jitter, jitter_scale, alpha, lda, cfirst, ncp, tps, scratch);
     else gram_resid_kernel<0, 0><<<grid, 256, 0, stream>>>(P, jitter, jitter_scale, alpha, lda, cfirst, ncp, tps, scratch);
+    BCBF_LAUNCH_CHECK();
+    gram_resid_finalize_kernel<<<ceil_div((long long)T * kGT * kResMaxC, 256), 256, 0, stream>>>(
+        scratch, S, T * kGT, N, Y, ldy, cfirst, ncp, R, ldr);
+    BCBF_LAUNCH_CHECK();
+  }
+  return BCBF_OK;
+}
+
+extern "C" int bcbf_gram_resid_stored(const double* Kb, int ldk, int N, const double* jitter, double jitter_scale,
+                                      const double* alpha, int lda, const double* Y, int ldy, int nc, double* R, int ldr,
+                                      double* scratch, long long scratch_elems, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BCBF_REQUIRE(Kb && alpha && Y && R && scratch, "bcbf_gram_resid_stored: null pointer");
+  BCBF_REQUIRE(N >= 1 && ldk >= N && nc >= 1 && nc <= kMaxN && lda >= nc && ldy >= nc && ldr >= nc,
+               "bcbf_gram_resid_stored: N=%d ldk=%d nc=%d lda=%d ldy=%d ldr=%d", N, ldk, nc, lda, ldy, ldr);
+  BCBF_REQUIRE(scratch_elems >= bcbf_gram_resid_scratch_elems(N), "bcbf_gram_resid_stored: scratch too small (%lld < %lld)",
+               scratch_elems, bcbf_gram_resid_scratch_elems(N));
+  GramParams P{};
+  P.a = N; P.c = N; P.n = 1; P.p = 1;
+  P.out = const_cast<double*>(Kb);   // read only in the STORED instantiation
+  P.ld = ldk;
+  int S, tps;
+  resid_splits(N, &S, &tps);
+  const int T = (N + kGT - 1) / kGT;
+  for (int cfirst = 0; cfirst < nc; cfirst += kResMaxC) {
+    const int ncp = (nc - cfirst) < kResMaxC ? (nc - cfirst) : kResMaxC;
+    dim3 grid(T, S);
+    gram_resid_kernel<1, 1, true><<<grid, 256, 0, stream>>>(P, jitter, jitter_scale, alpha, lda, cfirst, ncp, tps, scratch);
     BCBF_LAUNCH_CHECK();
     gram_resid_finalize_kernel<<<ceil_div((long long)T * kGT * kResMaxC, 256), 256, 0, stream>>>(
         scratch, S, T * kGT, N, Y, ldy, cfirst, ncp, R, ldr);

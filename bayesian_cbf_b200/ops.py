@@ -76,9 +76,25 @@ def gram_resid(X, UH, B, lengthscale, outputscale, alpha, Y, jitter=None, jitter
     return R
 
 
-def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, jitter_scale=0.0, iters=3):
+def gram_resid_stored(Kb, alpha, Y, jitter=None, jitter_scale=0.0):
+    """The same residual with Kb (>= N x N, lower triangle as gram_train_lower wrote it) read from memory
+    (bcbf_gram_resid_stored): the same result bits as gram_resid."""
+    _req(Kb, alpha, Y, jitter)
+    N, nc = alpha.shape
+    lib = _lib.load()
+    R = torch.zeros(N, nc, dtype=torch.float64, device=Kb.device)
+    ne = lib.bcbf_gram_resid_scratch_elems(N)
+    scratch = torch.empty(ne, dtype=torch.float64, device=Kb.device)
+    check(lib.bcbf_gram_resid_stored(_ptr(Kb), Kb.stride(0), N, _ptr(jitter), float(jitter_scale), _ptr(alpha),
+                                     alpha.stride(0), _ptr(Y), Y.stride(0), nc, _ptr(R), R.stride(0), _ptr(scratch), ne,
+                                     _stream()))
+    return R
+
+
+def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, jitter_scale=0.0, iters=3, store_kb=None):
     """alpha (Npad, nc) = (Kb + jitter)^-1 Y: explicit-inverse product + `iters` compensated refinement steps
-    (bcbf_alpha_refine; reference cholesky_solve, control_affine_model.py:545).  Ypad (Npad, nc), pad rows zero."""
+    (bcbf_alpha_refine[_ws]; reference cholesky_solve, control_affine_model.py:545).  Ypad (Npad, nc), pad rows zero.
+    store_kb: keep a copy of Kb for the residuals (default: when Npad >= 2048) — same result bits either way."""
     _req(X, UH, B, lengthscale, Linv, jitter)
     _req(Ypad, contiguous=False)
     N, n = X.shape
@@ -92,9 +108,12 @@ def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, ji
     lib = _lib.load()
     ne = lib.bcbf_alpha_refine_scratch_elems(N, Npad, ldy)
     scratch = torch.empty(ne, dtype=torch.float64, device=X.device)
-    check(lib.bcbf_alpha_refine(_ptr(X), _ptr(UH), _ptr(B), _ptr(lengthscale), float(outputscale), N, n, p, _ptr(jitter),
-                                float(jitter_scale), _ptr(Linv), Linv.stride(0), Npad, _ptr(Yp), ldy, nc, int(iters),
-                                _ptr(alpha), _ptr(scratch), ne, _stream()))
+    if store_kb is None:
+        store_kb = Npad >= 2048
+    kb = torch.empty(Npad, Npad, dtype=torch.float64, device=X.device) if (store_kb and iters > 0) else None
+    check(lib.bcbf_alpha_refine_ws(_ptr(X), _ptr(UH), _ptr(B), _ptr(lengthscale), float(outputscale), N, n, p, _ptr(jitter),
+                                   float(jitter_scale), _ptr(Linv), Linv.stride(0), Npad, _ptr(Yp), ldy, nc, int(iters),
+                                   _ptr(alpha), _ptr(scratch), ne, _ptr(kb), Npad, _stream()))
     return alpha[:, :nc]
 
 

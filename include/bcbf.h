@@ -86,6 +86,12 @@ int bcbf_gram_resid(const double* X, const double* UH, const double* Bmat, const
                     double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
                     const double* alpha, int lda, const double* Y, int ldy, int nc, double* R, int ldr, double* scratch,
                     long long scratch_elems, void* stream);
+/* The same residual with Kb READ from memory: Kb (N,N; ldk) with its lower triangle as bcbf_gram_train_lower wrote it (the
+ * upper triangle is not touched: entry (i,j), j > i, is read as (j,i)).  Same accumulation order, so the same result
+ * bits as bcbf_gram_resid, at the cost of streaming 2 N^2 doubles instead of evaluating N^2 exponentials.             */
+int bcbf_gram_resid_stored(const double* Kb, int ldk, int N, const double* jitter, double jitter_scale,
+                           const double* alpha, int lda, const double* Y, int ldy, int nc, double* R, int ldr,
+                           double* scratch, long long scratch_elems, void* stream);
 
 /* Cross Gram  Kstar[i, j] = k(X_i, Xq_j)   (control_affine_model.py:536 / :1051, the k_xs / k_sx factor).
  *   X (N,n), Xq (Q,n) -> Kstar (Npad, ldks) row-major with ldks >= Q; rows >= N are written as zero.     */
@@ -175,6 +181,12 @@ int bcbf_alpha_refine(const double* X, const double* UH, const double* Bmat, con
                       double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
                       const double* Linv, int ld, int Npad, const double* Y, int ldy, int nc, int iters, double* alpha,
                       double* scratch, long long scratch_elems, void* stream);
+/* bcbf_alpha_refine with a workspace kb_ws (Npad,Npad; ldk >= Npad) or NULL: Kb is written there once (bcbf_gram_train_lower)
+ * and the `iters` residuals read it (bcbf_gram_resid_stored) instead of re-evaluating it — same alpha, bit for bit.    */
+int bcbf_alpha_refine_ws(const double* X, const double* UH, const double* Bmat, const double* lengthscale,
+                         double outputscale, int N, int n, int p, const double* jitter, double jitter_scale,
+                         const double* Linv, int ld, int Npad, const double* Y, int ldy, int nc, int iters, double* alpha,
+                         double* scratch, long long scratch_elems, double* kb_ws, int ldk, void* stream);
 
 /* Row-major C(M,N) = alpha * op(A) op(B) + beta * C on the FP64 tensor-core GEMM.  op(A) is M x K: transa = 0 ->
  * A stored (M,K), 1 -> stored (K,M);  op(B) is K x N: transb = 0 -> stored (K,N), 1 -> stored (N,K).  M, N, K and

@@ -37,7 +37,7 @@ def gram_train_lower(X, UH, B, lengthscale, outputscale, Npad=None):
     return torch.tril(Kb) + torch.triu(torch.full_like(Kb, float('nan')), 1)   # storage above the diagonal: "untouched"
 
 
-def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, jitter_scale=0.0, iters=3):
+def alpha_refine(X, UH, B, lengthscale, outputscale, Linv, Ypad, jitter=None, jitter_scale=0.0, iters=3, store_kb=None):
     import numpy as np
     N = X.shape[0]
     Kb = _k(X, X, lengthscale, outputscale) * (UH @ B @ UH.T)

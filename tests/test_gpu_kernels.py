@@ -115,6 +115,34 @@ def test_gram_resid_is_the_exact_residual(N, n, m):
     assert ((Y - Kbp @ alpha - R_exact).abs() / scale).max().item() > 1e-18      # (the float64 residual is not)
 
 
+@pytest.mark.parametrize('N,n,m', [(300, 3, 2), (1000, 2, 1), (2111, 3, 2)])
+def test_stored_residual_and_refinement_equal_the_on_the_fly_ones_bit_for_bit(N, n, m):
+    """bcbf_gram_resid_stored reads the lower triangle bcbf_gram_train_lower wrote (garbage in the upper one) and must
+    return the bits of bcbf_gram_resid; bcbf_alpha_refine_ws with and without the Kb workspace likewise."""
+    from bayesian_cbf_b200 import ops
+    X, U, Xdot, hyp, jit, _, _ = _mk(17, N, n, m, 4, box=2.0)
+    UH = O.homogeneous(U)
+    args = (_d(X), _d(UH), _d(hyp.B), _d(hyp.lengthscale), float(hyp.outputscale))
+    Y = _d(O.residual_targets(hyp, UH, Xdot))
+    g = torch.Generator().manual_seed(3)
+    alpha = _d(torch.randn(N, n, generator=g, dtype=torch.float64))
+    Npad = ops.padded(N)
+    Kb = torch.full((Npad, Npad), float('nan'), dtype=torch.float64, device='cuda')
+    Kb = torch.triu(Kb, diagonal=1)                                # NaN strictly above the diagonal, zeros below
+    Kb = Kb + torch.tril(ops.gram_train_lower(*args))              # the lower triangle as the factorisation sees it
+    assert torch.isnan(Kb[0, 1])
+    R1 = ops.gram_resid(*args, alpha, Y, _d(jit), 1e-5)
+    R2 = ops.gram_resid_stored(Kb, alpha, Y, _d(jit), 1e-5)
+    assert torch.equal(R1, R2)
+    L, dinv = ops.potrf_(ops.gram_train_lower(*args), N, _d(jit), 1e-5)
+    Linv = ops.trtri(L, dinv)
+    Yp = torch.zeros(Npad, n, dtype=torch.float64, device='cuda')
+    Yp[:N] = Y
+    a1 = ops.alpha_refine(*args, Linv, Yp, _d(jit), 1e-5, iters=3, store_kb=False)
+    a2 = ops.alpha_refine(*args, Linv, Yp, _d(jit), 1e-5, iters=3, store_kb=True)
+    assert torch.equal(a1, a2)
+
+
 def test_alpha_refine_reaches_the_exact_solution_of_the_factorised_matrix():
     """N = 2048 of the bench workload (cond ~ 4e9): bcbf_alpha_refine (explicit inverse + 2 compensated refinement steps)
     returns the float64 rounding of the exact solution of the system the GPU factorised — closer to it than LAPACK's
