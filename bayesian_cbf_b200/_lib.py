@@ -125,6 +125,7 @@ _SIGNATURES = {
     'bcbf_set_trtri_i8': (c_int, [c_int]),
     'bcbf_set_potrf_i8': (c_int, [c_int]),
     'bcbf_set_potf2_variant': (c_int, [c_int]),
+    'bcbf_set_gemm_tile_policy': (c_int, [c_int]),
     'bcbf_oz_set_cluster': (c_int, [c_int]),
     'bcbf_oz_set_group': (c_int, [c_int]),
     'bcbf_oz_profile_enable': (c_int, [c_int]),

@@ -589,6 +589,13 @@ __global__ void scatter_diag_blocks_kernel(const double* __restrict__ dinv, doub
 
 using namespace bcbf;
 
+// 0: by problem size (default), 1: always 128 x 128 tiles, 2: always 32 x 128 tiles (tests and A/B timing)
+extern "C" int bcbf_set_gemm_tile_policy(int policy) {
+  BCBF_REQUIRE(policy >= 0 && policy <= 2, "bcbf_set_gemm_tile_policy: %d not in 0..2", policy);
+  gemm_tile_policy() = policy;
+  return BCBF_OK;
+}
+
 extern "C" long long bcbf_dinv_elems(int Npad) { return (long long)(Npad / kBlk) * kBlk * kBlk; }
 
 // Look-ahead of the single-matrix factorisation: the serial sweep (single-CTA diagonal factorisations, panel solves) and

@@ -1,6 +1,7 @@
 // FP64 tensor-core (DMMA.8x8x4) tiled GEMM used by the blocked Cholesky, the triangular inverse and the
 // Linv products.  Row-major operands, 128x128x16 CTA tiles, 3-stage cp.async pipeline, 8 warps (2x4),
-// 64x32 warp tiles -> 32 DMMA per k4-step per warp against 12 LDS.64 fragment loads.
+// 64x32 warp tiles -> 32 DMMA per k4-step per warp against 12 LDS.64 fragment loads; a 32x128x16 variant (1x8 warps)
+// for problems of a few tiles, where the machine is otherwise idle and the time is one CTA's latency.
 //
 //   C[M,N] = alpha * opA(A) * opB(B) + beta * C        (batched over blockIdx.z with element strides)
 //
@@ -35,18 +36,25 @@ struct GemmArgs {
 };
 
 constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmStages = 3, kGemmThreads = 256;
+constexpr int kGemmBMSmall = 32;         // row tile of the small-problem variant (see launch_gemm)
 constexpr int kStrideKC = kGemmBK + 4;   // 20
 constexpr int kStrideMN = kGemmBM + 4;   // 132
 constexpr int kTileElems = 128 * kStrideKC;  // 2560 doubles >= 16*132 = 2112
-constexpr int kGemmSmemBytes = kGemmStages * 2 * kTileElems * (int)sizeof(double);  // 122880
+__host__ __device__ constexpr int gemm_tile_elems(int rows) {
+  return rows * kStrideKC > kGemmBK * (rows + 4) ? rows * kStrideKC : kGemmBK * (rows + 4);
+}
+__host__ __device__ constexpr int gemm_smem_bytes(int bm) {
+  return kGemmStages * (gemm_tile_elems(bm) + gemm_tile_elems(kGemmBN)) * (int)sizeof(double);
+}
+constexpr int kGemmSmemBytes = gemm_smem_bytes(kGemmBM);  // 122880
 
-template <bool KC>
+template <bool KC, int R>
 __device__ __forceinline__ void gemm_load_tile(double* s, const double* g, int ld, int r0, int k0, int rmax,
                                                int kmax, int tid) {
-  // KC: tile rows r0..r0+127 (limit rmax) x k0..k0+15 (limit kmax), k contiguous in memory.
+  // KC: tile rows r0..r0+R-1 (limit rmax) x k0..k0+15 (limit kmax), k contiguous in memory.
   // !KC: memory is (K, R): rows k0..k0+15 of length R, r contiguous.
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < R * 8 / kGemmThreads; ++i) {
     int c = tid + i * kGemmThreads;
     if (KC) {
       int row = c >> 3, kc = (c & 7) * 2;
@@ -54,21 +62,29 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* g, int l
       const double* src = g + (long long)(r0 + row) * ld + (k0 + kc);
       cp_async16(s + row * kStrideKC + kc, ok ? src : g, ok);
     } else {
-      int k = c >> 6, rc = (c & 63) * 2;
+      int k = c / (R / 2), rc = (c % (R / 2)) * 2;
       bool ok = (r0 + rc < rmax) && (k0 + k < kmax);
       const double* src = g + (long long)(k0 + k) * ld + (r0 + rc);
-      cp_async16(s + k * kStrideMN + rc, ok ? src : g, ok);
+      cp_async16(s + k * (R + 4) + rc, ok ? src : g, ok);
     }
   }
 }
 
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_f64_kernel(GemmArgs p) {
+// BM = 128: 2 x 4 warps, 64 x 32 warp tiles.  BM = 32 (small problems: a handful of 128 x 128 tiles would leave most of
+// the 148 SMs idle while each CTA spends ~17 us per 128 k): 1 x 8 warps, 32 x 16 warp tiles, four times the CTAs, two
+// CTAs per SM.  BN stays 128, so a CTA still owns complete rows of a 128-wide panel: the in-place panel solve of the
+// Cholesky (C == A, N == K == 128) remains race-free.  Triangular k-ranges are in units of 128-blocks in both variants.
+template <bool A_KC, bool B_KC, int BM>
+__global__ void __launch_bounds__(kGemmThreads, BM == kGemmBM ? 1 : 2) gemm_f64_kernel(GemmArgs p) {
+  constexpr int WARPS_M = BM == kGemmBM ? 2 : 1, WARPS_N = 8 / WARPS_M;
+  constexpr int WTM = BM / WARPS_M, WTN = kGemmBN / WARPS_N, MI = WTM / 8, NJ = WTN / 8;
+  constexpr int TA = gemm_tile_elems(BM), TB = gemm_tile_elems(kGemmBN);
+  constexpr int SA_MN = BM + 4;            // row stride of an (k, m)-ordered A tile: = 4 mod 16 for BM = 32, 128
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   int ti, tj;
-  if (p.tri == kTriLowerOut) {
+  if (p.tri == kTriLowerOut && BM == kGemmBM) {
     // linear index over the lower triangle, largest rows first is not needed (uniform K)
     int t = blockIdx.x;
     int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -80,28 +96,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_f64_kernel(GemmArgs p) {
     ti = blockIdx.x / p.ntiles;
     tj = blockIdx.x % p.ntiles;
   }
+  const int m0 = ti * BM, n0 = tj * kGemmBN;
+  const int bi = m0 / kGemmBM;             // 128-block row of this tile
+  if (p.tri == kTriLowerOut && tj > bi) return;   // (small variant: rectangular grid, tiles above the diagonal idle)
   const double* A = p.A + (long long)blockIdx.z * p.sA;
   const double* B = p.B + (long long)blockIdx.z * p.sB;
   double* C = p.C + (long long)blockIdx.z * p.sC;
-  const int m0 = ti * kGemmBM, n0 = tj * kGemmBN;
   int kbeg = 0, kend = p.K;
-  if (p.tri == kTriALower) kend = min(p.K, (ti + 1) * kGemmBM);
-  if (p.tri == kTriAUpper) kbeg = ti * kGemmBM;
+  if (p.tri == kTriALower) kend = min(p.K, (bi + 1) * kGemmBM);
+  if (p.tri == kTriAUpper) kbeg = bi * kGemmBM;
   if (p.tri == kTriBLower) kbeg = tj * kGemmBN;
   const int nk = (kend - kbeg + kGemmBK - 1) / kGemmBK;
 
-  double acc[8][4][2];
+  double acc[MI][NJ][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto stageA = [&](int s) { return smem + (s * 2) * kTileElems; };
-  auto stageB = [&](int s) { return smem + (s * 2 + 1) * kTileElems; };
+  auto stageA = [&](int s) { return smem + s * (TA + TB); };
+  auto stageB = [&](int s) { return smem + s * (TA + TB) + TA; };
   auto load = [&](int kt, int s) {
     int k0 = kbeg + kt * kGemmBK;
-    gemm_load_tile<A_KC>(stageA(s), A, p.lda, m0, k0, p.M, kend, tid);
-    gemm_load_tile<B_KC>(stageB(s), B, p.ldb, n0, k0, p.N, kend, tid);
+    gemm_load_tile<A_KC, BM>(stageA(s), A, p.lda, m0, k0, p.M, kend, tid);
+    gemm_load_tile<B_KC, kGemmBN>(stageB(s), B, p.ldb, n0, k0, p.N, kend, tid);
   };
 
 #pragma unroll
@@ -122,34 +140,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_f64_kernel(GemmArgs p) {
     const double* Bs = stageB(kt % kGemmStages);
 #pragma unroll
     for (int k4 = 0; k4 < kGemmBK / 4; ++k4) {
-      double a[8], b[4];
+      double a[MI], b[NJ];
       const int kk = k4 * 4 + lk;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int row = wm * 64 + i * 8 + lr;
-        a[i] = A_KC ? As[row * kStrideKC + kk] : As[kk * kStrideMN + row];
+      for (int i = 0; i < MI; ++i) {
+        int row = wm * WTM + i * 8 + lr;
+        a[i] = A_KC ? As[row * kStrideKC + kk] : As[kk * SA_MN + row];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int col = wn * 32 + j * 8 + lr;
+      for (int j = 0; j < NJ; ++j) {
+        int col = wn * WTN + j * 8 + lr;
         b[j] = B_KC ? Bs[col * kStrideKC + kk] : Bs[kk * kStrideMN + col];
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
   cp_async_wait<0>();
   __syncthreads();  // every operand load of this CTA has landed: in-place C (== A or B block) is now safe
 
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int row = m0 + wm * 64 + i * 8 + lr;
+  for (int i = 0; i < MI; ++i) {
+    int row = m0 + wm * WTM + i * 8 + lr;
     if (row >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int col = n0 + wn * 32 + j * 8 + lk * 2;
+    for (int j = 0; j < NJ; ++j) {
+      int col = n0 + wn * WTN + j * 8 + lk * 2;
       if (col >= p.N) continue;
       double* dst = C + (long long)row * p.ldc + col;
       double2 v;
@@ -165,19 +183,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_f64_kernel(GemmArgs p) {
   }
 }
 
+// 0: choose by problem size (default), 1: always 128-row tiles, 2: always the small variant (tests, A/B timing)
+inline int& gemm_tile_policy() {
+  static int policy = 0;
+  return policy;
+}
+
 // Host launcher.  Returns a cudaError_t-like int through BCBF conventions in the callers.
 template <bool A_KC, bool B_KC>
 inline cudaError_t launch_gemm(GemmArgs a, int batch, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(gemm_f64_kernel<A_KC, B_KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kGemmSmemBytes);
-  if (e != cudaSuccess) return e;
   a.mtiles = (a.M + kGemmBM - 1) / kGemmBM;
   a.ntiles = (a.N + kGemmBN - 1) / kGemmBN;
   if (a.mtiles <= 0 || a.ntiles <= 0 || batch <= 0) return cudaSuccess;
   long long tiles = (a.tri == kTriLowerOut) ? (long long)a.mtiles * (a.mtiles + 1) / 2
                                              : (long long)a.mtiles * a.ntiles;
+  // under half a wave of 128 x 128 tiles: quarter the row tile (4x the CTAs, 2 per SM)
+  const int policy = gemm_tile_policy();
+  const bool small = policy == 2 || (policy == 0 && tiles * batch <= 74);
+  if (small) {
+    constexpr int smem = gemm_smem_bytes(kGemmBMSmall);
+    cudaError_t e = cudaFuncSetAttribute(gemm_f64_kernel<A_KC, B_KC, kGemmBMSmall>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    a.mtiles = (a.M + kGemmBMSmall - 1) / kGemmBMSmall;
+    dim3 grid((unsigned)((long long)a.mtiles * a.ntiles), 1, (unsigned)batch);
+    gemm_f64_kernel<A_KC, B_KC, kGemmBMSmall><<<grid, kGemmThreads, smem, stream>>>(a);
+    ++g_launch_count;
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaFuncSetAttribute(gemm_f64_kernel<A_KC, B_KC, kGemmBM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
   dim3 grid((unsigned)tiles, 1, (unsigned)batch);
-  gemm_f64_kernel<A_KC, B_KC><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(a);
+  gemm_f64_kernel<A_KC, B_KC, kGemmBM><<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(a);
   ++g_launch_count;
   return cudaGetLastError();
 }

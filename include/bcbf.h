@@ -194,6 +194,10 @@ int bcbf_alpha_refine_ws(const double* X, const double* UH, const double* Bmat, 
  * products of custom_predict: kb*^T alpha (:547), v^T v' (:586), kb*^T.reshape(bp,N) @ Bdagger (:1079-1088).   */
 int bcbf_gemm(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
               int ldb, double beta, double* C, int ldc, void* stream);
+/* Tile shape of the FP64 GEMM: 0 = by problem size (default: 32 x 128 row tiles when the problem has at most 74 tiles of
+ * 128 x 128, i.e. would leave most SMs idle), 1 = always 128 x 128, 2 = always 32 x 128.  Results are identical to the
+ * last bit either way (same k order per output element); the knob exists for tests and timing.                        */
+int bcbf_set_gemm_tile_policy(int policy);
 
 /* R independent products, element strides sA / sB / sC between consecutive operands (even). */
 int bcbf_gemm_batched(int transa, int transb, int M, int N, int K, double alpha, const double* A, int lda, long long sA,

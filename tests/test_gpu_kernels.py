@@ -143,6 +143,48 @@ def test_stored_residual_and_refinement_equal_the_on_the_fly_ones_bit_for_bit(N,
     assert torch.equal(a1, a2)
 
 
+def test_small_tile_gemm_variant_returns_the_same_bits():
+    """The 32 x 128 row-tile variant of the FP64 GEMM (picked for problems of a few tiles) against the 128 x 128 one:
+    general products in the four storage orders with ragged extents, the triangular products, and a whole blocked
+    Cholesky + triangular inverse (in-place panel solves, SYRK updates, k-range masks) — bit for bit."""
+    from bayesian_cbf_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64).cuda()
+
+    def run(policy):
+        _lib.check(lib.bcbf_set_gemm_tile_policy(policy))
+        out = []
+        try:
+            for (M, N, K) in ((2, 802, 256), (300, 130, 260), (97, 33, 515)):
+                for ta in (False, True):
+                    for tb in (False, True):
+                        A = rnd(*((K, M) if ta else (M, K)))
+                        B = rnd(*((N, K) if tb else (K, N)))
+                        C = rnd(M, N)
+                        out.append(ops.gemm(A, B, transa=ta, transb=tb, alpha=-0.5, beta=1.0, C=C))
+            n = 640
+            Mx = rnd(n, n)
+            S = Mx @ Mx.t() + n * torch.eye(n, dtype=torch.float64, device='cuda')
+            L, dinv = ops.potrf_(S.clone(), n, None, 0.0)
+            Linv = ops.trtri(L, dinv)
+            Bm = rnd(n, 34)
+            out += [L.clone(), Linv, ops.trmm_lower(Linv, Bm), ops.trmm_lower(Linv, Bm, trans=True)]
+        finally:
+            _lib.check(lib.bcbf_set_gemm_tile_policy(0))
+        return out
+
+    g.manual_seed(5)
+    big = run(1)
+    g.manual_seed(5)
+    small = run(2)
+    assert len(big) == len(small) == 16
+    for a, b in zip(big, small):
+        assert torch.equal(a, b)
+    L, Linv = big[12], big[13]
+    assert (torch.tril(L) @ Linv - torch.eye(640, dtype=torch.float64, device='cuda')).abs().max().item() < 1e-10
+
+
 def test_alpha_refine_reaches_the_exact_solution_of_the_factorised_matrix():
     """N = 2048 of the bench workload (cond ~ 4e9): bcbf_alpha_refine (explicit inverse + 2 compensated refinement steps)
     returns the float64 rounding of the exact solution of the system the GPU factorised — closer to it than LAPACK's
