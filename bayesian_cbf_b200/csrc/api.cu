@@ -235,18 +235,26 @@ __global__ void __launch_bounds__(256) tri_mv_n_kernel(const double* __restrict_
     }
 }
 
-// op(T) = T^T: thread per column j of a 128-column strip, rows split over blockIdx.y; partial[split][j][c]
-constexpr int kMvRows = 1024;
+// op(T) = T^T: thread per column j of a 128-column strip, rows split over blockIdx.y (mv_rows(Npad) rows per split, a
+// function of Npad alone so that the summation order — and the result bits — depend on nothing else); partial[split][j][c]
+static int mv_rows(int Npad) {
+  // enough (strip, split) CTAs to cover the machine at small Npad: 1024 rows per split from Npad = 16384 down to 64 at
+  // Npad <= 1024 (Npad = 256: 2 x 4 CTAs of 64 rows instead of 2 CTAs walking 256 rows, 26 us -> ~8 us)
+  long long r = (long long)Npad * Npad / (128LL * 148LL);
+  int rows = 64;
+  while (rows * 2 <= r && rows < 1024) rows *= 2;
+  return rows;
+}
 __global__ void __launch_bounds__(128) tri_mv_t_kernel(const double* __restrict__ T, int ld, int Npad,
                                                        const double* __restrict__ x, int ldx, int nc,
-                                                       double* __restrict__ partial) {
+                                                       double* __restrict__ partial, int kMvRows) {
   __shared__ double xs[64 * kMvMaxC];
   const int j = blockIdx.x * 128 + threadIdx.x;
   const int i0 = max(blockIdx.y * kMvRows, blockIdx.x * 128), i1 = min(Npad, (blockIdx.y + 1) * kMvRows);
   double acc[kMvMaxC];
 #pragma unroll
   for (int c = 0; c < kMvMaxC; ++c) acc[c] = 0.0;
-  for (int ib = i0; ib < i1; ib += 64) {   // i0 and i1 are multiples of 128
+  for (int ib = i0; ib < i1; ib += 64) {   // i0 and i1 are multiples of 64
     __syncthreads();
     for (int e = threadIdx.x; e < 64 * nc; e += 128) xs[(e / nc) * kMvMaxC + e % nc] = x[(long long)(ib + e / nc) * ldx + e % nc];
     __syncthreads();
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(128) tri_mv_t_kernel(const double* __restrict_
 
 __global__ void tri_mv_t_finalize_kernel(const double* __restrict__ partial, int Npad, int nc, int nsplit, int ldx,
                                          double alpha, double beta, const double* __restrict__ y0,
-                                         double* __restrict__ y) {
+                                         double* __restrict__ y, int kMvRows) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Npad * nc) return;
   const int j = static_cast<int>(idx / nc), c = static_cast<int>(idx % nc);
@@ -536,7 +544,7 @@ extern "C" int bcbf_model_alloc_state(bcbf_model* m, const bcbf_hyper* hyp, int 
   return BCBF_OK;
 }
 
-// y = beta * y0 + alpha * op(T) x  (y0 may be null); `partial` holds ceil(Npad / 1024) * Npad * nc doubles
+// y = beta * y0 + alpha * op(T) x  (y0 may be null); `partial` holds ceil(Npad / mv_rows(Npad)) * Npad * nc doubles
 static int tri_mv(const double* T, int ld, int Npad, int trans, const double* x, int ldx, int nc, double alpha, double beta,
                   const double* y0, double* y, double* partial, cudaStream_t s) {
   if (!trans) {
@@ -544,17 +552,17 @@ static int tri_mv(const double* T, int ld, int Npad, int trans, const double* x,
     BCBF_LAUNCH_CHECK();
     return BCBF_OK;
   }
-  const int nsplit = ceil_div(Npad, kMvRows);
-  tri_mv_t_kernel<<<dim3(Npad / 128, nsplit), 128, 0, s>>>(T, ld, Npad, x, ldx, nc, partial);
+  const int rows = mv_rows(Npad), nsplit = ceil_div(Npad, rows);
+  tri_mv_t_kernel<<<dim3(Npad / 128, nsplit), 128, 0, s>>>(T, ld, Npad, x, ldx, nc, partial, rows);
   BCBF_LAUNCH_CHECK();
   tri_mv_t_finalize_kernel<<<ceil_div((long long)Npad * nc, 256), 256, 0, s>>>(partial, Npad, nc, nsplit, ldx, alpha, beta,
-                                                                               y0, y);
+                                                                               y0, y, rows);
   BCBF_LAUNCH_CHECK();
   return BCBF_OK;
 }
 
 extern "C" long long bcbf_alpha_refine_scratch_elems(int N, int Npad, int ldy) {
-  return (long long)Npad * ldy * (2 + ceil_div(Npad, kMvRows)) + bcbf_gram_resid_scratch_elems(N);
+  return (long long)Npad * ldy * (2 + ceil_div(Npad, mv_rows(Npad))) + bcbf_gram_resid_scratch_elems(N);
 }
 
 // alpha = Kb^-1 Y by iterative refinement (include/bcbf.h): start alpha0 = Linv^T (Linv Y), then `iters` times
@@ -579,7 +587,7 @@ extern "C" int bcbf_alpha_refine_ws(const double* X, const double* UH, const dou
   double* t = scratch;
   double* r = t + (size_t)Npad * ldy;
   double* part = r + (size_t)Npad * ldy;
-  double* rs = part + (size_t)ceil_div(Npad, kMvRows) * Npad * ldy;
+  double* rs = part + (size_t)ceil_div(Npad, mv_rows(Npad)) * Npad * ldy;
   const long long rs_elems = bcbf_gram_resid_scratch_elems(N);
   int rc;
   if ((rc = tri_mv(Linv, ld, Npad, 0, Y, ldy, ldy, 1.0, 0.0, nullptr, t, part, s))) return rc;

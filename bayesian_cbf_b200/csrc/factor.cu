@@ -362,24 +362,29 @@ __device__ __forceinline__ void inv_level(double* __restrict__ a, const double* 
 // lower triangle of the block and 1 / diag in invd[c0 ..].  Returns 0 or the 1-based index of a non-positive pivot.
 __device__ __forceinline__ int factor_diag16(double* __restrict__ a, double* __restrict__ invd, int c0, int lane,
                                              bool apply_update) {
-  const int rl = lane & (kSB - 1);
+  // Both half-warps hold row rl = lane & 15 of the block (the upper half is a working copy: it halves the update below and
+  // is otherwise redundant).  Entries above the diagonal (k > rl) are carried as don't-care values — never selected out —
+  // so that the 16-pivot chain is straight-line code: they are read by no lane (pivot j comes from lane j's r[j],
+  // multiplier L[k][j] from lane k's r[j], k > j) and are not stored.
+  const int rl = lane & (kSB - 1), half = lane >> 4;
   double r[kSB];
 #pragma unroll
-  for (int k = 0; k < kSB; ++k) r[k] = (k <= rl) ? a[(c0 + rl) * kPad + c0 + k] : 0.0;
+  for (int k = 0; k < kSB; ++k) r[k] = a[(c0 + rl) * kPad + c0 + k];
   if (apply_update) {      // a[c0+rl][c0+k] -= sum_t P[c0+rl][t] P[c0+k][t],  P = panel columns c0-16 .. c0-1
-    double prow[kSB];
+    constexpr int HT = kSB / 2;          // each half-warp sums 8 of the 16 terms; the halves are added in a fixed order
+    double prow[HT];
 #pragma unroll
-    for (int t = 0; t < kSB; ++t) prow[t] = a[(c0 + rl) * kPad + c0 - kSB + t];
+    for (int t = 0; t < HT; ++t) prow[t] = a[(c0 + rl) * kPad + c0 - kSB + half * HT + t];
 #pragma unroll
     for (int k = 0; k < kSB; ++k) {
       double s = 0.0;
 #pragma unroll
-      for (int t = 0; t < kSB; ++t) s = fma(prow[t], a[(c0 + k) * kPad + c0 - kSB + t], s);
-      if (k <= rl) r[k] -= s;
+      for (int t = 0; t < HT; ++t) s = fma(prow[t], a[(c0 + k) * kPad + c0 - kSB + half * HT + t], s);
+      const double o = __shfl_xor_sync(0xffffffffu, s, 16);
+      r[k] -= (half == 0) ? (s + o) : (o + s);      // low half + high half in both copies: identical bits
     }
   }
   int bad = 0;
-  double myinv = 0.0;
 #pragma unroll
   for (int j = 0; j < kSB; ++j) {
     double djj = __shfl_sync(0xffffffffu, r[j], j);
@@ -388,13 +393,13 @@ __device__ __forceinline__ int factor_diag16(double* __restrict__ a, double* __r
       djj = __longlong_as_double(0x7ff8000000000000LL);
     }
     const double inv = rsqrt(djj);
-    if (rl == j) { r[j] = djj * inv; myinv = inv; }
-    else if (rl > j) r[j] = r[j] * inv;
+    if (lane == j) invd[c0 + j] = inv;
+    r[j] *= inv;                         // lane j: djj / sqrt(djj) = L[j][j]; lanes > j: L[rl][j]
 #pragma unroll
     for (int k = 0; k < kSB; ++k) {
       if (k > j) {
         const double lkj = __shfl_sync(0xffffffffu, r[j], k);
-        if (rl >= k) r[k] = fma(-r[j], lkj, r[k]);
+        r[k] = fma(-r[j], lkj, r[k]);
       }
     }
   }
@@ -402,7 +407,6 @@ __device__ __forceinline__ int factor_diag16(double* __restrict__ a, double* __r
 #pragma unroll
     for (int k = 0; k < kSB; ++k)
       if (k <= lane) a[(c0 + lane) * kPad + c0 + k] = r[k];
-    invd[c0 + lane] = myinv;
   }
   return bad;
 }
