@@ -230,9 +230,29 @@ class ControlAffineRegressor(DynamicsModel):
     def state_size(self):
         return self.x_dim
 
+    def _params(self):
+        """The model's parameters through cached (module, name) slots: the module tree is fixed after construction, and
+        reading the slots sees re-assigned Parameter objects, unlike a cached list; `model.parameters()` walks the tree
+        (~40 us here) and used to run several times per predict."""
+        slots = getattr(self, '_param_slots', None)
+        if slots is None or slots[0] is not self.model:
+            found = []
+            for mod in self.model.modules():
+                for name in mod._parameters:
+                    if mod._parameters[name] is not None:
+                        found.append((mod, name))
+            seen, uniq = set(), []
+            for mod, name in found:
+                prm = mod._parameters[name]
+                if id(prm) not in seen:
+                    seen.add(id(prm))
+                    uniq.append((mod, name))
+            self._param_slots = slots = (self.model, uniq)
+        return [mod._parameters[name] for mod, name in slots[1]]
+
     @property
     def dtype(self):
-        return next(self.model.parameters()).dtype
+        return self._params()[0].dtype
 
     def to(self, dtype=torch.float64):
         if dtype is torch.float64:
@@ -290,7 +310,7 @@ class ControlAffineRegressor(DynamicsModel):
         parameter changes (in-place updates bump `_version`; re-assignment changes the object): the constrained values
         cost ~15 tiny launches and one device->host read (the outputscale), which used to be paid on every predict."""
         m = self.model
-        key = tuple((id(p), p._version, p.dtype, p.device) for p in m.parameters())
+        key = tuple((id(p), p._version, p.dtype, p.device) for p in self._params())
         hc = getattr(self, '_hyper_cache', None)
         if hc is None or hc[0] != key:
             ls = m.input_covar.base_kernel.lengthscale.detach().reshape(-1).double().expand(self.x_dim).contiguous()
@@ -493,7 +513,12 @@ class ControlAffineRegressor(DynamicsModel):
             eps = eps.to(device=X64.device, dtype=torch.float64).contiguous()
             Kb = ops.gram_train_lower(X64, UH64, B64, ls, s)
             try:
-                L, dinv = ops.potrf_(Kb, N, eps, factor)
+                # the inverse is queued BEFORE the factor's status is read back (the read synchronises): a failed factor
+                # is all-NaN, its inverse is harmless, and the device does not idle while the host comes back
+                info = torch.zeros(1, dtype=torch.int32, device=X64.device)
+                L, dinv = ops.potrf_(Kb, N, eps, factor, check_pd=False, info_out=info)
+                Linv = ops.trtri(L, dinv)
+                ops.check_info(info)
                 break
             except RuntimeError as e:
                 if ntry == cholesky_tries - 1:
@@ -501,7 +526,7 @@ class ControlAffineRegressor(DynamicsModel):
                 LOG.warning("Cholesky failed with perturb={} on error {}".format(factor, str(e)))
                 factor = factor * cholesky_perturb_scale
         self._cache['_Lpad'] = L
-        self._cache['_Linv'] = ops.trtri(L, dinv)
+        self._cache['_Linv'] = Linv
         self._cache['_jitter'] = (eps, factor)          # what was added to the diagonal: the alpha refinement needs it
         return L[:N, :N]
 
@@ -658,8 +683,10 @@ class ControlAffineRegressor(DynamicsModel):
         return mean.to(out_dt), torch_kron(scalar_var.unsqueeze(0), A.unsqueeze(0)).to(out_dt)
 
     # ---- matrix form (class Exact in the reference; kept on the base class so that predict() can use it) ----------
-    def _custom_predict_matrix(self, Xtest_in, Xtestp_in=None, compute_cov=True, _out_jitter=True):
-        """M_k (b,n,p), A (n,n), B_k (b,b',p,p)  (reference :983-1096)."""
+    def _custom_predict_matrix(self, Xtest_in, Xtestp_in=None, compute_cov=True, _out_jitter=True, _pending=None,
+                               _psd_start_try=0):
+        """M_k (b,n,p), A (n,n), B_k (b,b',p,p)  (reference :983-1096).  _pending: a list; when given, the status read of
+        the output make_psd is deferred and its check appended for the caller to run last (custom_predict_fullmat)."""
         _need_cuda(self.device)
         Xtest = self._ensure_device_dtype(Xtest_in)
         Xtestp = self._ensure_device_dtype(Xtestp_in) if Xtestp_in is not None else Xtest
@@ -700,22 +727,40 @@ class ControlAffineRegressor(DynamicsModel):
         else:
             V = ops.trmm_lower(Linv, frakB.contiguous())
             BkXX = ops.gemm(V, V, transa=True, alpha=-1.0, beta=1.0, C=KB)
-        if _out_jitter:
-            BkXX, _ = self._make_psd_output(BkXX)                           # (:1089)
+        if _out_jitter and _pending is not None and not diff:
+            BkXX, _, chk = self._make_psd_output(BkXX, start_try=_psd_start_try, defer=True)
+            _pending.append(chk)
+        elif _out_jitter:
+            BkXX, _ = self._make_psd_output(BkXX, start_try=_psd_start_try)  # (:1089)
         BkXX = BkXX.reshape(b, p, bp_, p).transpose(1, 2)                   # (:1091)
         return mean_k.to(out_dt), A.to(out_dt), BkXX.to(out_dt)
 
-    def _make_psd_output(self, M):
-        """The reference's second make_psd (:1089): random jitter ADDED to the returned covariance, retried x10 until
-        the blocked Cholesky accepts it."""
+    def _make_psd_output(self, M, start_try=0, defer=False):
+        """The reference's second make_psd (:1089): random jitter ADDED to the returned covariance, retried x10 (factor
+        1e-5 * 10^t) until the blocked Cholesky accepts it.  defer=True: the first attempt's status is not read back here;
+        returns (Mp, L, pending) with `pending()` -> True when that attempt succeeded — the caller queues the rest of its
+        work first and reads the status last, so the device does not idle behind the read (a failed attempt is redone by
+        the caller with start_try + 1)."""
         n = M.shape[0]
-        factor = 1e-5
-        for ntry in range(10):
+        factor = 1e-5 * 10 ** start_try
+        for ntry in range(start_try, 10):
             eps = next(self._jitter_source) if self._jitter_source is not None else _draw_jitter(n, self.dtype)
             eps = eps.to(device=M.device, dtype=torch.float64)
             Mp = M + factor * torch.diag(eps)
             buf = torch.eye(ops.padded(n), dtype=torch.float64, device=M.device)
             buf[:n, :n] = Mp.detach()
+            if defer:
+                info = torch.zeros(1, dtype=torch.int32, device=M.device)
+                L, _ = ops.potrf_(buf, n, None, 0.0, check_pd=False, info_out=info)
+
+                def pending(factor=factor, info=info):
+                    try:
+                        ops.check_info(info)
+                        return True
+                    except RuntimeError as e:
+                        LOG.warning("Cholesky failed with perturb={} on error {}".format(factor, str(e)))
+                        return False
+                return Mp, L[:n, :n], pending
             try:
                 L, _ = ops.potrf_(buf, n, None, 0.0)
                 return Mp, L[:n, :n]
@@ -763,13 +808,23 @@ class ControlAffineRegressor(DynamicsModel):
     def custom_predict_fullmat(self, Xtest_in, Xtestp_in=None):
         """vec F(x) in (b,p,n) order and its (bpn, bpn) covariance (reference :963-980)."""
         Xtest = self._ensure_device_dtype(Xtest_in)
-        meanFX, A, BkXX = self._custom_predict_matrix(Xtest_in, Xtestp_in, compute_cov=True)
-        assert not torch.isnan(meanFX).any()
         b, p = Xtest.shape[0], 1 + self.u_dim
-        assert meanFX.shape == (b, self.x_dim, p)
-        meanFX = meanFX.transpose(-2, -1)
-        var_FX = torch_kron(BkXX.transpose(2, 1).reshape(b * p, b * p), A, batch_dims=0)
-        return meanFX.reshape(-1), var_FX
+        for start_try in range(10):
+            # every launch of the call is queued before the two status reads (output make_psd, NaN check): each read
+            # synchronises, and the device would otherwise idle while the host queues what follows
+            pending = []
+            meanFX, A, BkXX = self._custom_predict_matrix(Xtest_in, Xtestp_in, compute_cov=True, _pending=pending,
+                                                          _psd_start_try=start_try)
+            assert meanFX.shape == (b, self.x_dim, p)
+            nan_mean = torch.isnan(meanFX).any()
+            mean_out = meanFX.transpose(-2, -1).reshape(-1)
+            var_FX = torch_kron(BkXX.transpose(2, 1).reshape(b * p, b * p), A, batch_dims=0)
+            if all(chk() for chk in pending):
+                break
+            if start_try == 9:
+                raise RuntimeError("make_psd: the output covariance is not positive definite after 10 perturbations")
+        assert not bool(nan_mean)
+        return mean_out, var_FX
 
     def predict(self, Xtest_in, return_cov=True):
         """mean F(x)^T (b,p,n) and covariance (bpn,bpn) on the INPUT's device / dtype (reference :343-364; there the

@@ -95,6 +95,10 @@ def potrf_(A, N, jitter=None, jitter_scale=1e-5, check_pd=True, info_out=None):
     return A, L      # the "dinv" slot carries L for the fake trtri
 
 
+def check_info(info):
+    return None          # the fake potrf_ raises at once
+
+
 def trtri(L, dinv):
     return torch.linalg.solve_triangular(L, torch.eye(L.shape[0], dtype=torch.float64), upper=False)
 
@@ -170,7 +174,7 @@ def installed(monkeypatch):
     import bayesian_cbf_b200.gp_modules as gm
     from bayesian_cbf_b200 import ops
     me = globals()
-    for name in ('padded', 'query_pad', 'gram_train', 'gram_train_lower', 'alpha_refine', 'ca_weight', 'cross_gram', 'gram_ca', 'rbf_blocks', 'potrf_', 'trtri',
+    for name in ('padded', 'query_pad', 'gram_train', 'gram_train_lower', 'alpha_refine', 'ca_weight', 'cross_gram', 'gram_ca', 'rbf_blocks', 'potrf_', 'check_info', 'trtri',
                  'trmm_lower', 'gemm', 'posterior_blocks', 'contract_u', 'socp_factor', 'cbc1_terms',
                  'gram_train_backward', 'socp_solve', 'oz_max_npad', 'oz_split_factor', 'posterior_blocks_i8',
                  'oz_gemm_tn'):

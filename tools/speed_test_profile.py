@@ -22,6 +22,7 @@ def main():
     ap.add_argument('--series', default='matrix')
     ap.add_argument('--dtype', default='float32')
     ap.add_argument('--number', type=int, default=100)
+    ap.add_argument('--cprofile', action='store_true', help='host-side profile of 200 calls instead of the device timeline')
     a = ap.parse_args()
     from bayesian_cbf_b200 import control_affine_model as cam
     classes = dict(matrix=cam.ControlAffineRegressorExact, vector=cam.ControlAffineRegressorVector)
@@ -46,6 +47,19 @@ def main():
         torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / a.number
     print(json.dumps(dict(series=a.series, N=a.N, wall_ms_per_call=wall * 1e3)))
+    if a.cprofile:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(200):
+            stmt()
+        torch.cuda.synchronize()
+        pr.disable()
+        st = pstats.Stats(pr)
+        st.sort_stats('tottime').print_stats(45)
+        st.sort_stats('cumulative').print_stats(45)
+        return
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         stmt()
