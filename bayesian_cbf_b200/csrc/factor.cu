@@ -291,68 +291,62 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
 //      current panel — the 16-pivot chain is off the other warps' path.  The panel solve is a forward substitution per
 //      row (no inverse of the diagonal block needed), so the 16x16 inverses leave the serial chain:
 //   A' all eight 16x16 diagonal inverses at once, one warp each.
-//   B  inverse by recursive doubling, X21 = -X22 (L21 X11) for blocks of 16, 32, 64: three levels of two register-tiled
-//      products with every thread busy (critical path 224 k-steps instead of 560); column tiles are strided so that the
-//      shared-memory reads of a half-warp fall into distinct banks.
+//   B  inverse by recursive doubling, X21 = -X22 (L21 X11) for blocks of 16, 32, 64: three levels of two products on
+//      8 x 8 DMMA tiles (inv_level).
 // Same storage convention (L in the lower triangle of `a`, strictly-lower X transposed into the upper triangle, diagonal of
 // X in xd), same outputs, same failure protocol.
 constexpr int kTS = 65;                      // row stride of the 64 x 64 scratch of phase B
 constexpr int kT2Elems = 64 * kTS;
 
+// One level of the recursive-doubling inverse, X21 = -X22 (L21 X11) for every pair of half-size H, on the FP64 tensor
+// pipe: 8 x 8 output tiles, one warp per tile at a time, DMMA.8x8x4 with the operands gathered straight from the packed
+// storage (L below the diagonal, X transposed above it, diag(X) in xd).  Against the 4 x 4 register-tile FMA version this
+// issues a quarter of the instructions per multiply-add, which is what a 2-warps-per-scheduler kernel is short of
+// (round-2 ncu: phase B was 34 % of the kernel at 12x its FMA floor).  Two accumulator pairs (even / odd k-steps) halve
+// the dependent DMMA chain; the triangular operands shorten the k range (k >= column tile for X11, k <= row tile for X22).
 template <int H>
 __device__ __forceinline__ void inv_level(double* __restrict__ a, const double* __restrict__ xd, double* __restrict__ T,
                                           int tid) {
-  constexpr int NPR = kBlk / (2 * H);        // pairs at this level
-  constexpr int TT = H / 4;                  // 4x4 tiles per edge; thread tile = rows 4 ti + e, columns tj + TT f
-  for (int t = tid; t < NPR * TT * TT; t += 256) {      // T_p = L21_p X11_p
+  constexpr int NPR = kBlk / (2 * H), TT = H / 8, NT = NPR * TT * TT;
+  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+  for (int t = warp; t < NT; t += 8) {       // T_p = L21_p X11_p
     const int pr = t / (TT * TT), tt = t % (TT * TT), ti = tt / TT, tj = tt % TT;
     const int base = pr * 2 * H;
-    double acc[4][4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-#pragma unroll
-      for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
-    for (int k = tj; k < H; ++k) {           // X11 is lower triangular: X11[k][c] = 0 for k < c, smallest column is tj
-      double va[4], vb[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) va[e] = a[(base + H + 4 * ti + e) * kPad + base + k];
-#pragma unroll
-      for (int f = 0; f < 4; ++f) vb[f] = inv_get(a, xd, base + k, base + tj + TT * f);
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vb[f], acc[e][f]);
+    const int row = base + H + 8 * ti + lr;  // A fragment: L21[row][k]
+    const int col = base + 8 * tj + lr;      // B fragment: X11[k][col]
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    for (int k4 = 2 * tj; k4 < H / 4; k4 += 2) {
+      const int ka = base + 4 * k4 + lk, kb = ka + 4;
+      const double a0 = a[row * kPad + ka], a1 = a[row * kPad + kb];
+      const double b0 = ka > col ? a[col * kPad + ka] : (ka == col ? xd[ka] : 0.0);
+      const double b1 = kb > col ? a[col * kPad + kb] : (kb == col ? xd[kb] : 0.0);
+      dmma884(c0, c1, a0, b0);
+      dmma884(d0, d1, a1, b1);
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-#pragma unroll
-      for (int f = 0; f < 4; ++f) T[(pr * H + 4 * ti + e) * kTS + tj + TT * f] = acc[e][f];
+    double* dst = T + (pr * H + 8 * ti + lr) * kTS + 8 * tj + 2 * lk;
+    dst[0] = c0 + d0;
+    dst[1] = c1 + d1;
   }
   __syncthreads();
-  for (int t = tid; t < NPR * TT * TT; t += 256) {      // X21_p = -X22_p T_p
+  for (int t = warp; t < NT; t += 8) {       // X21_p = -X22_p T_p
     const int pr = t / (TT * TT), tt = t % (TT * TT), ti = tt / TT, tj = tt % TT;
     const int base = pr * 2 * H;
-    double acc[4][4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-#pragma unroll
-      for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
-    for (int k = 0; k <= 4 * ti + 3; ++k) {  // X22 is lower triangular: X22[r][k] = 0 for k > r
-      double va[4], vb[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) va[e] = inv_get(a, xd, base + H + 4 * ti + e, base + H + k);
-#pragma unroll
-      for (int f = 0; f < 4; ++f) vb[f] = T[(pr * H + k) * kTS + tj + TT * f];
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int f = 0; f < 4; ++f) acc[e][f] = fma(va[e], vb[f], acc[e][f]);
+    const int row = base + H + 8 * ti + lr;  // A fragment: X22[row][k], stored at a[k][row] for row > k
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    for (int k4 = 0; k4 < 2 * (ti + 1); k4 += 2) {
+      const int kl = 4 * k4 + lk;            // k inside the pair's second half
+      const int ka = base + H + kl, kb = ka + 4;
+      const double a0 = row > ka ? a[ka * kPad + row] : (row == ka ? xd[row] : 0.0);
+      const double a1 = row > kb ? a[kb * kPad + row] : (row == kb ? xd[row] : 0.0);
+      const double b0 = T[(pr * H + kl) * kTS + 8 * tj + lr];
+      const double b1 = T[(pr * H + kl + 4) * kTS + 8 * tj + lr];
+      dmma884(c0, c1, a0, b0);
+      dmma884(d0, d1, a1, b1);
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-#pragma unroll
-      for (int f = 0; f < 4; ++f)        // X[r][c], r > c, lives at a[c][r]
-        a[(base + tj + TT * f) * kPad + base + H + 4 * ti + e] = -acc[e][f];
+    // X21[r][c] (r in the second half, c in the first) lives at a[c][r]
+    const int cc = base + 8 * tj + 2 * lk;
+    a[cc * kPad + row] = -(c0 + d0);
+    a[(cc + 1) * kPad + row] = -(c1 + d1);
   }
   __syncthreads();
 }
