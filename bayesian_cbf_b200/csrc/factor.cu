@@ -272,12 +272,16 @@ potf2_inv_kernel(double* __restrict__ A_, int ld, int k0, const double* __restri
     }
     __syncthreads();
   }
-  for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
-    int r = idx >> 7, c = idx & 127;
-    double l = (c <= r) ? a[r * kPad + c] : 0.0;
-    double x = (c < r) ? a[c * kPad + r] : (c == r ? xd[r] : 0.0);
-    A[(long long)(k0 + r) * ld + (k0 + c)] = l;
-    dinv[idx] = x;
+#pragma unroll 4
+  for (int idx2 = tid; idx2 < kBlk * kBlk / 2; idx2 += 256) {      // two columns per thread: 16-byte stores
+    const int r = idx2 >> 6, c = (idx2 & 63) * 2;
+    double2 l, x;
+    l.x = (c <= r) ? a[r * kPad + c] : 0.0;
+    l.y = (c + 1 <= r) ? a[r * kPad + c + 1] : 0.0;
+    x.x = (c < r) ? a[c * kPad + r] : (c == r ? xd[r] : 0.0);
+    x.y = (c + 1 < r) ? a[(c + 1) * kPad + r] : (c + 1 == r ? xd[r] : 0.0);
+    *reinterpret_cast<double2*>(A + (long long)(k0 + r) * ld + (k0 + c)) = l;
+    *reinterpret_cast<double2*>(dinv + r * kBlk + c) = x;
   }
 }
 
@@ -315,6 +319,7 @@ __device__ __forceinline__ void inv_level(double* __restrict__ a, const double* 
     const int row = base + H + 8 * ti + lr;  // A fragment: L21[row][k]
     const int col = base + 8 * tj + lr;      // B fragment: X11[k][col]
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll 4
     for (int k4 = 2 * tj; k4 < H / 4; k4 += 2) {
       const int ka = base + 4 * k4 + lk, kb = ka + 4;
       const double a0 = a[row * kPad + ka], a1 = a[row * kPad + kb];
@@ -333,6 +338,7 @@ __device__ __forceinline__ void inv_level(double* __restrict__ a, const double* 
     const int base = pr * 2 * H;
     const int row = base + H + 8 * ti + lr;  // A fragment: X22[row][k], stored at a[k][row] for row > k
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll 4
     for (int k4 = 0; k4 < 2 * (ti + 1); k4 += 2) {
       const int kl = 4 * k4 + lk;            // k inside the pair's second half
       const int ka = base + H + kl, kb = ka + 4;
@@ -549,12 +555,16 @@ potf2_inv2_kernel(double* __restrict__ A_, int ld, int k0, const double* __restr
   inv_level<32>(a, xd, T, tid);
   inv_level<64>(a, xd, T, tid);
 
-  for (int idx = tid; idx < kBlk * kBlk; idx += 256) {
-    int r = idx >> 7, c = idx & 127;
-    double l = (c <= r) ? a[r * kPad + c] : 0.0;
-    double x = (c < r) ? a[c * kPad + r] : (c == r ? xd[r] : 0.0);
-    A[(long long)(k0 + r) * ld + (k0 + c)] = l;
-    dinv[idx] = x;
+#pragma unroll 4
+  for (int idx2 = tid; idx2 < kBlk * kBlk / 2; idx2 += 256) {      // two columns per thread: 16-byte stores
+    const int r = idx2 >> 6, c = (idx2 & 63) * 2;
+    double2 l, x;
+    l.x = (c <= r) ? a[r * kPad + c] : 0.0;
+    l.y = (c + 1 <= r) ? a[r * kPad + c + 1] : 0.0;
+    x.x = (c < r) ? a[c * kPad + r] : (c == r ? xd[r] : 0.0);
+    x.y = (c + 1 < r) ? a[(c + 1) * kPad + r] : (c + 1 == r ? xd[r] : 0.0);
+    *reinterpret_cast<double2*>(A + (long long)(k0 + r) * ld + (k0 + c)) = l;
+    *reinterpret_cast<double2*>(dinv + r * kBlk + c) = x;
   }
 }
 
