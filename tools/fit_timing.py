@@ -28,13 +28,18 @@ def main():
         reg.model.double()
         reg.fit(X, U, Xdot, training_iter=3, lr=0.01)
         torch.cuda.synchronize()
-        iters = 20 if N <= 1024 else 5
-        t0 = time.perf_counter()
-        reg.fit(X, U, Xdot, training_iter=iters, lr=0.01)
-        torch.cuda.synchronize()
-        ms = 1e3 * (time.perf_counter() - t0) / iters
-        rec = dict(N=N, ms_per_adam_iteration=ms, cpu_reference_ms=CPU_REF_MS.get(N),
+        iters = 50 if N <= 1024 else 5      # 50 = the reference's default training_iter (control_affine_model.py:274)
+
+        def timed(**kw):
+            t0 = time.perf_counter()
+            reg.fit(X, U, Xdot, training_iter=iters, lr=0.01, **kw)
+            torch.cuda.synchronize()
+            return 1e3 * (time.perf_counter() - t0) / iters
+        ms = timed()                        # default policy: captured iteration when Npad <= 1024 (capture cost included)
+        rec = dict(N=N, iterations=iters, ms_per_adam_iteration=ms, cpu_reference_ms=CPU_REF_MS.get(N),
                    speedup_vs_cpu_reference=(CPU_REF_MS[N] / ms) if N in CPU_REF_MS else None)
+        if N <= 1024:
+            rec['ms_per_adam_iteration_eager'] = timed(cuda_graph=False)
         print(json.dumps(rec), flush=True)
         out.append(rec)
 
