@@ -128,6 +128,7 @@ _SIGNATURES = {
     'bcbf_set_gemm_tile_policy': (c_int, [c_int]),
     'bcbf_oz_set_cluster': (c_int, [c_int]),
     'bcbf_oz_set_group': (c_int, [c_int]),
+    'bcbf_oz_debug_skip_loads': (c_int, [c_int]),
     'bcbf_oz_profile_enable': (c_int, [c_int]),
     'bcbf_oz_profile_read': (c_int, [POINTER(c_double), POINTER(c_int)]),
     'bcbf_model_set_var_path': (c_int, [c_void_p, c_int]),

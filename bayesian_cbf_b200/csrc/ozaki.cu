@@ -240,6 +240,7 @@ struct VarArgs {
   int Qpad;
   long long total_tiles;  // work items: group ceil(nb / group) nJg
   int group;              // row blocks per scheduling group (see tile_of)
+  int skip;               // development aid (bcbf_oz_debug_skip_loads): bit 0 / 1 = do not copy the A / B digits (results void)
   unsigned long long* dbg;
 };
 
@@ -337,6 +338,15 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
             mbar_wait(&empty[stage], phase ^ 1u);
           }
           uint8_t* dst = smem + stage * STAGE;
+          if (CL == 1 && (a.skip & 3) != 0) {   // timing experiment: how much of a K step is the incoming copies' share of the port
+            const uint32_t tx = ((a.skip & 1) ? 0 : A_STEP) + ((a.skip & 2) ? 0 : B_STEP);
+            if (tx == 0) mbar_arrive(&full[stage]);
+            else mbar_arrive_expect_tx(&full[stage], tx);
+            if (!(a.skip & 1)) bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
+            if (!(a.skip & 2)) bulk_g2s(dst + A_STEP, bp + (long long)ks * B_STEP, B_STEP, &full[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full[stage], STAGE);
           if (CL == 1) {
             bulk_g2s(dst, ap + (long long)ks * A_STEP, A_STEP, &full[stage]);
@@ -414,6 +424,12 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(tmem_full, tile_iter & 1u);
       tc_fence_after();
+      if (a.skip & 8) {   // timing experiment: no drain at all
+        tc_fence_before();
+        mbar_arrive(tmem_empty);
+        ++tile_iter;
+        continue;
+      }
       double V[TN];
 #pragma unroll
       for (int c = 0; c < TN; ++c) V[c] = 0.0;
@@ -432,6 +448,11 @@ __global__ void __launch_bounds__(kThreads, 1) oz_var_kernel(VarArgs a) {
       }
       tc_fence_before();
       mbar_arrive(tmem_empty);  // accumulators are in registers: the next tile's MMAs may start
+      if (a.skip & 4) {   // timing experiment: drain only, no FP64 recombination / Gram products
+        if (V[0] == 1.2345e-300) a.Spart[0] = V[1];   // keeps the loads alive
+        ++tile_iter;
+        continue;
+      }
       const double rs = a.rowscale[(long long)I * TM + warp * 32 + lane];
 #pragma unroll
       for (int c = 0; c < TN; ++c) V[c] *= rs * cs[c];
@@ -513,6 +534,7 @@ static unsigned long long* g_dbg = nullptr;
 
 static int g_cluster = 1;  // CTAs per cluster of oz_var_kernel (1, 2 or 4); bcbf_oz_set_cluster
 static int g_group = 4;    // row blocks per scheduling group of oz_var_kernel; bcbf_oz_set_group
+static int g_skip = 0;     // bcbf_oz_debug_skip_loads
 
 template <int P, int CL, int SD>
 static int launch_var(VarArgs a, cudaStream_t stream) {
@@ -610,6 +632,7 @@ static int run_blocks(const int8_t* Ablob, const double* rowscale, int Npad, con
   a.nJg = nJg;
   a.Qpad = Qpad;
   a.group = g_group;
+  a.skip = g_skip;
   a.total_tiles = (long long)ceil_div(nb, g_group) * g_group * nJg;
   a.dbg = g_dbg;
   rc = CL == 4   ? launch_var<P, 4, SD>(a, stream)
@@ -1276,6 +1299,15 @@ extern "C" int bcbf_posterior_var_i8(const void* digits, const double* rowscale,
 // Pipeline counters of oz_var_kernel (development aid; adds clock64 reads while enabled): out[0] cycles of the MMA
 // issue thread summed over CTAs, [1] of which waiting for operand stages, [2] waiting for the epilogue to drain TMEM,
 // [3] producer cycles waiting for a free stage, [4] K steps issued.
+// Development aid: oz_var_kernel stops copying the A (bit 0) and / or B (bit 1) digits into shared memory — the MMAs run on
+// whatever the stages hold, results are void — to measure what the incoming copies cost the MMA pipeline (tools/oz_sweep.py);
+// bit 2: the epilogue drains the accumulators but skips its FP64 work, bit 3: it does not even drain them.
+extern "C" int bcbf_oz_debug_skip_loads(int mask) {
+  BCBF_REQUIRE(mask >= 0 && mask <= 15, "bcbf_oz_debug_skip_loads: mask %d not in 0..15", mask);
+  oz::g_skip = mask;
+  return BCBF_OK;
+}
+
 extern "C" int bcbf_oz_debug_counters(int enable, unsigned long long out[8]) {
   if (out != nullptr && oz::g_dbg != nullptr) {
     BCBF_CUDA(cudaDeviceSynchronize());

@@ -268,6 +268,9 @@ int bcbf_oz_set_cluster(int ctas);
 int bcbf_oz_set_group(int row_blocks);
 /* Development aid: pipeline counters of oz_var_kernel (see csrc/ozaki.cu). */
 int bcbf_oz_debug_counters(int enable, unsigned long long out[8]);
+/* Development aid (timing experiments only; results are void while set): oz_var_kernel skips the shared-memory copies of
+ * the L^-1 digits (bit 0) and / or the frakB digits (bit 1).  0 restores normal operation.                              */
+int bcbf_oz_debug_skip_loads(int mask);
 /* General FP64-accurate GEMM on the int8 tensor cores (same digit splitting; csrc/ozaki.cu: oz_gemm_kernel):
  *   C (M,N; ldc) = alpha * A (M,K; lda) * B (K,N; ldb),  row-major, M % 128 == 0, N % 64 == 0, K % 32 == 0, K <= bcbf_oz_max_npad();
  *   tri = 0, or 1: A is square lower triangular (its strictly upper storage is not read), or 2: B is square lower triangular.
