@@ -353,11 +353,15 @@ def run_ours(args):
     launches0 = lib.bcbf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    # cudaProfilerStart/Stop bracket exactly the timed region: `ncu --profile-from-start off` then lists its launches
+    # only (profiles/*_ncu_launches_bench.csv); without a profiler attached the two calls do nothing
+    torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for i in range(W, W + K):
         outs = step(i)
     e1.record()
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
